@@ -1,0 +1,93 @@
+"""Automatic MPO construction -- restates
+/root/reference/src/structures/mps/mpo.jl:323-472 (``MPO(st, H)`` + ``expand``).
+
+MPO site tensor layout (w_l, out, in, w_r).  The builder starts from the
+2x2 "identity ladder", adds on-site terms to the top-right corner, routes every
+longer-range term through fresh bond channels, then compresses with a
+right-going and a left-going truncated-SVD sweep (cutoff 1e-15)."""
+import numpy as np
+from .tensors import svd
+from .gmps import GMPS
+
+
+def _expand(O, D1, D2):
+    """mpo.jl:463-471."""
+    d0, d1, d2, d3 = O.shape
+    new = np.zeros((d0 + D1, d1, d2, d3 + D2), dtype=np.complex128)
+    k = 1 if d0 == 1 else d0 - 1
+    new[:k, :, :, :d3 - 1] = O[:k, :, :, :d3 - 1]
+    new[:k, :, :, -1] = O[:k, :, :, -1]
+    new[d0 + D1 - 1, :, :, d3 + D2 - 1] = O[d0 - 1, :, :, d3 - 1]
+    return new
+
+
+def MPO(st, H, cutoff=1e-15, maxdim=0, mindim=1):
+    N, d = len(H), st.dim
+    ident = st.op("id")
+    ten = np.zeros((2, d, d, 2), dtype=np.complex128)
+    ten[0, :, :, 0] = ident
+    ten[1, :, :, 1] = ident
+    O = GMPS.zeros(2, d, N)
+    O[1] = ten[0:1, :, :, 0:2].copy()
+    for i in range(2, N):
+        O[i] = ten.copy()
+    O[N] = ten[0:2, :, :, 1:2].copy()
+
+    maxrng = H.siterange()
+    rngs = [[] for _ in range(maxrng)]
+    for i in range(len(H.ops)):
+        rngs[H.sites[i][-1] - H.sites[i][0]].append(i)
+
+    for rng in range(1, maxrng + 1):  # mpo.jl:354
+        nextterms = [[] for _ in range(rng)]
+        coeffs = [[] for _ in range(rng)]
+        ingoings = [[] for _ in range(rng)]
+        outgoings = [[] for _ in range(rng)]
+        for site in range(1, N + 1):
+            idxs = [j for j in rngs[rng - 1] if H.sites[j][0] == site]
+            if rng == 1:  # mpo.jl:370-374
+                for idx in idxs:
+                    O[site][0, :, :, -1] += H.coeffs[idx] * st.op(H.ops[idx][0])
+                continue
+            for idx in idxs:  # mpo.jl:377-403
+                ops, sites = H.ops[idx], H.sites[idx]
+                outgoing = 0
+                for k in range(1, rng + 1):
+                    ingoing = outgoing
+                    for l in range(1, len(outgoings[k - 1]) + 2):
+                        outgoing = l
+                        if outgoing not in outgoings[k - 1]:
+                            break
+                    if k == rng:
+                        outgoing = 0
+                    s = site + k - 1
+                    opname = ops[sites.index(s)] if s in sites else "id"
+                    nextterms[k - 1].append(opname)
+                    coeffs[k - 1].append(H.coeffs[idx] if k == 1 else 1)
+                    ingoings[k - 1].append(ingoing)
+                    outgoings[k - 1].append(outgoing)
+            terms, ins, outs, cos = nextterms[0], ingoings[0], outgoings[0], coeffs[0]  # mpo.jl:406-419
+            nextterms = nextterms[1:] + [[]]
+            ingoings = ingoings[1:] + [[]]
+            outgoings = outgoings[1:] + [[]]
+            coeffs = coeffs[1:] + [[]]
+            if terms:  # mpo.jl:422-437
+                ingoinglen = sum(1 for x in ins if x != 0)
+                outgoinglen = sum(1 for x in outs if x != 0)
+                ingoingsrt = O[site].shape[0] - 1
+                outgoingsrt = O[site].shape[3] - 1
+                O[site] = _expand(O[site], ingoinglen, outgoinglen)
+                for j in range(len(terms)):
+                    x = 1 if ins[j] == 0 else ingoingsrt + ins[j]
+                    y = outgoingsrt + 1 + outgoinglen if outs[j] == 0 else outgoingsrt + outs[j]
+                    O[site][x - 1, :, :, y - 1] = cos[j] * st.op(terms[j])
+
+    for site in range(1, N):  # mpo.jl:443-449
+        U, S, V = svd(O[site], 4, cutoff=cutoff, maxdim=maxdim, mindim=mindim)
+        O[site] = np.tensordot(U, S, axes=([3], [0]))
+        O[site + 1] = np.tensordot(V, O[site + 1], axes=([1], [0]))
+    for site in range(N, 1, -1):  # mpo.jl:451-457
+        U, S, V = svd(O[site], 1, cutoff=cutoff, maxdim=maxdim, mindim=mindim)
+        O[site] = np.tensordot(S, U, axes=([1], [0]))
+        O[site - 1] = np.tensordot(O[site - 1], V, axes=([3], [1]))
+    return O

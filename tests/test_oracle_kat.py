@@ -1,0 +1,127 @@
+"""Tier-2 oracle known-answer tests: the restated algorithms reproduce exact-
+diagonalisation energies to the north_star
+tolerance (1e-10 relative), and the MPO builder reproduces the dense operator."""
+import numpy as np
+import pytest
+
+import oracle
+from models import tfim, xxz, j1j2_cylinder, dense_hamiltonian, ed_ground_energy, mps_to_dense, KAT
+
+
+def mpo_to_dense(M):
+    t = M[1]
+    for i in range(2, len(M) + 1):
+        t = np.tensordot(t, M[i], axes=([t.ndim - 1], [0]))
+    t = t[0, ..., 0]
+    N = len(M)
+    outs = list(range(0, 2 * N, 2))
+    ins = list(range(1, 2 * N, 2))
+    t = np.transpose(t, outs + ins)
+    return t.reshape(2 ** N, 2 ** N)
+
+
+@pytest.mark.parametrize("name,H", [("tfim", tfim(6)), ("xxz", xxz(6, 0.5)), ("j1j2", j1j2_cylinder(2, 3))])
+def test_mpo_builder_matches_dense(name, H):
+    sh = oracle.spinhalf()
+    M = oracle.MPO(sh, H)
+    assert np.allclose(mpo_to_dense(M), dense_hamiltonian(sh, H).toarray(), atol=1e-12)
+
+
+def test_ed_table_is_reproduced_by_independent_ed():
+    sh = oracle.spinhalf()
+    assert np.isclose(ed_ground_energy(sh, tfim(8)), KAT[("tfim", 8)], rtol=0, atol=1e-10)
+    assert np.isclose(ed_ground_energy(sh, xxz(8, 1.0)), KAT[("heis", 8)], rtol=0, atol=1e-10)
+    assert np.isclose(ed_ground_energy(sh, xxz(10, 0.5)), KAT[("xxz0.5", 10)], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("key,H", [
+    (("tfim", 8), tfim(8)), (("tfim", 10), tfim(10)),
+    (("heis", 8), xxz(8, 1.0)), (("heis", 10), xxz(10, 1.0)),
+    (("xxz0.5", 10), xxz(10, 0.5)),
+    (("j1j2_4x3", 12), j1j2_cylinder(4, 3)),
+])
+def test_dmrg_reaches_ed_energy(key, H):
+    sh = oracle.spinhalf()
+    M = oracle.MPO(sh, H)
+    psi = oracle.randomMPS(2, len(H), 4, np.random.default_rng(1234))
+    psi, E = oracle.dmrg(psi, M, maxdim=64, cutoff=1e-14, maxsweeps=30)
+    assert abs((np.real(E) - KAT[key]) / KAT[key]) < 1e-10
+    # energy returned by the eigensolver == <psi|H|psi>
+    v = mps_to_dense(psi)
+    assert np.isclose(np.real(np.vdot(v, dense_hamiltonian(sh, H) @ v)), KAT[key], rtol=1e-10)
+
+
+def test_dmrg_optimal_order_same_energy():
+    sh = oracle.spinhalf()
+    H = tfim(10)
+    M = oracle.MPO(sh, H)
+    hist_a, hist_b = [], []
+    pa = oracle.randomMPS(2, 10, 2, np.random.default_rng(5))
+    pb = pa.copy()
+    oracle.dmrg(pa, M, maxdim=16, maxsweeps=4, history=hist_a)
+    oracle.dmrg(pb, M, maxdim=16, maxsweeps=4, history=hist_b, optimal_order=True)
+    for a, b in zip(hist_a, hist_b):
+        assert abs(a[1] - b[1]) < 1e-10 * abs(a[1]) and a[2] == b[2]
+
+
+def test_tebd_imaginary_time_converges_to_ground_state():
+    sh = oracle.spinhalf()
+    N = 8
+    H = tfim(N, 1.0, 0.0, 0.5)          # paramagnetic: gap ~ 1, converges within T = 8
+    E0 = ed_ground_energy(sh, H)
+    psi = oracle.randomMPS(2, N, 8, np.random.default_rng(11))
+    dt = 0.01
+    psi, E = oracle.tebd(sh, psi, -1 * H, dt, 8.0, 1.0, cutoff=1e-12, maxdim=16)
+    # tebd evolves with exp(+dt*(-H)); the energy it reports is <-H> (tebd.jl:90)
+    assert abs(-E - E0) < 2e-4           # second-order Trotter error at dt = 0.01
+
+
+def test_qjmc_matches_dense_state_trajectory():
+    """Same Trotter gates + same uniforms applied to a dense state vector give the
+    same jump record and <z_i>: checks gate application, truncation-free SVD
+    splitting, emission rates and the jump update in one go (N small, no truncation)."""
+    sh = oracle.spinhalf()
+    N, dt, steps = 5, 0.05, 60
+    H = tfim(N, 1.0, 0.3, 0.7)
+    J = oracle.OpList(N)
+    for i in range(1, N + 1):
+        J.add("s-", i, np.sqrt(0.8))
+    u = np.random.default_rng(3).random(3 * steps + 8)
+    it = iter(u)
+    psi = oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)])
+    psi.movecenter(1)
+    zs = oracle.OpList(N)
+    for i in range(1, N + 1):
+        zs.add("z", i)
+    ob = oracle.qjmc.QJMCOperators(zs, sh)
+    jumps, times = oracle.qjmc_simulation(sh, psi, H, J, steps * dt, dt, [ob], uniforms=lambda: next(it), cutoff=0, maxdim=0)
+
+    # dense replay
+    _, gates = oracle.qjmc_gates(sh, H, J, dt)
+    it = iter(u)
+    v = mps_to_dense(oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)])).reshape((2,) * N)
+
+    def apply(v, g, site):
+        n = g.ndim // 2
+        gm = np.transpose(g, [2 * k for k in range(n)] + [2 * k + 1 for k in range(n)])  # (outs..., ins...)
+        v = np.tensordot(gm, v, axes=(list(range(n, 2 * n)), list(range(site - 1, site - 1 + n))))
+        return np.moveaxis(v, list(range(n)), list(range(site - 1, site - 1 + n)))
+    sm = sh.op("s-")
+    dj, dz = [], []
+    for step in range(steps):
+        for rs, rg in zip(gates.sites, gates.gates):
+            for s, g in zip(rs, rg):
+                v = apply(v, g, s)
+        next(it)
+        v = v / np.linalg.norm(v)
+        rates = np.array([0.8 * np.linalg.norm(apply(v, sm, s)) ** 2 for s in range(1, N + 1)])
+        if next(it) > np.exp(-rates.sum() * dt):
+            r = next(it)
+            k = int(np.nonzero(r < np.cumsum(rates) / rates.sum())[0][0])
+            v = apply(v, sm, k + 1)
+            v = v / np.linalg.norm(v)
+            dj.append(k + 1)
+        dz.append([np.real(np.vdot(v, apply(v, sh.op("z"), s))) for s in range(1, N + 1)])
+    assert jumps == dj and len(jumps) > 0
+    got = np.real(np.array(ob.measurements[1:]))
+    assert np.allclose(got, np.array(dz), atol=1e-8)
