@@ -1,0 +1,140 @@
+/* libtnb200 -- C ABI of the B200-native MPS hot path for TensorNetworks.jl.
+ *
+ * Every entry point is what a `ccall` from the reference's Julia code would bind for the hot path
+ * (INTEGRATION.md shows the Julia side).  Conventions:
+ *   - plain C: opaque handles, pointers and sizes; no C++/torch types.
+ *   - complex data are interleaved (re, im) doubles, COLUMN-MAJOR, exactly a Julia Array{ComplexF64}
+ *     / NumPy complex128 order='F'; `tn_cplx` is layout-compatible with `double _Complex`.
+ *   - site / block indices are 1-based like the reference.
+ *   - host buffers are borrowed for the duration of the call only; device memory is owned by the library
+ *     and stays resident in HBM between calls.
+ *   - every function returns 0 on success, a negative status otherwise; tn_last_error() gives the
+ *     message (thread-local), which the Julia shim turns into error("...") like the reference does.
+ *   - a tn_ctx is bound to one GPU and one CUDA stream and is not re-entrant across threads.
+ * All paths below are relative to /root/reference/src.
+ */
+#ifndef TN_C_API_H
+#define TN_C_API_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } tn_cplx;
+typedef struct tn_ctx tn_ctx;
+typedef struct tn_mps tn_mps;     /* GMPS of rank 1 (MPS) or 2 (MPO): structures/mps/gmps.jl:8-13 */
+typedef struct tn_env tn_env;     /* ProjMPS: structures/mps/projmps.jl:1-8 */
+typedef struct tn_gates tn_gates; /* GateList: structures/mps/gatelist.jl:8-13 */
+
+/* kwargs of svd(): tensors.jl:170-172 (cutoff=0, maxdim=0 meaning unlimited, mindim=1) */
+typedef struct { double cutoff; int64_t maxdim; int64_t mindim; } tn_trunc_t;
+/* kwargs of KrylovKit.eigsolve as passed at algorithms/mps/dmrg.jl:51-53 */
+typedef struct { int32_t krylovdim; int32_t maxiter; double tol; } tn_lanczos_t;
+
+#define TN_OK 0
+#define TN_ERR_INVALID (-1)   /* argument / shape error (the reference's error("...")) */
+#define TN_ERR_CUDA (-2)
+#define TN_ERR_INTERNAL (-3)
+
+const char* tn_last_error(void);
+int32_t tn_version(void);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int32_t tn_ctx_create(int32_t device, tn_ctx** out);
+int32_t tn_ctx_destroy(tn_ctx* ctx);
+int32_t tn_sync(tn_ctx* ctx);
+/* CUDA stream handle (cudaStream_t) the context launches on, for event timing by the caller */
+int32_t tn_ctx_stream(tn_ctx* ctx, void** stream_out);
+/* counters: kernels launched by this library (process-wide), matvecs and SVDs done by this ctx */
+int32_t tn_counters(tn_ctx* ctx, int64_t* launches, int64_t* matvecs, int64_t* svds);
+
+/* ---- GMPS container: structures/mps/gmps.jl, abstractmps.jl ---------------------------------- */
+/* dims: N x (rank+2) row-major table of site tensor sizes; site_ptrs[i]: host tensor of site i+1 */
+int32_t tn_mps_upload(tn_ctx* ctx, int32_t rank, int32_t d, int32_t N, const int64_t* dims,
+                      const tn_cplx* const* site_ptrs, int32_t center, tn_mps** out);
+int32_t tn_mps_free(tn_mps* m);
+int32_t tn_mps_info(tn_mps* m, int32_t* rank, int32_t* d, int32_t* N, int32_t* center);
+int32_t tn_mps_dims(tn_mps* m, int64_t* dims /* N x (rank+2) */);
+int32_t tn_mps_download_site(tn_mps* m, int32_t site, tn_cplx* out);
+int32_t tn_mps_upload_site(tn_mps* m, int32_t site, const int64_t* dims, const tn_cplx* data);
+int32_t tn_mps_set_center(tn_mps* m, int32_t center);
+int32_t tn_mps_maxbonddim(tn_mps* m, int64_t* out);                       /* abstractmps.jl:71-77 */
+int32_t tn_mps_norm(tn_mps* m, tn_cplx* out);                             /* gmps.jl:29-37 */
+int32_t tn_mps_normalize(tn_mps* m);                                      /* gmps.jl:46-51 */
+int32_t tn_mps_movecenter(tn_mps* m, int32_t idx, tn_trunc_t trunc);      /* gmps.jl:90-112 (+ :60-82) */
+/* replacesites!(psi, A, site, direction, normalize; kwargs) for a two-site tensor: gmps.jl:199-267 */
+int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta_host, int32_t site, int32_t direction,
+                            int32_t normalize, tn_trunc_t trunc);
+int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op_host /* d x d */);   /* mps.jl:141-152 */
+/* singular values across bond (site, site+1) -- the SVD inside entropy(): gmps.jl:184-189 */
+int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out);
+/* <psi| O_k |psi> for single-site operators: mps.jl:87-134 (one-site terms), qjmc.jl:170-220 */
+int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_cplx* ops_host, tn_cplx* out);
+
+/* ---- truncated SVD: tensors.jl:168-227 -------------------------------------------------------- */
+/* mat: m x n column-major on the host.  U: m x k, S: k, Vh: k x n written to the host buffers, which
+ * must hold min(m,n) columns / rows (the rank is only known afterwards). */
+int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t trunc,
+                     tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
+
+/* ---- contraction: tensors.jl:9-18 restricted to the strided-GEMM form the hot path uses ------- */
+/* C[m,n] = alpha * sum_k op(A)[m,k] op(B)[k,n]; each of m, n, k is a fused pair of tensor indices
+ * (extent n0 x rest) with element strides (s0, s1); conj flags as the reference's conjx/conjy. */
+typedef struct { int64_t n0, s0, s1; } tn_idx2_t;
+int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K,
+                            const tn_cplx* A, int64_t a_elems, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
+                            const tn_cplx* B, int64_t b_elems, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB,
+                            tn_cplx* C, int64_t c_elems, tn_idx2_t cm, tn_idx2_t cn, tn_cplx alpha);
+
+/* ---- projected environments: structures/mps/projmps.jl, abstractprojmps.jl -------------------- */
+/* ProjMPS(bra, mpo, ket; rank=2, coeff, center): projmps.jl:16-42.  mpo may be NULL (overlap <bra|ket>). */
+int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cplx coeff, int32_t center, tn_env** out);
+int32_t tn_env_free(tn_env* e);
+int32_t tn_env_buildleft(tn_env* e, int32_t idx);       /* projmps.jl:50-66 */
+int32_t tn_env_buildright(tn_env* e, int32_t idx);      /* projmps.jl:74-95 */
+int32_t tn_env_movecenter(tn_env* e, int32_t idx);      /* abstractprojmps.jl:60-81 */
+int32_t tn_env_center(tn_env* e, int32_t* out);
+int32_t tn_env_block_dims(tn_env* e, int32_t idx, int64_t* dims3);   /* (chi_bra, w, chi_ket) */
+int32_t tn_env_block_download(tn_env* e, int32_t idx, tn_cplx* out); /* block(projV, idx): abstractprojmps.jl:43-46 */
+/* product(projV, A, direction, nsites=2): projmps.jl:103-145 rank-2 branch.  theta / out on the HOST,
+ * shape (chi_l, d, d, chi_r) of sites (site, site+1) with site = direction ? center-1 : center. */
+int32_t tn_env_product(tn_env* e, const tn_cplx* theta_host, int32_t direction, tn_cplx* out_host);
+/* same with DEVICE buffers (no PCIe traffic), `reps` back-to-back applications (reps >= 1) */
+int32_t tn_env_product_dev(tn_env* e, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps);
+int32_t tn_env_calculate(tn_env* e, tn_cplx* out);      /* projmps.jl:192-216 */
+
+/* ---- fused steps (what the drivers call) ------------------------------------------------------ */
+/* One direction of a two-site DMRG sweep, algorithms/mps/dmrg.jl:35-63: for every bond movecenter!(Hs),
+ * theta = psi[s]*psi[s+1], eigsolve (Lanczos, KrylovKit schedule), replacesites!(..., normalize=true);
+ * then movecenter!(Hs, end).  direction 0 = left-to-right.  Returns the last Ritz value and maxbonddim. */
+int32_t tn_dmrg_sweep(tn_mps* psi, tn_env* env, int32_t direction, tn_lanczos_t lanczos, tn_trunc_t trunc,
+                      double* energy_out, int64_t* maxbond_out);
+/* eigsolve alone on the two sites at the environment centre (host theta in/out); numops = H_eff applications */
+int32_t tn_eigsolve(tn_env* e, const tn_cplx* theta0_host, int32_t direction, tn_lanczos_t lanczos,
+                    double* eig_out, tn_cplx* theta_out_host, int32_t* numops_out);
+
+/* GateList upload: nrows rows; counts[r] gates in row r; per gate (flattened in row order) the first
+ * site, the number of sites (1 or 2) and a host pointer to the gate tensor (out1,in1[,out2,in2]),
+ * column-major, as produced by trotterize(): gatelist.jl:75-121. */
+int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* counts, const int32_t* sites,
+                        const int32_t* nsites, const tn_cplx* const* gate_ptrs, tn_gates** out);
+int32_t tn_gates_free(tn_gates* g);
+/* applygates!(psi, gates; cutoff, maxdim, mindim): gatelist.jl:191-227 (MPS rank 1 or MPO rank 2) */
+int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc);
+
+/* One QJMC trajectory, algorithms/mps/qjmc.jl:59-164 (classical=true branch): per step applygates!,
+ * normalize!, emission rates (single-site jump operators jump_ops[k] d x d at jump_sites[k], rates scaled by
+ * jump_coeffs[k]^2), jump test and jump update.  uniforms: 3 per step (host) or NULL for the built-in
+ * counter-based generator keyed by (seed, trajectory, step).  Observables: <obs_op> on every site is
+ * written to obs_out[(step/save_every - 1) * N + i] every save_every steps (obs_op may be NULL).
+ * jumps_out / jumptimes_out: up to jump_cap records (1-based channel index, time). */
+int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
+                    const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t trunc, const double* uniforms,
+                    uint64_t seed, uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out,
+                    int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TN_C_API_H */

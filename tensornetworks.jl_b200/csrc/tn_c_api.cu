@@ -1,0 +1,296 @@
+// extern "C" boundary of libtnb200 (declared in include/tn_c_api.h).
+#include "../../include/tn_c_api.h"
+#include "tn_mps.cuh"
+#include <cstring>
+
+namespace tn {
+int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,
+             int steps, double dt, Trunc tr, const double* uniforms, uint64_t seed, uint64_t traj,
+             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap);
+}
+
+using namespace tn;
+
+struct tn_ctx { Ctx c; };
+struct tn_mps { Mps* m; };
+struct tn_env { Env* e; };
+struct tn_gates { Gates* g; };
+
+static thread_local std::string g_err;
+
+template <class F>
+static int32_t guard(F&& f) {
+  try { f(); return TN_OK; }
+  catch (const tn::Error& e) { g_err = e.what(); return e.code; }
+  catch (const std::exception& e) { g_err = e.what(); return TN_ERR_INTERNAL; }
+  catch (...) { g_err = "unknown error"; return TN_ERR_INTERNAL; }
+}
+static inline const cplx* C(const tn_cplx* p) { return reinterpret_cast<const cplx*>(p); }
+static inline cplx* C(tn_cplx* p) { return reinterpret_cast<cplx*>(p); }
+static inline Trunc T(tn_trunc_t t) { return Trunc{t.cutoff, (long long)t.maxdim, (long long)t.mindim}; }
+
+extern "C" {
+
+const char* tn_last_error(void) { return g_err.c_str(); }
+int32_t tn_version(void) { return 100; }
+
+int32_t tn_ctx_create(int32_t device, tn_ctx** out) {
+  return guard([&] {
+    TN_CHECK(out != nullptr, "null output pointer");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) throw tn::Error(TN_ERR_CUDA, "no CUDA device available: libtnb200 has no CPU fallback");
+    TN_CHECK(device >= 0 && device < ndev, "device index out of range");
+    TN_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop; TN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw tn::Error(TN_ERR_CUDA, std::string("libtnb200 is built for sm_100a (B200) only; found ") + prop.name);
+    auto* c = new tn_ctx();
+    c->c.device = device;
+    TN_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
+    cudaMemPool_t pool; TN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX; TN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    TN_CUDA(cudaMalloc((void**)&c->c.dscal, 64 * sizeof(cplx)));
+    TN_CUDA(cudaMemset(c->c.dscal, 0, 64 * sizeof(cplx)));
+    TN_CUDA(cudaMallocHost((void**)&c->c.hscal, 64 * sizeof(cplx)));
+    TN_CUDA(cudaMalloc((void**)&c->c.partials, 4 * (DOT_BLOCKS + 8) * sizeof(cplx)));
+    *out = c;
+  });
+}
+int32_t tn_ctx_destroy(tn_ctx* ctx) {
+  return guard([&] {
+    if (!ctx) return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    svd_free(ctx->c.svd);
+    for (auto& b : ctx->c.scratch) b.release();
+    cudaFree(ctx->c.dscal); cudaFreeHost(ctx->c.hscal); cudaFree(ctx->c.partials);
+    cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+  });
+}
+int32_t tn_sync(tn_ctx* ctx) { return guard([&] { ctx->c.sync(); }); }
+int32_t tn_ctx_stream(tn_ctx* ctx, void** s) { return guard([&] { *s = (void*)ctx->c.stream; }); }
+int32_t tn_counters(tn_ctx* ctx, int64_t* launches, int64_t* matvecs, int64_t* svds) {
+  return guard([&] {
+    if (launches) *launches = zgemm_launch_count();
+    if (matvecs) *matvecs = ctx->c.matvecs;
+    if (svds) *svds = ctx->c.svds;
+  });
+}
+
+// ---- MPS ---------------------------------------------------------------------------------------
+int32_t tn_mps_upload(tn_ctx* ctx, int32_t rank, int32_t d, int32_t N, const int64_t* dims, const tn_cplx* const* site_ptrs,
+                      int32_t center, tn_mps** out) {
+  return guard([&] {
+    TN_CHECK(ctx && dims && site_ptrs && out, "null pointer");
+    TN_CHECK(center >= 0 && center <= N, "center out of range");
+    std::vector<long long> dd((size_t)N * (rank + 2));
+    for (size_t i = 0; i < dd.size(); ++i) dd[i] = dims[i];
+    auto* h = new tn_mps();
+    h->m = mps_create(&ctx->c, rank, d, N, dd.data(), reinterpret_cast<const cplx* const*>(site_ptrs), center);
+    *out = h;
+  });
+}
+int32_t tn_mps_free(tn_mps* m) { return guard([&] { if (m) { mps_free(m->m); delete m; } }); }
+int32_t tn_mps_info(tn_mps* m, int32_t* rank, int32_t* d, int32_t* N, int32_t* center) {
+  return guard([&] { if (rank) *rank = m->m->rank; if (d) *d = m->m->d; if (N) *N = m->m->N; if (center) *center = m->m->center; });
+}
+int32_t tn_mps_dims(tn_mps* m, int64_t* dims) {
+  return guard([&] {
+    int r = m->m->rank + 2;
+    for (int i = 0; i < m->m->N; ++i) for (int k = 0; k < r; ++k) dims[(size_t)i * r + k] = m->m->sites[i].dims[k];
+  });
+}
+int32_t tn_mps_download_site(tn_mps* m, int32_t site, tn_cplx* out) { return guard([&] { mps_download_site(m->m, site, C(out)); }); }
+int32_t tn_mps_upload_site(tn_mps* m, int32_t site, const int64_t* dims, const tn_cplx* data) {
+  return guard([&] { std::vector<long long> dd(dims, dims + m->m->rank + 2); mps_upload_site(m->m, site, dd.data(), C(data)); });
+}
+int32_t tn_mps_set_center(tn_mps* m, int32_t center) {
+  return guard([&] { TN_CHECK(center >= 0 && center <= m->m->N, "center out of range"); m->m->center = center; });
+}
+int32_t tn_mps_maxbonddim(tn_mps* m, int64_t* out) { return guard([&] { *out = m->m->maxbonddim(); }); }
+int32_t tn_mps_norm(tn_mps* m, tn_cplx* out) { return guard([&] { cplx v = mps_norm(m->m); out->re = v.x; out->im = v.y; }); }
+int32_t tn_mps_normalize(tn_mps* m) { return guard([&] { mps_normalize(m->m); }); }
+int32_t tn_mps_movecenter(tn_mps* m, int32_t idx, tn_trunc_t tr) { return guard([&] { mps_movecenter(m->m, idx, T(tr)); }); }
+int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta, int32_t site, int32_t direction, int32_t normalize, tn_trunc_t tr) {
+  return guard([&] {
+    Mps* p = m->m; Ctx* c = p->ctx;
+    TN_CHECK(site >= 1 && site + 1 <= p->N, "replacesites: site out of range");
+    long long n = p->chiL(site) * p->phys() * p->phys() * p->chiR(site + 1);
+    cplx* d = c->scratch[14].get((size_t)n, c->stream);
+    TN_CUDA(cudaMemcpyAsync(d, theta, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+    mps_replacesites2(p, d, site, direction != 0, normalize != 0, T(tr));
+    c->sync();
+  });
+}
+int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op) {
+  return guard([&] {
+    Mps* p = m->m; Ctx* c = p->ctx;
+    TN_CHECK(site >= 1 && site <= p->N, "site out of range");
+    cplx* d = c->scratch[15].get((size_t)p->d * p->d, c->stream);
+    TN_CUDA(cudaMemcpyAsync(d, op, (size_t)p->d * p->d * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+    mps_applyop1(p, site, d);
+  });
+}
+int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out) {
+  return guard([&] {
+    std::vector<double> s; mps_bond_spectrum(m->m, site, s);
+    TN_CHECK((int64_t)s.size() <= cap, "spectrum buffer too small");
+    std::memcpy(out, s.data(), s.size() * sizeof(double));
+    *k_out = (int64_t)s.size();
+  });
+}
+int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_cplx* ops, tn_cplx* out) {
+  return guard([&] { expect_local(m->m, nops, sites, C(ops), C(out)); });
+}
+
+// ---- SVD ---------------------------------------------------------------------------------------
+int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t tr, tn_cplx* U, double* S, tn_cplx* Vh,
+                     int64_t* k_out, int32_t* sweeps_out) {
+  return guard([&] {
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
+    cplx* dM = c->scratch[0].get((size_t)(m * n), s);
+    TN_CUDA(cudaMemcpyAsync(dM, mat, (size_t)(m * n) * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    int k = svd_factor(c->svd, dM, (int)m, (int)n, m, T(tr), s); c->svds++;
+    cplx* dU = c->scratch[1].get((size_t)(m * k), s);
+    cplx* dV = c->scratch[2].get((size_t)(k * n), s);
+    svd_gather_U(c->svd, dU, m, false, s);
+    svd_gather_Vh(c->svd, dV, k, false, s);
+    TN_CUDA(cudaMemcpyAsync(U, dU, (size_t)(m * k) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(Vh, dV, (size_t)(k * n) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(S, c->svd.sig, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    c->sync();
+    *k_out = k;
+    if (sweeps_out) *sweeps_out = c->svd.sweeps;
+  });
+}
+
+static Idx2 I2(tn_idx2_t i) { return Idx2{(int)std::min<int64_t>(i.n0, 0x7fffffff), (long long)i.s0, (long long)i.s1, nullptr, 0}; }
+
+int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const tn_cplx* A, int64_t ae, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
+                            const tn_cplx* B, int64_t be, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB, tn_cplx* Cc, int64_t ce,
+                            tn_idx2_t cm, tn_idx2_t cn, tn_cplx alpha) {
+  return guard([&] {
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    cplx* dA = c->scratch[0].get((size_t)ae, s);
+    cplx* dB = c->scratch[1].get((size_t)be, s);
+    cplx* dC = c->scratch[2].get((size_t)ce, s);
+    TN_CUDA(cudaMemcpyAsync(dA, A, (size_t)ae * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemcpyAsync(dB, B, (size_t)be * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemsetAsync(dC, 0, (size_t)ce * sizeof(cplx), s));
+    GemmDesc g{};
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.A = dA; g.am = I2(am); g.ak = I2(ak); g.conjA = conjA;
+    g.B = dB; g.bk = I2(bk); g.bn = I2(bn); g.conjB = conjB;
+    g.C = dC; g.cm = I2(cm); g.cn = I2(cn);
+    g.alpha = cplx{alpha.re, alpha.im}; g.beta = cplx{0, 0};
+    g.batch = 1; g.ksplit = 1; g.kchunk = (int)K;
+    zgemm_auto(g, s);
+    TN_CUDA(cudaMemcpyAsync(Cc, dC, (size_t)ce * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+  });
+}
+
+// ---- environments ------------------------------------------------------------------------------
+int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cplx coeff, int32_t center, tn_env** out) {
+  return guard([&] {
+    TN_CHECK(ctx && bra && ket && out, "null pointer");
+    auto* h = new tn_env();
+    h->e = env_create(&ctx->c, bra->m, mpo ? mpo->m : nullptr, ket->m, cplx{coeff.re, coeff.im}, center);
+    *out = h;
+  });
+}
+int32_t tn_env_free(tn_env* e) { return guard([&] { if (e) { env_free(e->e); delete e; } }); }
+int32_t tn_env_buildleft(tn_env* e, int32_t idx) { return guard([&] { env_buildleft(e->e, idx); }); }
+int32_t tn_env_buildright(tn_env* e, int32_t idx) { return guard([&] { env_buildright(e->e, idx); }); }
+int32_t tn_env_movecenter(tn_env* e, int32_t idx) { return guard([&] { env_movecenter(e->e, idx); }); }
+int32_t tn_env_center(tn_env* e, int32_t* out) { return guard([&] { *out = e->e->center; }); }
+int32_t tn_env_block_dims(tn_env* e, int32_t idx, int64_t* dims3) {
+  return guard([&] { const Tensor& t = env_block(e->e, idx); for (int k = 0; k < 3; ++k) dims3[k] = t.dims[k]; });
+}
+int32_t tn_env_block_download(tn_env* e, int32_t idx, tn_cplx* out) {
+  return guard([&] {
+    const Tensor& t = env_block(e->e, idx);
+    TN_CUDA(cudaMemcpyAsync(out, t.p, (size_t)t.size() * sizeof(cplx), cudaMemcpyDeviceToHost, e->e->ctx->stream));
+    e->e->ctx->sync();
+  });
+}
+static int product_site(Env* e, int direction) {   // projmps.jl:109
+  TN_CHECK(e->center >= 1, "the environment centre is not set");
+  int site = direction ? e->center - 1 : e->center;
+  TN_CHECK(site >= 1 && site + 1 <= e->ket->N, "product: the two sites fall outside the chain");
+  return site;
+}
+int32_t tn_env_product(tn_env* eh, const tn_cplx* theta, int32_t direction, tn_cplx* out) {
+  return guard([&] {
+    Env* e = eh->e; Ctx* c = e->ctx; cudaStream_t s = c->stream;
+    int site = product_site(e, direction);
+    long long n = e->ket->chiL(site) * e->ket->d * e->ket->d * e->ket->chiR(site + 1);
+    cplx* din = c->scratch[13].get((size_t)n, s);
+    cplx* dout = c->scratch[14].get((size_t)n, s);
+    TN_CUDA(cudaMemcpyAsync(din, theta, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    env_product_dev(e, din, site, dout);
+    TN_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+  });
+}
+int32_t tn_env_product_dev(tn_env* eh, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps) {
+  return guard([&] {
+    Env* e = eh->e;
+    int site = product_site(e, direction);
+    for (int r = 0; r < std::max(1, reps); ++r) env_product_dev(e, (const cplx*)theta_dev, site, (cplx*)out_dev);
+  });
+}
+int32_t tn_env_calculate(tn_env* e, tn_cplx* out) { return guard([&] { cplx v = env_calculate(e->e); out->re = v.x; out->im = v.y; }); }
+
+// ---- drivers -----------------------------------------------------------------------------------
+int32_t tn_dmrg_sweep(tn_mps* psi, tn_env* env, int32_t direction, tn_lanczos_t lz, tn_trunc_t tr, double* energy, int64_t* maxbond) {
+  return guard([&] {
+    long long mb = 0;
+    dmrg_halfsweep(psi->m, env->e, direction != 0, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, T(tr), energy, &mb);
+    psi->m->ctx->sync();
+    if (maxbond) *maxbond = mb;
+  });
+}
+int32_t tn_eigsolve(tn_env* eh, const tn_cplx* theta0, int32_t direction, tn_lanczos_t lz, double* eig, tn_cplx* theta_out, int32_t* numops) {
+  return guard([&] {
+    Env* e = eh->e; Ctx* c = e->ctx; cudaStream_t s = c->stream;
+    int site = product_site(e, direction);
+    long long n = e->ket->chiL(site) * e->ket->d * e->ket->d * e->ket->chiR(site + 1);
+    cplx* din = c->scratch[13].get((size_t)n, s);
+    cplx* dout = c->scratch[14].get((size_t)n, s);
+    TN_CUDA(cudaMemcpyAsync(din, theta0, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    int ops = 0;
+    double v = lanczos_lowest(e, site, din, dout, n, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, &ops);
+    TN_CUDA(cudaMemcpyAsync(theta_out, dout, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+    *eig = v;
+    if (numops) *numops = ops;
+  });
+}
+int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* counts, const int32_t* sites, const int32_t* nsites,
+                        const tn_cplx* const* gate_ptrs, tn_gates** out) {
+  return guard([&] {
+    auto* h = new tn_gates();
+    h->g = gates_create(&ctx->c, d, nrows, counts, sites, nsites, reinterpret_cast<const cplx* const*>(gate_ptrs));
+    *out = h;
+  });
+}
+int32_t tn_gates_free(tn_gates* g) { return guard([&] { if (g) { gates_free(g->g); delete g; } }); }
+int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t tr) {
+  return guard([&] { apply_gates(psi->m, gates->g, T(tr)); psi->m->ctx->sync(); });
+}
+int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
+                    const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, const double* uniforms, uint64_t seed,
+                    uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* jumps_out,
+                    double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out) {
+  return guard([&] {
+    int nj = qjmc_run(psi->m, gates->g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), uniforms, seed, trajectory,
+                      obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap);
+    if (njumps_out) *njumps_out = nj;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Device-resident MPS / MPO / environment containers and the hot-path algorithms built on the
+// strided ZGEMM (tn_zgemm.cu), the Jacobi SVD (tn_svd.cu) and the vector kernels (tn_vec.cu).
+// Site numbers are 1-based like the reference.
+#pragma once
+#include "tn_common.cuh"
+#include "tn_svd.cuh"
+#include "tn_vec.cuh"
+#include <memory>
+
+namespace tn {
+
+struct Buf {
+  cplx* p = nullptr; size_t cap = 0;
+  cplx* get(size_t n, cudaStream_t s);
+  void release();
+};
+
+struct Tensor {           // column-major, first index fastest
+  cplx* p = nullptr; size_t cap = 0;
+  std::vector<long long> dims;
+  long long size() const { long long n = 1; for (auto d : dims) n *= d; return n; }
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  SvdWork svd;
+  Buf scratch[16];
+  cplx* dscal = nullptr;     // 64 device scalars
+  cplx* hscal = nullptr;     // 64 pinned host scalars
+  cplx* partials = nullptr;  // dot-product partial sums
+  long long matvecs = 0, svds = 0;
+  void alloc(Tensor& t, const std::vector<long long>& dims);
+  void free(Tensor& t);
+  void swap(Tensor& a, Tensor& b) { std::swap(a, b); }
+  void sync() { TN_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+struct Mps {
+  Ctx* ctx; int rank, d, N, center;
+  std::vector<Tensor> sites;     // sites[i-1] = (chi_l, d [, d], chi_r)
+  long long chiL(int i) const { return sites[i - 1].dims.front(); }
+  long long chiR(int i) const { return sites[i - 1].dims.back(); }
+  long long phys() const { long long p = 1; for (int k = 0; k < rank; ++k) p *= d; return p; }
+  long long maxbonddim() const;
+};
+
+struct Env {                     // ProjMPS(bra, mpo, ket; rank=2)  or overlap ProjMPS(bra, ket) when mpo == nullptr
+  Ctx* ctx; Mps* bra; Mps* mpo; Mps* ket;
+  std::vector<Tensor> blocks;    // (chi_bra, w, chi_ket)
+  Tensor edge;                   // ones(1,1,1)
+  int center; cplx coeff;
+};
+
+struct Gate { int site, nsites; cplx* dev; };
+struct Gates { Ctx* ctx; int d; std::vector<std::vector<Gate>> rows; };
+
+struct Lanczos { int krylovdim, maxiter; double tol; };
+
+// --- MPS -------------------------------------------------------------------------------------
+Mps* mps_create(Ctx* c, int rank, int d, int N, const long long* dims, const cplx* const* host_sites, int center);
+void mps_free(Mps* m);
+void mps_download_site(Mps* m, int i, cplx* host);
+void mps_upload_site(Mps* m, int i, const long long* dims, const cplx* host);
+cplx mps_norm(Mps* m);
+void mps_normalize(Mps* m);
+void mps_movecenter(Mps* m, int idx, Trunc tr);
+void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool normalize, Trunc tr);
+void mps_applyop1(Mps* m, int site, const cplx* op_dev);
+void mps_bond_spectrum(Mps* m, int site, std::vector<double>& out);
+
+// --- environments -----------------------------------------------------------------------------
+Env* env_create(Ctx* c, Mps* bra, Mps* mpo, Mps* ket, cplx coeff, int center);
+void env_free(Env* e);
+void env_buildleft(Env* e, int idx);
+void env_buildright(Env* e, int idx);
+void env_movecenter(Env* e, int idx);
+const Tensor& env_block(Env* e, int idx);
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out);   // sites (site, site+1)
+cplx env_calculate(Env* e);
+
+// --- drivers ------------------------------------------------------------------------------------
+double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, long long n, Lanczos lz, int* numops);
+void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, double* energy, long long* maxbond);
+Gates* gates_create(Ctx* c, int d, int nrows, const int* counts, const int* sites, const int* nsites, const cplx* const* host_gates);
+void gates_free(Gates* g);
+void apply_gates(Mps* psi, Gates* g, Trunc tr);
+void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cplx* out_host);
+
+}  // namespace tn

@@ -1,0 +1,79 @@
+// One quantum-jump Monte Carlo trajectory on the device: reference algorithms/mps/qjmc.jl:59-164
+// (classical = true branch, :88-112) with the emission rates of :170-220.
+#include "tn_mps.cuh"
+#include <cmath>
+
+namespace tn {
+
+// counter-based generator keyed by (seed, trajectory, step, slot): splitmix64 finaliser
+static double counter_uniform(uint64_t seed, uint64_t traj, uint64_t step, uint64_t slot) {
+  uint64_t z = seed * 0x9E3779B97F4A7C15ull + traj * 0xBF58476D1CE4E5B9ull + step * 0x94D049BB133111EBull + slot * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,
+             int steps, double dt, Trunc tr, const double* uniforms, uint64_t seed, uint64_t traj,
+             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap) {
+  Ctx* c = psi->ctx;
+  int d = psi->d, N = psi->N;
+  TN_CHECK(psi->rank == 1, "qjmc: psi must be an MPS");
+  // escape operators L^dag L (qjmc.jl:11-20) and device copies of the jump operators
+  std::vector<cplx> esc((size_t)njump * d * d);
+  for (int k = 0; k < njump; ++k)
+    for (int i = 0; i < d; ++i)
+      for (int j = 0; j < d; ++j) {
+        double xr = 0, xi = 0;
+        for (int q = 0; q < d; ++q) {
+          cplx a = jump_ops[(size_t)k * d * d + q + d * i];   // L(q,i), conj -> L^dag(i,q)
+          cplx b = jump_ops[(size_t)k * d * d + q + d * j];   // L(q,j)
+          xr += a.x * b.x + a.y * b.y; xi += a.x * b.y - a.y * b.x;
+        }
+        esc[(size_t)k * d * d + i + d * j] = cplx{xr, xi};
+      }
+  cplx* djump; TN_CUDA(cudaMalloc((void**)&djump, sizeof(cplx) * (size_t)njump * d * d));
+  TN_CUDA(cudaMemcpyAsync(djump, jump_ops, sizeof(cplx) * (size_t)njump * d * d, cudaMemcpyHostToDevice, c->stream));
+  std::vector<cplx> ex(njump);
+  std::vector<double> rates(njump);
+  std::vector<int> all_sites(N);
+  std::vector<cplx> obs_ops;
+  if (obs_op) { for (int i = 0; i < N; ++i) { all_sites[i] = i + 1; for (int q = 0; q < d * d; ++q) obs_ops.push_back(obs_op[q]); } }
+  int njumps = 0;
+  double time = 0;
+  auto draw = [&](int step, int slot) { return uniforms ? uniforms[(size_t)3 * step + slot] : counter_uniform(seed, traj, step, slot); };
+  for (int i = 1; i <= steps; ++i) {
+    apply_gates(psi, gates, tr);                                   // qjmc.jl:61
+    (void)draw(i - 1, 0);                                          // qjmc.jl:64 (drawn, unused in classical mode)
+    mps_normalize(psi);                                            // qjmc.jl:90
+    expect_local(psi, njump, jump_sites, esc.data(), ex.data());   // qjmc.jl:93
+    double er = 0;
+    for (int k = 0; k < njump; ++k) {
+      double c2 = jump_coeffs[k] * jump_coeffs[k];
+      rates[k] = std::hypot(c2 * ex[k].x, c2 * ex[k].y);
+      er += rates[k];
+    }
+    double prob = std::exp(-er * dt);
+    if (draw(i - 1, 1) > prob) {                                   // qjmc.jl:97
+      double r = draw(i - 1, 2), cum = 0;
+      int idx = njump - 1;
+      for (int k = 0; k < njump; ++k) { cum += rates[k]; if (r < cum / er) { idx = k; break; } }
+      mps_movecenter(psi, 1, Trunc{0.0, 0, 1});                    // qjmc.jl:103-107
+      mps_applyop1(psi, jump_sites[idx], djump + (size_t)idx * d * d);
+      mps_movecenter(psi, N, Trunc{0.0, 0, 1});
+      mps_movecenter(psi, 1, tr);
+      mps_normalize(psi);
+      if (njumps < jump_cap) { if (jumps_out) jumps_out[njumps] = idx + 1; if (jumptimes_out) jumptimes_out[njumps] = time + dt; }
+      njumps++;
+    }
+    time += dt;
+    if (obs_op && save_every > 0 && i % save_every == 0)
+      expect_local(psi, N, all_sites.data(), obs_ops.data(), obs_out + (size_t)(i / save_every - 1) * N);
+  }
+  c->sync();
+  cudaFree(djump);
+  return njumps;
+}
+
+}  // namespace tn

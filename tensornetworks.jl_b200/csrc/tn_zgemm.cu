@@ -1,0 +1,253 @@
+// Complex-FP64 tensor contraction as a strided GEMM on the FP64 tensor pipe (DMMA.8x8x4) for sm_100a.
+//
+// Replaces every `contract` on the hot path (reference src/tensors.jl:9-18 -> TensorOperations TTGT:
+// permute copy + zgemm + permute copy).  Here the permutes are folded into the tile loads: each operand
+// index (m, n, k) may be a fused pair of tensor indices with independent strides (Idx2), addressed
+// directly by the 16-byte cp.async that stages the tile, so no transpose pass ever touches HBM.
+//
+// Arithmetic: complex MAC = 4 real DMMA.8x8x4 (re += ar*br, re += ai*(-bi), im += ar*bi, im += ai*br).
+// Complex elements stay interleaved in shared memory; one LDS.128 per fragment element yields the re and
+// im fragment registers at once, so the "de-interleave" costs nothing.
+//
+// Tile: CTA = BM x BN complex outputs, 8 warps (WARPS_M x WARPS_N), warp tile (8*TM) x (8*TN),
+// BK = 8 per stage, 4-stage cp.async pipeline.  Shared layout is [k][m] / [k][n] with the leading
+// dimension padded to == 2 (mod 8) 16-byte units so the 8 lanes of a quarter-warp hit 8 distinct
+// bank groups on fragment loads.
+#include "tn_common.cuh"
+#include <atomic>
+
+namespace tn {
+
+static std::atomic<long long> g_launches{0};
+long long zgemm_launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool pred) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ long long idx_off(const Idx2& ix, int i, int batch) {
+  if (i < ix.n0) return (long long)i * ix.s0;
+  int i1 = i / ix.n0, i0 = i - i1 * ix.n0;
+  if (ix.tab) i1 = ix.tab[(long long)ix.tab_bs * batch + i1];
+  return (long long)i0 * ix.s0 + (long long)i1 * ix.s1;
+}
+// table lookups must also apply when i < n0 (i1 == 0)
+__device__ __forceinline__ long long idx_off_t(const Idx2& ix, int i, int batch) {
+  if (!ix.tab) return idx_off(ix, i, batch);
+  int i1 = i / ix.n0, i0 = i - i1 * ix.n0;
+  i1 = ix.tab[(long long)ix.tab_bs * batch + i1];
+  return (long long)i0 * ix.s0 + (long long)i1 * ix.s1;
+}
+
+template <int WARPS_M, int WARPS_N, int TM, int TN>
+struct TileCfg {
+  static constexpr int BM = WARPS_M * TM * 8;
+  static constexpr int BN = WARPS_N * TN * 8;
+  static constexpr int BK = 8;
+  static constexpr int STAGES = 4;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int LDA = BM + 2;
+  static constexpr int LDB = BN + 2;
+  static constexpr int A_STAGE = BK * LDA;   // complex elements
+  static constexpr int B_STAGE = BK * LDB;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE + B_STAGE) * 16;
+  static constexpr int A_PER_THR = BM * BK / THREADS;
+  static constexpr int B_PER_THR = BN * BK / THREADS;
+};
+
+template <int WARPS_M, int WARPS_N, int TM, int TN>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const GemmDesc d) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
+  constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* As = reinterpret_cast<cplx*>(smem_raw);
+  cplx* Bs = As + STAGES * Cfg::A_STAGE;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp % WARPS_M, wn = warp / WARPS_M;
+  const int g = lane >> 2, t = lane & 3;
+  const int z = blockIdx.z;
+  const int batch = z / d.ksplit, split = z - batch * d.ksplit;
+  const int m_blk = blockIdx.x * BM, n_blk = blockIdx.y * BN;
+  const int k_begin = split * d.kchunk;
+  const int k_end = min(d.K, k_begin + d.kchunk);
+  const cplx* __restrict__ Ab = d.A + (long long)batch * d.bsA;
+  const cplx* __restrict__ Bb = d.B + (long long)batch * d.bsB;
+
+  // ---- per-thread global->shared load assignment (fixed m/n, walking k) ------------------------
+  int a_m[Cfg::A_PER_THR], a_k[Cfg::A_PER_THR];
+  long long a_moff[Cfg::A_PER_THR]; bool a_ok[Cfg::A_PER_THR];
+#pragma unroll
+  for (int i = 0; i < Cfg::A_PER_THR; ++i) {
+    int e = tid + i * THREADS;
+    if (d.a_kfast) { a_k[i] = e % BK; a_m[i] = e / BK; } else { a_m[i] = e % BM; a_k[i] = e / BM; }
+    int m = m_blk + a_m[i];
+    a_ok[i] = m < d.M;
+    a_moff[i] = a_ok[i] ? idx_off_t(d.am, m, batch) : 0;
+  }
+  int b_n[Cfg::B_PER_THR], b_k[Cfg::B_PER_THR];
+  long long b_noff[Cfg::B_PER_THR]; bool b_ok[Cfg::B_PER_THR];
+#pragma unroll
+  for (int i = 0; i < Cfg::B_PER_THR; ++i) {
+    int e = tid + i * THREADS;
+    if (d.b_kfast) { b_k[i] = e % BK; b_n[i] = e / BK; } else { b_n[i] = e % BN; b_k[i] = e / BN; }
+    int n = n_blk + b_n[i];
+    b_ok[i] = n < d.N;
+    b_noff[i] = b_ok[i] ? idx_off_t(d.bn, n, batch) : 0;
+  }
+
+  auto load_stage = [&](int stage, int k0) {
+    cplx* as = As + stage * Cfg::A_STAGE;
+    cplx* bs = Bs + stage * Cfg::B_STAGE;
+#pragma unroll
+    for (int i = 0; i < Cfg::A_PER_THR; ++i) {
+      int k = k0 + a_k[i];
+      bool p = a_ok[i] && (k < k_end);
+      long long off = p ? a_moff[i] + idx_off_t(d.ak, k, batch) : 0;
+      cp_async16(as + a_k[i] * LDA + a_m[i], Ab + off, p);
+    }
+#pragma unroll
+    for (int i = 0; i < Cfg::B_PER_THR; ++i) {
+      int k = k0 + b_k[i];
+      bool p = b_ok[i] && (k < k_end);
+      long long off = p ? b_noff[i] + idx_off_t(d.bk, k, batch) : 0;
+      cp_async16(bs + b_k[i] * LDB + b_n[i], Bb + off, p);
+    }
+  };
+
+  double cre[TM][TN][2], cim[TM][TN][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
+
+  const int ktiles = (k_end - k_begin + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < ktiles) load_stage(s, k_begin + s * BK);
+    cp_async_commit();
+  }
+
+  const double sa = d.conjA ? -1.0 : 1.0;   // conj-on-load: flip the sign of the imaginary fragment
+  const double sb = d.conjB ? -1.0 : 1.0;
+  const int a_frag = wm * TM * 8 + g;       // + mi*8, row (k) = t
+  const int b_frag = wn * TN * 8 + g;
+
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {  // prefetch tile kt+STAGES-1 into the slot freed at iteration kt-1
+      int nk = kt + STAGES - 1;
+      if (nk < ktiles) load_stage(nk % STAGES, k_begin + nk * BK);
+      cp_async_commit();
+    }
+    const cplx* as = As + (kt % STAGES) * Cfg::A_STAGE;
+    const cplx* bs = Bs + (kt % STAGES) * Cfg::B_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double ar[TM], ai[TM], br[TN], bi[TN], nbi[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        cplx v = as[(kk + t) * LDA + a_frag + i * 8];
+        ar[i] = v.x; ai[i] = sa * v.y;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        cplx v = bs[(kk + t) * LDB + b_frag + j * 8];
+        br[j] = v.x; bi[j] = sb * v.y; nbi[j] = -bi[j];
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+          dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
+          dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
+          dmma(cre[i][j][0], cre[i][j][1], ai[i], nbi[j]);
+          dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
+        }
+    }
+  }
+  cp_async_wait<0>();
+
+  // ---- epilogue: C = alpha*acc + beta*C, strided store -----------------------------------------
+  cplx* __restrict__ Cb = d.C + (long long)batch * d.bsC + (long long)split * d.ssC;
+  const bool has_beta = (d.beta.x != 0.0 || d.beta.y != 0.0);
+  long long noff[TN][2]; bool nok[TN][2];
+#pragma unroll
+  for (int j = 0; j < TN; ++j)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      int n = n_blk + wn * TN * 8 + j * 8 + 2 * t + q;
+      nok[j][q] = n < d.N;
+      noff[j][q] = nok[j][q] ? idx_off_t(d.cn, n, batch) : 0;
+    }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int m = m_blk + wm * TM * 8 + i * 8 + g;
+    if (m >= d.M) continue;
+    long long moff = idx_off_t(d.cm, m, batch);
+#pragma unroll
+    for (int j = 0; j < TN; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!nok[j][q]) continue;
+        double xr = cre[i][j][q], xi = cim[i][j][q];
+        cplx o;
+        o.x = d.alpha.x * xr - d.alpha.y * xi;
+        o.y = d.alpha.x * xi + d.alpha.y * xr;
+        cplx* p = Cb + moff + noff[j][q];
+        if (has_beta) {
+          cplx c = *p;
+          o.x += d.beta.x * c.x - d.beta.y * c.y;
+          o.y += d.beta.x * c.y + d.beta.y * c.x;
+        }
+        *p = o;
+      }
+  }
+}
+
+template <int WARPS_M, int WARPS_N, int TM, int TN>
+static void launch(const GemmDesc& d, cudaStream_t stream) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
+  static bool configured = false;
+  auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN>;
+  if (!configured) {
+    TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return;
+  dim3 grid((d.M + Cfg::BM - 1) / Cfg::BM, (d.N + Cfg::BN - 1) / Cfg::BN, d.batch * d.ksplit);
+  TN_CHECK(grid.y <= 65535 && grid.z <= 65535, "zgemm: grid too large");
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d);
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
+
+void zgemm(const GemmDesc& d, cudaStream_t stream) { launch<4, 2, 4, 4>(d, stream); }
+
+// Chooses the CTA tile from the problem shape and the load mapping from which sub-index is unit-stride.
+void zgemm_auto(GemmDesc d, cudaStream_t stream) {
+  if (d.ksplit <= 0) { d.ksplit = 1; }
+  if (d.ksplit == 1) d.kchunk = d.K;
+  if (d.batch <= 0) d.batch = 1;
+  d.a_kfast = (d.ak.s0 == 1 && d.am.s0 != 1) ? 1 : 0;
+  d.b_kfast = (d.bk.s0 == 1 && d.bn.s0 != 1) ? 1 : 0;
+  if (d.M <= 64 && d.N <= 64)      launch<2, 4, 4, 2>(d, stream);   // 64 x 64   (Gram blocks, tiny bonds)
+  else if (d.N <= 32)              launch<8, 1, 4, 4>(d, stream);   // 256 x 32  (skinny right operand)
+  else if (d.M <= 64)              launch<2, 4, 4, 4>(d, stream);   // 64 x 128
+  else                             launch<4, 2, 4, 4>(d, stream);   // 128 x 64
+}
+
+}  // namespace tn

@@ -1,0 +1,47 @@
+"""GPU parity: strided complex-FP64 contraction kernel (K1) vs NumPy (tolerance: relative
+Frobenius <= 1e-13, SURVEY.md section 4 tier 4)."""
+import numpy as np
+import pytest
+
+from gpu_util import crandn, relerr
+
+pytestmark = pytest.mark.gpu
+BIG = 1 << 40
+
+
+def test_plain_nn_and_edges():
+    import tnb200
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(1, 1, 1), (7, 5, 3), (64, 64, 64), (129, 65, 33), (300, 200, 150), (256, 20, 20), (40, 300, 17)]:
+        A, B = crandn(rng, M, K), crandn(rng, K, N)
+        Af, Bf = np.asfortranarray(A), np.asfortranarray(B)
+        C = tnb200.contract_strided(M, N, K, Af.reshape(-1, order='F'), (BIG, 1, 0), (BIG, M, 0), 0,
+                                    Bf.reshape(-1, order='F'), (BIG, 1, 0), (BIG, K, 0), 0, M * N, (BIG, 1, 0), (BIG, M, 0))
+        assert relerr(C.reshape(M, N, order='F'), A @ B) < 1e-13
+
+
+def test_conj_transpose_and_alpha():
+    import tnb200
+    rng = np.random.default_rng(1)
+    M, N, K = 70, 90, 130
+    A, B = crandn(rng, K, M), crandn(rng, N, K)     # C = alpha * A^H B^T(conj)
+    C = tnb200.contract_strided(M, N, K, np.asfortranarray(A).reshape(-1, order='F'), (BIG, K, 0), (BIG, 1, 0), 1,
+                                np.asfortranarray(B).reshape(-1, order='F'), (BIG, N, 0), (BIG, 1, 0), 1,
+                                M * N, (BIG, 1, 0), (BIG, M, 0), alpha=0.5 - 2j)
+    assert relerr(C.reshape(M, N, order='F'), (0.5 - 2j) * (A.conj().T @ B.conj().T)) < 1e-13
+
+
+def test_fused_two_level_indices():
+    """T2(a,s,w2,b') = sum_{w,s'} T1(a,w,s',b') M(w,s,s',w2): rows (a,b') and the MPO operand use
+    two-level strides -- the permute-into-tile path (no transposed copies)."""
+    import tnb200
+    rng = np.random.default_rng(2)
+    ca, w, d, cb, w2 = 37, 5, 2, 29, 4
+    T1 = crandn(rng, ca, w, d, cb)
+    Mo = crandn(rng, w, d, d, w2)
+    want = np.einsum('awtb,wstx->asxb', T1, Mo)
+    C = tnb200.contract_strided(ca * cb, d * w2, w * d,
+                                np.asfortranarray(T1).reshape(-1, order='F'), (ca, 1, ca * w * d), (BIG, ca, 0), 0,
+                                np.asfortranarray(Mo).reshape(-1, order='F'), (w, 1, w * d), (d, w, w * d * d), 0,
+                                ca * d * w2 * cb, (ca, 1, ca * d * w2), (BIG, ca, 0))
+    assert relerr(C.reshape(ca, d, w2, cb, order='F'), want) < 1e-13
