@@ -292,11 +292,12 @@ void env_buildright(Env* e, int idx) {
                   M.p, idx2(w, (long long)wl * d * d, (long long)wl * d), idx2(d, wl, 1), 0,
                   Y2, idx1(1), idx1((long long)cbl * ca)), s);
   }
-  // R'(a_l, w_l, b_l) = sum_{(s,a)} conj(A1)[a_l,(s,a)] Y2(b_l, a, s, w_l); n = (b_l, w_l) with b_l fastest
+  // R'(a_l, w_l, b_l) = sum_{(a,s)} conj(A1)(a_l,s,a) Y2(b_l,a,s,w_l); k = (a,s) with a fastest (uniform stride in Y2),
+  // n = (b_l, w_l) with b_l fastest so that both operands are read along their unit-stride index
   Tensor& out = e->blocks[idx - 1];
   c->alloc(out, {cal, wl, cbl});
-  zgemm_auto(mk(cal, cbl * wl, d * ca, A1.p, idx1(1), idx1(cal), 1,
-                Y2, idx2(d, (long long)cbl * ca, cbl), idx2(cbl, 1, (long long)cbl * ca * d), 0,
+  zgemm_auto(mk(cal, cbl * wl, d * ca, A1.p, idx1(1), idx2(ca, (long long)cal * d, cal), 1,
+                Y2, idx1(cbl), idx2(cbl, 1, (long long)cbl * ca * d), 0,
                 out.p, idx1(1), idx2(cbl, (long long)cal * wl, cal)), s);
 }
 

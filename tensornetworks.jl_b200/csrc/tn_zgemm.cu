@@ -66,7 +66,9 @@ struct TileCfg {
   static constexpr int B_PER_THR = BN * BK / THREADS;
 };
 
-template <int WARPS_M, int WARPS_N, int TM, int TN>
+// SIMPLE_K: both operands' k index is single-level without a lookup table, so each load slot just
+// advances a pointer by BK * stride per k-tile (no index arithmetic inside the pipeline).
+template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const GemmDesc d) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
@@ -87,43 +89,77 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const 
   const cplx* __restrict__ Bb = d.B + (long long)batch * d.bsB;
 
   // ---- per-thread global->shared load assignment (fixed m/n, walking k) ------------------------
+  // Each slot keeps its running k position as (k0, k1) = (k mod n0, k div n0) so that advancing by BK
+  // needs no integer division inside the pipeline.
+  struct KPos { int k, k0, k1; };
+  auto kpos_init = [&](const Idx2& ix, int k) { KPos p; p.k = k; p.k1 = k / ix.n0; p.k0 = k - p.k1 * ix.n0; return p; };
+  auto kpos_off = [&](const Idx2& ix, const KPos& p) -> long long {
+    int l1 = p.k1;
+    if (ix.tab) l1 = ix.tab[(long long)ix.tab_bs * batch + p.k1];
+    return (long long)p.k0 * ix.s0 + (long long)l1 * ix.s1;
+  };
+  auto kpos_adv = [&](const Idx2& ix, KPos& p) {
+    p.k += BK; p.k0 += BK;
+    while (p.k0 >= ix.n0) { p.k0 -= ix.n0; p.k1++; }
+  };
   int a_m[Cfg::A_PER_THR], a_k[Cfg::A_PER_THR];
-  long long a_moff[Cfg::A_PER_THR]; bool a_ok[Cfg::A_PER_THR];
+  const cplx* a_base[Cfg::A_PER_THR]; bool a_ok[Cfg::A_PER_THR]; KPos a_pos[Cfg::A_PER_THR];
 #pragma unroll
   for (int i = 0; i < Cfg::A_PER_THR; ++i) {
     int e = tid + i * THREADS;
     if (d.a_kfast) { a_k[i] = e % BK; a_m[i] = e / BK; } else { a_m[i] = e % BM; a_k[i] = e / BM; }
     int m = m_blk + a_m[i];
     a_ok[i] = m < d.M;
-    a_moff[i] = a_ok[i] ? idx_off_t(d.am, m, batch) : 0;
+    a_base[i] = Ab + (a_ok[i] ? idx_off_t(d.am, m, batch) : 0);
+    a_pos[i] = kpos_init(d.ak, k_begin + a_k[i]);
+    if (SIMPLE_K) a_base[i] += (long long)(k_begin + a_k[i]) * d.ak.s0;
   }
   int b_n[Cfg::B_PER_THR], b_k[Cfg::B_PER_THR];
-  long long b_noff[Cfg::B_PER_THR]; bool b_ok[Cfg::B_PER_THR];
+  const cplx* b_base[Cfg::B_PER_THR]; bool b_ok[Cfg::B_PER_THR]; KPos b_pos[Cfg::B_PER_THR];
 #pragma unroll
   for (int i = 0; i < Cfg::B_PER_THR; ++i) {
     int e = tid + i * THREADS;
     if (d.b_kfast) { b_k[i] = e % BK; b_n[i] = e / BK; } else { b_n[i] = e % BN; b_k[i] = e / BN; }
     int n = n_blk + b_n[i];
     b_ok[i] = n < d.N;
-    b_noff[i] = b_ok[i] ? idx_off_t(d.bn, n, batch) : 0;
+    b_base[i] = Bb + (b_ok[i] ? idx_off_t(d.bn, n, batch) : 0);
+    b_pos[i] = kpos_init(d.bk, k_begin + b_k[i]);
+    if (SIMPLE_K) b_base[i] += (long long)(k_begin + b_k[i]) * d.bk.s0;
   }
 
-  auto load_stage = [&](int stage, int k0) {
+  // loads the next k-tile (tiles are always requested in increasing order)
+  const long long a_step = (long long)BK * d.ak.s0, b_step = (long long)BK * d.bk.s0;
+  auto load_stage = [&](int stage) {
     cplx* as = As + stage * Cfg::A_STAGE;
     cplx* bs = Bs + stage * Cfg::B_STAGE;
+    if (SIMPLE_K) {
+#pragma unroll
+      for (int i = 0; i < Cfg::A_PER_THR; ++i) {
+        bool p = a_ok[i] && (a_pos[i].k < k_end);
+        cp_async16(as + a_k[i] * LDA + a_m[i], p ? a_base[i] : Ab, p);
+        a_base[i] += a_step; a_pos[i].k += BK;
+      }
+#pragma unroll
+      for (int i = 0; i < Cfg::B_PER_THR; ++i) {
+        bool p = b_ok[i] && (b_pos[i].k < k_end);
+        cp_async16(bs + b_k[i] * LDB + b_n[i], p ? b_base[i] : Bb, p);
+        b_base[i] += b_step; b_pos[i].k += BK;
+      }
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < Cfg::A_PER_THR; ++i) {
-      int k = k0 + a_k[i];
-      bool p = a_ok[i] && (k < k_end);
-      long long off = p ? a_moff[i] + idx_off_t(d.ak, k, batch) : 0;
-      cp_async16(as + a_k[i] * LDA + a_m[i], Ab + off, p);
+      bool p = a_ok[i] && (a_pos[i].k < k_end);
+      long long off = p ? kpos_off(d.ak, a_pos[i]) : 0;
+      cp_async16(as + a_k[i] * LDA + a_m[i], a_base[i] + off, p);
+      kpos_adv(d.ak, a_pos[i]);
     }
 #pragma unroll
     for (int i = 0; i < Cfg::B_PER_THR; ++i) {
-      int k = k0 + b_k[i];
-      bool p = b_ok[i] && (k < k_end);
-      long long off = p ? b_noff[i] + idx_off_t(d.bk, k, batch) : 0;
-      cp_async16(bs + b_k[i] * LDB + b_n[i], Bb + off, p);
+      bool p = b_ok[i] && (b_pos[i].k < k_end);
+      long long off = p ? kpos_off(d.bk, b_pos[i]) : 0;
+      cp_async16(bs + b_k[i] * LDB + b_n[i], b_base[i] + off, p);
+      kpos_adv(d.bk, b_pos[i]);
     }
   };
 
@@ -136,7 +172,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const 
   const int ktiles = (k_end - k_begin + BK - 1) / BK;
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < ktiles) load_stage(s, k_begin + s * BK);
+    if (s < ktiles) load_stage(s);
     cp_async_commit();
   }
 
@@ -150,7 +186,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const 
     __syncthreads();
     {  // prefetch tile kt+STAGES-1 into the slot freed at iteration kt-1
       int nk = kt + STAGES - 1;
-      if (nk < ktiles) load_stage(nk % STAGES, k_begin + nk * BK);
+      if (nk < ktiles) load_stage(nk % STAGES);
       cp_async_commit();
     }
     const cplx* as = As + (kt % STAGES) * Cfg::A_STAGE;
@@ -171,12 +207,19 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const 
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) {
-          dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
-          dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
-          dmma(cre[i][j][0], cre[i][j][1], ai[i], nbi[j]);
-          dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
-        }
+        for (int j = 0; j < TN; ++j) dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma(cre[i][j][0], cre[i][j][1], ai[i], nbi[j]);
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
     }
   }
   cp_async_wait<0>();
@@ -218,11 +261,11 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const 
   }
 }
 
-template <int WARPS_M, int WARPS_N, int TM, int TN>
-static void launch(const GemmDesc& d, cudaStream_t stream) {
+template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+static void launch2(const GemmDesc& d, cudaStream_t stream) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   static bool configured = false;
-  auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN>;
+  auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>;
   if (!configured) {
     TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -233,6 +276,13 @@ static void launch(const GemmDesc& d, cudaStream_t stream) {
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d);
   TN_CUDA(cudaGetLastError());
   count_launch(1);
+}
+
+template <int WARPS_M, int WARPS_N, int TM, int TN>
+static void launch(const GemmDesc& d, cudaStream_t stream) {
+  bool simple = d.ak.tab == nullptr && d.bk.tab == nullptr && d.ak.n0 >= d.K && d.bk.n0 >= d.K;
+  if (simple) launch2<WARPS_M, WARPS_N, TM, TN, true>(d, stream);
+  else launch2<WARPS_M, WARPS_N, TM, TN, false>(d, stream);
 }
 
 void zgemm(const GemmDesc& d, cudaStream_t stream) { launch<4, 2, 4, 4>(d, stream); }
