@@ -97,11 +97,17 @@ int32_t tn_env_movecenter(tn_env* e, int32_t idx);      /* abstractprojmps.jl:60
 int32_t tn_env_center(tn_env* e, int32_t* out);
 int32_t tn_env_block_dims(tn_env* e, int32_t idx, int64_t* dims3);   /* (chi_bra, w, chi_ket) */
 int32_t tn_env_block_download(tn_env* e, int32_t idx, tn_cplx* out); /* block(projV, idx): abstractprojmps.jl:43-46 */
+/* projV[idx] = x (setindex!): abstractprojmps.jl:49-52.  dims3 = (chi_bra, w, chi_ket); data on the host. */
+int32_t tn_env_block_upload(tn_env* e, int32_t idx, const int64_t* dims3, const tn_cplx* data);
+int32_t tn_env_set_center(tn_env* e, int32_t center);
 /* product(projV, A, direction, nsites=2): projmps.jl:103-145 rank-2 branch.  theta / out on the HOST,
  * shape (chi_l, d, d, chi_r) of sites (site, site+1) with site = direction ? center-1 : center. */
 int32_t tn_env_product(tn_env* e, const tn_cplx* theta_host, int32_t direction, tn_cplx* out_host);
 /* same with DEVICE buffers (no PCIe traffic), `reps` back-to-back applications (reps >= 1) */
 int32_t tn_env_product_dev(tn_env* e, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps);
+/* instrumented variant for the roofline: CUDA-event time (ms, summed over reps) of the three contraction
+ * stages L.theta / .W / .R of the matvec, measured on the context's stream. */
+int32_t tn_env_product_profile(tn_env* e, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps, double* stage_ms3);
 int32_t tn_env_calculate(tn_env* e, tn_cplx* out);      /* projmps.jl:192-216 */
 
 /* ---- fused steps (what the drivers call) ------------------------------------------------------ */

@@ -1,0 +1,68 @@
+# Thin ccall shim a TensorNetworks.jl maintainer would add (UNVERIFIED: Julia is not available in the
+# build image).  It keeps the reference's API and dispatches the hot path into libtnb200.so.
+module TNB200
+using TensorNetworks
+import TensorNetworks: GMPS, AbstractProjMPS, movecenter!, product, calculate, buildleft!, buildright!, block, applygates!, norm, normalize!
+
+const lib = get(ENV, "TNB200_LIB", "libtnb200.so")
+struct TruncT; cutoff::Cdouble; maxdim::Int64; mindim::Int64; end
+struct LanczosT; krylovdim::Int32; maxiter::Int32; tol::Cdouble; end
+check(st) = st == 0 || error(unsafe_string(ccall((:tn_last_error, lib), Cstring, ())))
+
+mutable struct Ctx; h::Ptr{Cvoid}; end
+function Ctx(device::Integer=0)
+    r = Ref{Ptr{Cvoid}}(); check(ccall((:tn_ctx_create, lib), Int32, (Int32, Ref{Ptr{Cvoid}}), device, r))
+    c = Ctx(r[]); finalizer(x -> ccall((:tn_ctx_destroy, lib), Int32, (Ptr{Cvoid},), x.h), c); c
+end
+
+# device mirror of a GMPS (structures/mps/gmps.jl:8-13)
+mutable struct CuGMPS; h::Ptr{Cvoid}; rank::Int; dim::Int; N::Int; ctx::Ctx; end
+function CuGMPS(ctx::Ctx, psi::GMPS)
+    N = length(psi); r = psi.rank
+    dims = Int64[size(psi[i])[k] for i in 1:N for k in 1:r+2]          # N x (rank+2), row-major
+    ptrs = [pointer(psi.tensors[i]) for i in 1:N]
+    h = Ref{Ptr{Cvoid}}()
+    GC.@preserve psi check(ccall((:tn_mps_upload, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Int64}, Ptr{Ptr{ComplexF64}}, Int32, Ref{Ptr{Cvoid}}),
+        ctx.h, r, psi.dim, N, dims, ptrs, psi.center, h))
+    m = CuGMPS(h[], r, psi.dim, N, ctx); finalizer(x -> ccall((:tn_mps_free, lib), Int32, (Ptr{Cvoid},), x.h), m); m
+end
+function download!(psi::GMPS, m::CuGMPS)
+    dims = Matrix{Int64}(undef, m.rank + 2, m.N)
+    check(ccall((:tn_mps_dims, lib), Int32, (Ptr{Cvoid}, Ptr{Int64}), m.h, dims))
+    for i in 1:m.N
+        t = Array{ComplexF64}(undef, dims[:, i]...)
+        check(ccall((:tn_mps_download_site, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{ComplexF64}), m.h, i, t))
+        psi.tensors[i] = t
+    end
+    c = Ref{Int32}(); check(ccall((:tn_mps_info, lib), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Int32}), m.h, C_NULL, C_NULL, C_NULL, c))
+    psi.center = c[]; psi
+end
+
+# device-backed projector: slots into dmrg(psi, Hs::ProjMPSSum) through the AbstractProjMPS protocol
+mutable struct CuProjMPS <: AbstractProjMPS; h::Ptr{Cvoid}; psi::CuGMPS; H::CuGMPS; center::Int; end
+function CuProjMPS(psi::CuGMPS, H::CuGMPS; coeff=1.0, center=1)
+    h = Ref{Ptr{Cvoid}}()
+    check(ccall((:tn_env_create, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, ComplexF64, Int32, Ref{Ptr{Cvoid}}),
+                psi.ctx.h, psi.h, H.h, psi.h, ComplexF64(coeff), center, h))
+    CuProjMPS(h[], psi, H, center)
+end
+movecenter!(p::CuProjMPS, idx::Int) = (check(ccall((:tn_env_movecenter, lib), Int32, (Ptr{Cvoid}, Int32), p.h, idx)); p.center = idx)
+buildleft!(p::CuProjMPS, idx::Int) = check(ccall((:tn_env_buildleft, lib), Int32, (Ptr{Cvoid}, Int32), p.h, idx))
+buildright!(p::CuProjMPS, idx::Int) = check(ccall((:tn_env_buildright, lib), Int32, (Ptr{Cvoid}, Int32), p.h, idx))
+function product(p::CuProjMPS, A, direction::Bool=false, nsites::Int=2)   # projmps.jl:103-145
+    out = similar(A)
+    check(ccall((:tn_env_product, lib), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Ptr{ComplexF64}), p.h, A, direction, out)); out
+end
+function calculate(p::CuProjMPS)
+    v = Ref{ComplexF64}(); check(ccall((:tn_env_calculate, lib), Int32, (Ptr{Cvoid}, Ref{ComplexF64}), p.h, v)); v[]
+end
+
+# fused sweep: replaces the body of dmrg.jl:35-63
+function dmrg_sweep!(psi::CuGMPS, Hs::CuProjMPS, direction::Bool; krylovdim=3, kryloviter=2, cutoff=1e-12, maxdim=1000, mindim=1)
+    e = Ref{Cdouble}(); D = Ref{Int64}()
+    check(ccall((:tn_dmrg_sweep, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, LanczosT, TruncT, Ref{Cdouble}, Ref{Int64}),
+                psi.h, Hs.h, direction, LanczosT(krylovdim, kryloviter, 1e-14), TruncT(cutoff, maxdim, mindim), e, D))
+    e[], D[]
+end
+end # module

@@ -217,6 +217,19 @@ int32_t tn_env_block_download(tn_env* e, int32_t idx, tn_cplx* out) {
     e->e->ctx->sync();
   });
 }
+int32_t tn_env_block_upload(tn_env* eh, int32_t idx, const int64_t* dims3, const tn_cplx* data) {
+  return guard([&] {
+    Env* e = eh->e; Ctx* c = e->ctx;
+    TN_CHECK(idx >= 1 && idx <= e->ket->N, "block index out of range");
+    Tensor& t = e->blocks[idx - 1];
+    c->alloc(t, {(long long)dims3[0], (long long)dims3[1], (long long)dims3[2]});
+    TN_CUDA(cudaMemcpyAsync(t.p, data, (size_t)t.size() * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+  });
+}
+int32_t tn_env_set_center(tn_env* eh, int32_t center) {
+  return guard([&] { TN_CHECK(center >= 0 && center <= eh->e->ket->N, "center out of range"); eh->e->center = center; });
+}
 static int product_site(Env* e, int direction) {   // projmps.jl:109
   TN_CHECK(e->center >= 1, "the environment centre is not set");
   int site = direction ? e->center - 1 : e->center;
@@ -241,6 +254,21 @@ int32_t tn_env_product_dev(tn_env* eh, const void* theta_dev, int32_t direction,
     Env* e = eh->e;
     int site = product_site(e, direction);
     for (int r = 0; r < std::max(1, reps); ++r) env_product_dev(e, (const cplx*)theta_dev, site, (cplx*)out_dev);
+  });
+}
+int32_t tn_env_product_profile(tn_env* eh, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps, double* stage_ms3) {
+  return guard([&] {
+    Env* e = eh->e; Ctx* c = e->ctx;
+    int site = product_site(e, direction);
+    reps = std::max(1, reps);
+    std::vector<cudaEvent_t> ev((size_t)4 * reps);
+    for (auto& x : ev) TN_CUDA(cudaEventCreate(&x));
+    for (int r = 0; r < reps; ++r) env_product_dev(e, (const cplx*)theta_dev, site, (cplx*)out_dev, &ev[(size_t)4 * r]);
+    c->sync();
+    for (int k = 0; k < 3; ++k) stage_ms3[k] = 0;
+    for (int r = 0; r < reps; ++r)
+      for (int k = 0; k < 3; ++k) { float ms = 0; TN_CUDA(cudaEventElapsedTime(&ms, ev[(size_t)4 * r + k], ev[(size_t)4 * r + k + 1])); stage_ms3[k] += ms; }
+    for (auto& x : ev) cudaEventDestroy(x);
   });
 }
 int32_t tn_env_calculate(tn_env* e, tn_cplx* out) { return guard([&] { cplx v = env_calculate(e->e); out->re = v.x; out->im = v.y; }); }

@@ -333,7 +333,7 @@ __global__ void build_w2_kernel(const cplx* __restrict__ M1, const cplx* __restr
 }
 
 // H_eff * theta for sites (site, site+1):  out(a,s1,s2,a') = coeff * sum L M1 M2 theta R   (projmps.jl:107-134, :144)
-void env_product_dev(Env* e, const cplx* theta, int site, cplx* out) {
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4) {
   Ctx* c = e->ctx; cudaStream_t s = c->stream;
   TN_CHECK(e->mpo != nullptr, "product: the rank-2 branch needs an MPO layer");
   TN_CHECK(site >= 1 && site + 1 <= e->ket->N, "product: site out of range");
@@ -352,17 +352,21 @@ void env_product_dev(Env* e, const cplx* theta, int site, cplx* out) {
     build_w2_kernel<<<(tot + 127) / 128, 128, 0, s>>>(M1.p, M2.p, W, w, w1, w2, d);
     count_launch(1);
   }
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[0], s));
   // T1[(a,w),(s1',s2',b')] = L[(a,w),b] theta[b,(s1',s2',b')]
   cplx* T1 = c->scratch[4].get((size_t)ca * w * d2 * cb2, s);
   zgemm_auto(mk(ca * w, d2 * cb2, cb, L.p, idx1(1), idx1((long long)ca * w), 0, theta, idx1(1), idx1(cb), 0, T1, idx1(1), idx1((long long)ca * w)), s);
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[1], s));
   // T2(a,s1,s2,w2,b') = sum_{(w,s1',s2')} T1(a,(w,s1',s2'),b') W; rows m = (a,b')
   cplx* T2 = c->scratch[5].get((size_t)ca * d2 * w2 * cb2, s);
   zgemm_auto(mk(ca * cb2, d2 * w2, w * d2, T1, idx2(ca, 1, (long long)ca * w * d2), idx1(ca), 0,
                 W, idx1(1), idx1((long long)w * d2), 0,
                 T2, idx2(ca, 1, (long long)ca * d2 * w2), idx1(ca)), s);
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[2], s));
   // out[(a,s1,s2),a'] = coeff * sum_{(w2,b')} T2[(a,s1,s2),(w2,b')] R[a',(w2,b')]
   zgemm_auto(mk(ca * d2, ca2, w2 * cb2, T2, idx1(1), idx1((long long)ca * d2), 0, R.p, idx1(ca2), idx1(1), 0,
                 out, idx1(1), idx1((long long)ca * d2), e->coeff), s);
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[3], s));
   c->matvecs++;
 }
 

@@ -76,7 +76,7 @@ void env_buildleft(Env* e, int idx);
 void env_buildright(Env* e, int idx);
 void env_movecenter(Env* e, int idx);
 const Tensor& env_block(Env* e, int idx);
-void env_product_dev(Env* e, const cplx* theta, int site, cplx* out);   // sites (site, site+1)
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4 = nullptr);   // sites (site, site+1)
 cplx env_calculate(Env* e);
 
 // --- drivers ------------------------------------------------------------------------------------

@@ -64,6 +64,9 @@ PROTOTYPES = {
     "tn_env_center": [P, pI32],
     "tn_env_block_dims": [P, I32, pI64],
     "tn_env_block_download": [P, I32, P],
+    "tn_env_block_upload": [P, I32, pI64, P],
+    "tn_env_set_center": [P, I32],
+    "tn_env_product_profile": [P, P, I32, P, I32, pF64],
     "tn_env_product": [P, P, I32, P],
     "tn_env_product_dev": [P, P, I32, P, I32],
     "tn_env_calculate": [P, C.POINTER(tn_cplx)],

@@ -223,12 +223,22 @@ class ProjMPS:
         check(self.lib.tn_env_block_download(self.h, int(idx), _ptr(out)))
         return out
 
-    def product(self, A, direction=False, nsites=2):
-        """H_eff * A for the two sites at the centre: projmps.jl:103-145 (rank-2 branch)."""
+    def setblock(self, idx, x):
+        """projV[idx] = x: abstractprojmps.jl:49-52."""
+        x = _f(x)
+        d = np.array(x.shape, dtype=np.int64)
+        check(self.lib.tn_env_block_upload(self.h, int(idx), d.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(x)))
+
+    def product(self, A, direction=False, nsites=2, out=None):
+        """H_eff * A for the two sites at the centre: projmps.jl:103-145 (rank-2 branch).
+        ``out`` may be a caller-owned (e.g. pinned) complex128 Fortran-ordered buffer."""
         if nsites != 2:
             raise _lib.TNError("only the two-site product is on the hot path")
         A = _f(A)
-        out = np.zeros(A.shape, dtype=np.complex128, order='F')
+        if out is None:
+            out = np.zeros(A.shape, dtype=np.complex128, order='F')
+        elif not (out.dtype == np.complex128 and out.flags.f_contiguous and out.size == A.size):
+            raise _lib.TNError("out must be a complex128 Fortran-contiguous array of A's size")
         check(self.lib.tn_env_product(self.h, _ptr(A), int(bool(direction)), _ptr(out)))
         return out
 
