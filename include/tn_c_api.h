@@ -87,6 +87,13 @@ int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K,
                             const tn_cplx* B, int64_t b_elems, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB,
                             tn_cplx* C, int64_t c_elems, tn_idx2_t cm, tn_idx2_t cn, tn_cplx alpha);
 
+/* same contraction on DEVICE buffers (no copies), C = alpha*op(A)op(B) + beta*C, enqueued on the context's stream.
+ * Used by the multi-GPU MPO-bond-sharded matvec, whose collectives run between the stages. */
+int32_t tn_contract_strided_dev(tn_ctx* ctx, int64_t M, int64_t N, int64_t K,
+                                const void* A_dev, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
+                                const void* B_dev, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB,
+                                void* C_dev, tn_idx2_t cm, tn_idx2_t cn, tn_cplx alpha, tn_cplx beta);
+
 /* ---- projected environments: structures/mps/projmps.jl, abstractprojmps.jl -------------------- */
 /* ProjMPS(bra, mpo, ket; rank=2, coeff, center): projmps.jl:16-42.  mpo may be NULL (overlap <bra|ket>). */
 int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cplx coeff, int32_t center, tn_env** out);

@@ -193,6 +193,22 @@ int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const 
   });
 }
 
+int32_t tn_contract_strided_dev(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
+                                const void* B, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB, void* Cc, tn_idx2_t cm, tn_idx2_t cn,
+                                tn_cplx alpha, tn_cplx beta) {
+  return guard([&] {
+    TN_CHECK(M >= 0 && N >= 0 && K >= 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "contract: extent out of range");
+    GemmDesc g{};
+    g.M = (int)M; g.N = (int)N; g.K = (int)K;
+    g.A = (const cplx*)A; g.am = I2(am); g.ak = I2(ak); g.conjA = conjA;
+    g.B = (const cplx*)B; g.bk = I2(bk); g.bn = I2(bn); g.conjB = conjB;
+    g.C = (cplx*)Cc; g.cm = I2(cm); g.cn = I2(cn);
+    g.alpha = cplx{alpha.re, alpha.im}; g.beta = cplx{beta.re, beta.im};
+    g.batch = 1; g.ksplit = 1; g.kchunk = (int)K;
+    zgemm_auto(g, ctx->c.stream);
+  });
+}
+
 // ---- environments ------------------------------------------------------------------------------
 int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cplx coeff, int32_t center, tn_env** out) {
   return guard([&] {

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "tn_svd_trunc": [P, P, I64, I64, tn_trunc_t, P, pF64, P, pI64, pI32],
     "tn_contract_strided": [P, I64, I64, I64, P, I64, tn_idx2_t, tn_idx2_t, I32, P, I64, tn_idx2_t, tn_idx2_t, I32,
                             P, I64, tn_idx2_t, tn_idx2_t, tn_cplx],
+    "tn_contract_strided_dev": [P, I64, I64, I64, P, tn_idx2_t, tn_idx2_t, I32, P, tn_idx2_t, tn_idx2_t, I32, P, tn_idx2_t, tn_idx2_t, tn_cplx, tn_cplx],
     "tn_env_create": [P, P, P, P, tn_cplx, I32, PP],
     "tn_env_free": [P],
     "tn_env_buildleft": [P, I32],

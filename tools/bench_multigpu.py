@@ -1,0 +1,111 @@
+"""Multi-GPU measurements for the sharded paths; launch with torchrun, one rank per GPU:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+      tools/bench_multigpu.py --what heff --chi 2048 --w 20
+  ... --what qjmc --sites 32 --chi 64 --traj 64 --steps 5 --workers 4
+Prints one JSON line on rank 0.  Times on the device (CUDA events), max over ranks."""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tensornetworks.jl_b200")):
+    sys.path.insert(0, p)
+import numpy as np
+import torch
+import torch.distributed as dist
+import tnb200
+from tnb200.sharded import ShardedHeff, GpuContractor, run_ensemble
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--what", default="heff")
+    ap.add_argument("--chi", type=int, default=2048)
+    ap.add_argument("--w", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--sites", type=int, default=32)
+    ap.add_argument("--traj", type=int, default=32)
+    ap.add_argument("--workers", type=int, default=4)
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = tnb200.Context(local)
+    d = 2
+    if a.what == "heff":
+        rng = np.random.default_rng(0)      # same inputs on every rank
+        chi, w = a.chi, a.w
+        cr = lambda *s: (rng.standard_normal(s) + 1j * rng.standard_normal(s)) / np.sqrt(s[0])
+        L, R = cr(chi, w, chi), cr(chi, w, chi)
+        M1, M2 = cr(w, d, d, w), cr(w, d, d, w)
+        theta = cr(chi, d, d, chi)
+        sh = ShardedHeff(L, R, M1, M2, rank, world, GpuContractor(ctx), "cuda", dist if world > 1 else None)
+        th = torch.from_numpy(np.reshape(theta, -1, order='F').copy()).cuda()
+        for _ in range(2):
+            out = sh.apply(th)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(a.steps):
+            out = sh.apply(th)
+        e1.record(); torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item()) / a.steps
+        flops = 8.0 * (2.0 * chi ** 3 * d * d * w + 2.0 * chi ** 2 * d ** 3 * w * w)
+        err = None
+        if a.check and rank == 0:
+            want = np.einsum('awb,wstx,xuvy,btvc,eyc->asue', L, M1, M2, theta, R) if chi <= 256 else None
+            if want is not None:
+                got = out.cpu().numpy().reshape(chi, d, d, chi, order='F')
+                err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
+        chk = float(torch.view_as_real(out).abs().sum().item())
+        if rank == 0:
+            print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "ms_per_matvec": sec * 1e3,
+                              "tflops_total": flops / sec / 1e12, "checksum": chk, "rel_err_vs_einsum": err,
+                              "collectives": "NCCL reduce_scatter(T2 over w2) + all_reduce(out)" if world > 1 else "none"}), flush=True)
+    else:
+        Nn, chi = a.sites, a.chi
+        X, Z, I2, SM = tnb200.models.X, tnb200.models.Z, tnb200.models.I2, tnb200.models.SM
+        gamma, dt = 0.1, 5e-3
+        # H_eff = -iH - 1/2 sum gamma n  (qjmc.jl:9-26) with H = sum (x + 20 z) + 10 sum zz (examples/qjmc.jl couplings)
+        onsite = -1j * (1.0 * X + 20.0 * Z) - 0.5 * gamma * (SM.conj().T @ SM)
+        bond = -1j * 10.0 * np.kron(Z, Z)
+        ss, gg = tnb200.models.trotter_gates(Nn, onsite, bond, dt, evol="imag", order=2)
+        tens = tnb200.models.random_canonical_mps(Nn, d, chi, seed=1)
+        import threading
+        tl = threading.local()
+
+        def run(t):
+            if not hasattr(tl, "ctx"):
+                tl.ctx = tnb200.Context(local)
+                tl.gates = tnb200.GateList(d, ss, gg, ctx=tl.ctx)
+            psi = tnb200.GMPS(1, d, tens, 1, ctx=tl.ctx)
+            jumps, times, obs = tnb200.qjmc_simulation(psi, tl.gates, list(range(1, Nn + 1)), [SM] * Nn, [np.sqrt(gamma)] * Nn, a.steps, dt,
+                                                       seed=0, trajectory=t, obs_op=Z, save_every=a.steps, cutoff=0.0, maxdim=chi)
+            return len(jumps), float(np.real(obs[-1]).sum())
+        run_ensemble(run, min(a.workers, a.traj) * world, rank, world, dist if world > 1 else None, workers=a.workers)   # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        res = run_ensemble(run, a.traj, rank, world, dist if world > 1 else None, workers=a.workers)
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+        if rank == 0:
+            print(json.dumps({"what": "qjmc_ensemble", "n_gpus": world, "sites": Nn, "chi": chi, "steps_per_traj": a.steps, "trajectories": a.traj,
+                              "workers_per_gpu": a.workers, "seconds": sec, "traj_per_s": a.traj / sec, "traj_steps_per_s": a.traj * a.steps / sec,
+                              "jumps_total": int(sum(v[0] for v in res.values())), "sum_z_mean": float(np.mean([v[1] for v in res.values()]))}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
