@@ -59,7 +59,12 @@ def main():
         flops = 8.0 * (2.0 * chi ** 3 * d * d * w + 2.0 * chi ** 2 * d ** 3 * w * w)
         err = None
         if a.check and rank == 0:
-            want = np.einsum('awb,wstx,xuvy,btvc,eyc->asue', L, M1, M2, theta, R) if chi <= 256 else None
+            want = None
+            if chi <= 512:
+                T = np.tensordot(L, theta, axes=([2], [0]))
+                Wd = np.tensordot(M1, M2, axes=([3], [0]))
+                T = np.tensordot(T, Wd, axes=([1, 2, 3], [0, 2, 4]))
+                want = np.tensordot(T, R, axes=([4, 1], [1, 2]))
             if want is not None:
                 got = out.cpu().numpy().reshape(chi, d, d, chi, order='F')
                 err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
