@@ -78,6 +78,9 @@ int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_
 int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t trunc,
                      tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
 
+/* tuning switch (process-wide): 1 = QR-preconditioned Jacobi (default), 0 = plain Jacobi */
+int32_t tn_svd_set_precond(int32_t mode);
+
 /* ---- contraction: tensors.jl:9-18 restricted to the strided-GEMM form the hot path uses ------- */
 /* C[m,n] = alpha * sum_k op(A)[m,k] op(B)[k,n]; each of m, n, k is a fused pair of tensor indices
  * (extent n0 x rest) with element strides (s0, s1); conj flags as the reference's conjx/conjy. */

@@ -167,6 +167,8 @@ int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_t
   });
 }
 
+int32_t tn_svd_set_precond(int32_t mode) { return guard([&] { svd_set_precond(mode); }); }
+
 static Idx2 I2(tn_idx2_t i) { return Idx2{(int)std::min<int64_t>(i.n0, 0x7fffffff), (long long)i.s0, (long long)i.s1, nullptr, 0}; }
 
 int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const tn_cplx* A, int64_t ae, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,

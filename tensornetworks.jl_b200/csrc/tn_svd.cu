@@ -247,6 +247,132 @@ __global__ void __launch_bounds__(256) gather_kernel(const cplx* __restrict__ sr
   }
 }
 
+// ---- QR preconditioner kernels ----------------------------------------------------------------
+// Shifted Cholesky of one 64x64 Gram matrix (sum of split-K partials) in shared memory, inverse of the
+// triangular factor, and accumulation of the panel's R over the CholeskyQR passes:
+//   G (+ shift I) = R^H R ;  Rinv = R^-1 ;  Rtot <- R * Rtot      (pass 0: Rtot = R, with the shift)
+// Exactly-zero columns (padding, product states) are kept as null columns: pivot 1, row/column 0, and their
+// row of Rtot is zeroed after the last pass.  A failed pivot in later passes leaves that column untouched.
+__global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
+                                                             cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot, int pass, int last_pass,
+                                                             double shift_factor) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);
+  cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));
+  __shared__ double red[8];
+  __shared__ int nullcol[JP];
+  __shared__ double piv;
+  const int tid = threadIdx.x;
+  double fro = 0;
+  for (int e = tid; e < JP * JP; e += 256) {
+    int row = e % JP, col = e / JP;
+    double xr = 0, xi = 0;
+    for (int s = 0; s < nsplit; ++s) { cplx v = Gpart[s * split_stride + e]; xr += v.x; xi += v.y; }
+    G[row][col] = make_double2(xr, xi);
+    fro += xr * xr + xi * xi;
+  }
+  for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
+  if ((tid & 31) == 0) red[tid >> 5] = fro;
+  __syncthreads();
+  fro = 0; for (int i = 0; i < 8; ++i) fro += red[i];
+  const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
+  if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
+  __syncthreads();
+  // symmetrise + shift
+  for (int e = tid; e < JP * JP; e += 256) {
+    int row = e % JP, col = e / JP;
+    if (row < col) {
+      cplx a = G[row][col], b = G[col][row];
+      cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+      G[row][col] = h; G[col][row] = make_double2(h.x, -h.y);
+    } else if (row == col) { G[row][col].x += shift; G[row][col].y = 0; }
+  }
+  __syncthreads();
+  // right-looking Cholesky, upper factor stored in the upper triangle of G (row j = R(j, j:))
+  for (int j = 0; j < JP; ++j) {
+    if (tid == 0) {
+      double dd = G[j][j].x;
+      if (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) { piv = 0.0; }
+      else piv = sqrt(dd);
+    }
+    __syncthreads();
+    double r = piv;
+    if (r == 0.0) {   // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0, no trailing update
+      if (tid == 0) G[j][j] = make_double2(1.0, 0.0);
+      for (int c = j + 1 + tid; c < JP; c += 256) G[j][c] = make_double2(0, 0);
+      __syncthreads();
+      continue;
+    }
+    if (tid == 0) G[j][j] = make_double2(r, 0.0);
+    for (int c = j + 1 + tid; c < JP; c += 256) { cplx v = G[j][c]; G[j][c] = make_double2(v.x / r, v.y / r); }
+    __syncthreads();
+    int nt = JP - 1 - j;
+    for (int e = tid; e < nt * nt; e += 256) {
+      int i = j + 1 + e / nt, c = j + 1 + e % nt;
+      if (c >= i) { cplx a = G[j][i], b = G[j][c]; cplx pr = make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);   // conj(R(j,i)) R(j,c)
+        G[i][c].x -= pr.x; G[i][c].y -= pr.y; }
+    }
+    __syncthreads();
+  }
+  // zero the strictly lower triangle (R is upper triangular)
+  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; if (row > col) G[row][col] = make_double2(0, 0); }
+  __syncthreads();
+  // Rinv by back substitution, one column per thread
+  if (tid < JP) {
+    int c = tid;
+    for (int i = JP - 1; i >= 0; --i) {
+      cplx acc = make_double2(i == c ? 1.0 : 0.0, 0.0);
+      if (i > c) { Ri[i][c] = make_double2(0, 0); continue; }
+      for (int k = i + 1; k <= c; ++k) { cplx a = G[i][k], b = Ri[k][c]; acc.x -= a.x * b.x - a.y * b.y; acc.y -= a.x * b.y + a.y * b.x; }
+      double d = G[i][i].x;
+      Ri[i][c] = make_double2(acc.x / d, acc.y / d);
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
+  // Rtot <- R * Rtot  (Ri reused as the old Rtot)
+  __syncthreads();
+  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Ri[row][col] = pass == 0 ? make_double2(row == col ? 1.0 : 0.0, 0.0) : Rtot[e]; }
+  __syncthreads();
+  for (int e = tid; e < JP * JP; e += 256) {
+    int row = e % JP, col = e / JP;
+    double xr = 0, xi = 0;
+    for (int k = row; k < JP; ++k) { cplx a = G[row][k], b = Ri[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+    if (last_pass && nullcol[row]) { xr = 0; xi = 0; }
+    Rtot[e] = make_double2(xr, xi);
+  }
+}
+
+// out(rows x cols, leading dim ldo) (+)= sum_s part[s] ; part[s] is rows x cols contiguous
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, long long split_stride, int rows, int cols,
+                                                               cplx* __restrict__ out, long long ldo, int accumulate) {
+  long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    double xr = 0, xi = 0;
+    for (int s = 0; s < nsplit; ++s) { cplx v = part[s * split_stride + e]; xr += v.x; xi += v.y; }
+    cplx* o = out + (e % rows) + (e / rows) * ldo;
+    if (accumulate) { xr += o->x; xi += o->y; }
+    *o = make_double2(xr, xi);
+  }
+}
+// dst(c, r) = conj(src(r, c)): dst is cols x rows (ldd), src rows x cols (lds); optional zero fill beyond (rows_valid, cols_valid)
+__global__ void __launch_bounds__(256) conj_transpose_kernel(const cplx* __restrict__ src, long long lds, int rows, int cols,
+                                                              cplx* __restrict__ dst, long long ldd) {
+  long long total = (long long)rows * cols;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(e % cols), r = (int)(e / cols);
+    cplx v = src[r + (long long)c * lds];
+    dst[c + (long long)r * ldd] = make_double2(v.x, -v.y);
+  }
+}
+__global__ void __launch_bounds__(256) set_identity_kernel(cplx* __restrict__ dst, long long ld, int n) {
+  long long total = (long long)n * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(e % n), c = (int)(e / n);
+    dst[r + (long long)c * ld] = make_double2(r == c ? 1.0 : 0.0, 0.0);
+  }
+}
+
 // ---- host driver ------------------------------------------------------------------------------
 template <class T>
 static void ensure(T*& p, size_t& cap, size_t need, cudaStream_t s) {
@@ -278,51 +404,33 @@ static const int* pair_table(SvdWork& w, int nb, cudaStream_t s) {
   return d;
 }
 
-int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
-  TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
-  w.m = m; w.n = n;
-  w.transposed = m < n;
-  w.rows = w.transposed ? n : m;
-  w.ncols = w.transposed ? m : n;
-  w.nsv = w.ncols;
-  w.ncols_pad = ((w.ncols + JP - 1) / JP) * JP;
-  w.ldz = w.rows + w.ncols_pad;
-  TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
-  const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
-  ensure(w.Z, w.Z_cap, (size_t)w.ldz * w.ncols_pad, s);
-  // split-K so that the Gram GEMMs fill the 148 SMs
-  int ksplit = std::max(1, std::min(16, (2 * 148 + np - 1) / np));
-  int kchunk = ((w.rows + ksplit - 1) / ksplit + 7) / 8 * 8;
-  ksplit = (w.rows + kchunk - 1) / kchunk;
-  ensure(w.Gpart, w.G_cap, (size_t)ksplit * np * JP * JP, s);
-  ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
-  if (w.s_cap < (size_t)w.ncols_pad) {
-    if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
-    TN_CUDA(cudaMallocAsync((void**)&w.sig, w.ncols_pad * sizeof(double), s));
-    TN_CUDA(cudaMallocAsync((void**)&w.sig2, w.ncols_pad * sizeof(double), s));
-    TN_CUDA(cudaMallocAsync((void**)&w.perm, w.ncols_pad * sizeof(int), s));
-    w.s_cap = w.ncols_pad;
-  }
-  if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); }
-  const int* tab = pair_table(w, nb, s);
+static int g_precond_mode = -1;   // -1: read TN_SVD_PRECOND once (default on)
+void svd_set_precond(int mode) { g_precond_mode = mode ? 1 : 0; }
+static bool precond_enabled() {
+  if (g_precond_mode < 0) { const char* e = getenv("TN_SVD_PRECOND"); g_precond_mode = (e && e[0] == '0') ? 0 : 1; }
+  return g_precond_mode == 1;
+}
 
-  {
-    long long total = (long long)w.ldz * w.ncols_pad;
-    int blocks = (int)std::min<long long>(148 * 8, (total + 255) / 256);
-    svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Z, w.rows, w.ncols, w.ncols_pad, w.ldz);
-    TN_CUDA(cudaGetLastError());
-    count_launch(1);
-  }
+static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
+
+// Jacobi sweeps on Z = [W ; V] (W: jrows x ncols_pad, V: ncols_pad x ncols_pad), leading dimension ldz.
+static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
+  const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
+  int ksplit = std::max(1, std::min(16, (2 * 148 + np - 1) / np));
+  int kchunk = ((jrows + ksplit - 1) / ksplit + 7) / 8 * 8;
+  ksplit = (jrows + kchunk - 1) / kchunk;
+  ensure(w.Gpart, w.G_cap, (size_t)std::max(ksplit, 16) * np * JP * JP, s);
+  ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
+  const int* tab = pair_table(w, nb, s);
   static bool evd_cfg = false;
   const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
   if (!evd_cfg) { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem)); evd_cfg = true; }
-
-  const double tol = std::sqrt((double)w.rows) * 2.220446049250313e-16;
+  const double tol = std::sqrt((double)jrows) * 2.220446049250313e-16;
   const long long colblk = (long long)JB * w.ldz;
   const int max_sweeps = 60;
   // One inner sweep per visit gives the same number of outer sweeps as a full inner diagonalisation
-  // (measured with tools/jacobi_emul.py) at 1/8 of the cost and with less rounding accumulated in V;
-  // a single pair (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
+  // (tools/jacobi_emul.py) at 1/8 of the cost and with less rounding accumulated in V; a single pair
+  // (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
   const int inner_sweeps = (np == 1) ? 12 : 1;
   w.sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
@@ -331,7 +439,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
       const int* tb = tab + (size_t)st * np * 2;
       Idx2 cols{JB, (long long)w.ldz, colblk, tb, 2};
       GemmDesc g{};
-      g.M = JP; g.N = JP; g.K = w.rows;
+      g.M = JP; g.N = JP; g.K = jrows;
       g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
       g.B = w.Z; g.bk = idx1(1); g.bn = cols; g.conjB = 0;
       g.C = w.Gpart; g.cm = idx1(1); g.cn = idx1(JP);
@@ -360,11 +468,130 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
     w.sweeps = sweep + 1;
     if (off <= tol) break;
   }
-  colnorm2_kernel<<<w.ncols_pad, 128, 0, s>>>(w.Z, w.rows, w.ldz, w.sig2);
-  int npow2 = 64; while (npow2 < w.ncols_pad) npow2 <<= 1;
+}
+
+static GemmDesc gd(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int conjA, const cplx* B, Idx2 bk, Idx2 bn, int conjB,
+                   cplx* C, Idx2 cm, Idx2 cn, double alpha = 1.0, double beta = 0.0) {
+  GemmDesc g{};
+  g.M = M; g.N = N; g.K = K; g.A = A; g.am = am; g.ak = ak; g.conjA = conjA; g.B = B; g.bk = bk; g.bn = bn; g.conjB = conjB;
+  g.C = C; g.cm = cm; g.cn = cn; g.alpha = make_double2(alpha, 0); g.beta = make_double2(beta, 0);
+  g.batch = 1; g.ksplit = 1; g.kchunk = K;
+  return g;
+}
+
+// One pass of right-looking block Gram-Schmidt QR with shifted-CholeskyQR3 panels (64 columns):
+//   Q (rows x npad, ld = ldq) is overwritten by the orthonormal factor, R (npad x npad, ld = npad) receives the
+//   upper-triangular factor.  Everything is GEMM-shaped (tn_zgemm.cu) plus the 64x64 Cholesky kernel.
+static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, cudaStream_t s) {
+  static bool cfg = false;
+  const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
+  if (!cfg) { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); cfg = true; }
+  TN_CUDA(cudaMemsetAsync(R, 0, (size_t)npad * npad * sizeof(cplx), s));
+  ensure(w.Gpart, w.G_cap, (size_t)16 * JP * JP, s);
+  int ksplit = std::max(1, std::min(16, rows / 256));
+  int kchunk = ((rows + ksplit - 1) / ksplit + 7) / 8 * 8;
+  ksplit = (rows + kchunk - 1) / kchunk;
+  cplx* Rinv = w.small; cplx* Rtot = w.small + JP * JP;
+  const double shift_factor = 11.0 * ((double)rows * JP + (double)JP * (JP + 1)) * 2.220446049250313e-16;
+  const int npanels = npad / JP;
+  for (int pk = 0; pk < npanels; ++pk) {
+    cplx* P = Q + (long long)pk * JP * ldq;
+    for (int it = 0; it < 3; ++it) {
+      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
+      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)JP * JP;
+      zgemm_auto(g, s);
+      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, ksplit, (long long)JP * JP, Rinv, Rtot, it, it == 2 ? 1 : 0, shift_factor);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      // P <- P * Rinv (in place: each CTA owns 128 rows x all 64 columns)
+      zgemm_auto(gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq)), s);
+    }
+    // R(pk,pk) = Rtot
+    TN_CUDA(cudaMemcpy2DAsync(R + (long long)pk * JP + (long long)pk * JP * npad, (size_t)npad * sizeof(cplx), Rtot, (size_t)JP * sizeof(cplx),
+                              (size_t)JP * sizeof(cplx), JP, cudaMemcpyDeviceToDevice, s));
+    int nt = npad - (pk + 1) * JP;
+    if (nt > 0) {
+      cplx* T = Q + (long long)(pk + 1) * JP * ldq;
+      // C = P^H T  (64 x nt), split-K partials -> R(pk, trail)
+      ensure(w.Cpart, w.Cpart_cap, (size_t)ksplit * JP * nt, s);
+      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, w.Cpart, idx1(1), idx1(JP));
+      c.ksplit = ksplit; c.kchunk = kchunk; c.ssC = (long long)JP * nt;
+      zgemm_auto(c, s);
+      cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
+      int blocks; launch_1d((long long)JP * nt, blocks);
+      reduce_partials_kernel<<<blocks, 256, 0, s>>>(w.Cpart, ksplit, (long long)JP * nt, JP, nt, Rrow, npad, 0);
+      count_launch(1);
+      // T <- T - P C
+      zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
+    }
+  }
+}
+
+// Q <- orthonormal factor, Ra <- R with A = Q R; two Gram-Schmidt passes ("twice is enough"), R = R'' R'.
+static void bgs_qr(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cudaStream_t s) {
+  ensure(w.Ra, w.Ra_cap, (size_t)npad * npad, s);
+  ensure(w.Rb, w.Rb_cap, (size_t)npad * npad, s);
+  ensure(w.Rc, w.Rc_cap, (size_t)npad * npad, s);
+  bgs_pass(w, Q, ldq, rows, npad, w.Rc, s);       // R'
+  bgs_pass(w, Q, ldq, rows, npad, w.Rb, s);       // R''
+  zgemm_auto(gd(npad, npad, npad, w.Rb, idx1(1), idx1(npad), 0, w.Rc, idx1(1), idx1(npad), 0, w.Ra, idx1(1), idx1(npad)), s);
+}
+
+int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+  TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
+  w.m = m; w.n = n;
+  w.transposed = m < n;
+  w.rows = w.transposed ? n : m;
+  w.ncols = w.transposed ? m : n;
+  w.nsv = w.ncols;
+  w.ncols_pad = ((w.ncols + JP - 1) / JP) * JP;
+  TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
+  const int npad = w.ncols_pad;
+  w.precond = precond_enabled() && npad > JP;
+  if (w.s_cap < (size_t)npad) {
+    if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
+    TN_CUDA(cudaMallocAsync((void**)&w.sig, npad * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.sig2, npad * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.perm, npad * sizeof(int), s));
+    w.s_cap = npad;
+  }
+  if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
+  int blocks;
+  if (!w.precond) {
+    w.jrows = w.rows;
+    w.ldz = w.rows + npad;
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
+    launch_1d((long long)w.ldz * npad, blocks);
+    svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Z, w.rows, w.ncols, npad, w.ldz);
+    TN_CUDA(cudaGetLastError());
+    count_launch(1);
+    jacobi_sweeps(w, w.rows, s);
+  } else {
+    // A = Q1 R1 ; R1^H = Q2 R2 ; X = R2^H ;  X V' = U' Sigma  =>  A = (Q1 U') Sigma (Q2 V')^H
+    ensure(w.Q1, w.Q1_cap, (size_t)w.rows * npad, s);
+    launch_1d((long long)w.rows * npad, blocks);
+    svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Q1, w.rows, w.ncols, npad, w.rows);   // ldz = rows: no identity part
+    count_launch(1);
+    bgs_qr(w, w.Q1, w.rows, w.rows, npad, s);                    // Ra = R1
+    ensure(w.Q2, w.Q2_cap, (size_t)npad * npad, s);
+    launch_1d((long long)npad * npad, blocks);
+    conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Q2, npad);   // Q2 <- R1^H
+    count_launch(1);
+    bgs_qr(w, w.Q2, npad, npad, npad, s);                        // Ra = R2
+    w.jrows = npad;
+    w.ldz = 2 * npad;
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
+    conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Z, w.ldz);   // W <- R2^H
+    set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
+    TN_CUDA(cudaGetLastError());
+    count_launch(2);
+    jacobi_sweeps(w, npad, s);
+  }
+  colnorm2_kernel<<<npad, 128, 0, s>>>(w.Z, w.jrows, w.ldz, w.sig2);
+  int npow2 = 64; while (npow2 < npad) npow2 <<= 1;
   static bool sort_cfg = false;
   if (!sort_cfg) { TN_CUDA(cudaFuncSetAttribute(sort_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12)); sort_cfg = true; }
-  sort_trunc_kernel<<<1, 1024, npow2 * 12, s>>>(w.sig2, w.ncols_pad, npow2, w.sig, w.perm, w.nsv, tr.cutoff, tr.maxdim, tr.mindim, w.kout);
+  sort_trunc_kernel<<<1, 1024, npow2 * 12, s>>>(w.sig2, npad, npow2, w.sig, w.perm, w.nsv, tr.cutoff, tr.maxdim, tr.mindim, w.kout);
   TN_CUDA(cudaGetLastError());
   count_launch(2);
   int k = 0;
@@ -382,11 +609,38 @@ static void gather(const cplx* src, int lds, int rows, int k, const int* perm, c
   count_launch(1);
 }
 
+// With the preconditioner the Jacobi factors live in the small n x n problem:
+//   left vectors of A:  Q1 * (W/sigma)(:,perm)   right vectors of A:  Q2 * V(:,perm)
+static void precond_left(SvdWork& w, int scale_mode, cplx* out, long long ldo, bool conj_transposed, cudaStream_t s) {
+  const int npad = w.ncols_pad, k = w.k;
+  ensure(w.Tg, w.Tg_cap, (size_t)npad * std::max(k, 1), s);
+  gather(w.Z, w.ldz, npad, k, w.perm, w.sig, scale_mode, 0, w.Tg, npad, s);                 // (W * scale)(:, perm)
+  if (!conj_transposed) zgemm_auto(gd(w.rows, k, npad, w.Q1, idx1(1), idx1(w.rows), 0, w.Tg, idx1(1), idx1(npad), 0, out, idx1(1), idx1(ldo)), s);
+  else zgemm_auto(gd(k, w.rows, npad, w.Tg, idx1(npad), idx1(1), 1, w.Q1, idx1(w.rows), idx1(1), 1, out, idx1(1), idx1(ldo)), s);
+}
+static void precond_right(SvdWork& w, int scale_mode, cplx* out, long long ldo, bool conj_transposed, cudaStream_t s) {
+  const int npad = w.ncols_pad, k = w.k;
+  ensure(w.Tg, w.Tg_cap, (size_t)npad * std::max(k, 1), s);
+  gather(w.Z + npad, w.ldz, npad, k, w.perm, w.sig, scale_mode, 0, w.Tg, npad, s);          // (V * scale)(:, perm)
+  if (!conj_transposed) zgemm_auto(gd(w.ncols, k, npad, w.Q2, idx1(1), idx1(npad), 0, w.Tg, idx1(1), idx1(npad), 0, out, idx1(1), idx1(ldo)), s);
+  else zgemm_auto(gd(k, w.ncols, npad, w.Tg, idx1(npad), idx1(1), 1, w.Q2, idx1(npad), idx1(1), 1, out, idx1(1), idx1(ldo)), s);
+}
+
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
+  if (w.precond) {
+    if (!w.transposed) precond_left(w, times_S ? 0 : 2, U, ldu, false, s);       // Q1 (W[/sigma])
+    else precond_right(w, times_S ? 1 : 0, U, ldu, false, s);                    // Q2 (V[*sigma])
+    return;
+  }
   if (!w.transposed) gather(w.Z, w.ldz, w.m, w.k, w.perm, w.sig, times_S ? 0 : 2, 0, U, ldu, s);          // W / sigma
   else gather(w.Z + w.rows, w.ldz, w.m, w.k, w.perm, w.sig, times_S ? 1 : 0, 0, U, ldu, s);                // V' (* sigma)
 }
 void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream_t s) {
+  if (w.precond) {
+    if (!w.transposed) precond_right(w, times_S ? 1 : 0, Vh, ldv, true, s);      // (Q2 V[*sigma])^H
+    else precond_left(w, times_S ? 0 : 2, Vh, ldv, true, s);                     // (Q1 W[/sigma])^H
+    return;
+  }
   if (!w.transposed) gather(w.Z + w.rows, w.ldz, w.n, w.k, w.perm, w.sig, times_S ? 1 : 0, 1, Vh, ldv, s); // conj(V)^T (* sigma)
   else gather(w.Z, w.ldz, w.n, w.k, w.perm, w.sig, times_S ? 0 : 2, 1, Vh, ldv, s);                        // conj(W'/sigma)^T
 }
@@ -398,7 +652,8 @@ void svd_free(SvdWork& w) {
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
-  if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); }
+  if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); }
+  for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Cpart, w.Tg}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
   w = SvdWork{};
 }

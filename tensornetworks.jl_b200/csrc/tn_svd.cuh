@@ -17,6 +17,16 @@ struct SvdWork {
   unsigned long long* offmax = nullptr;            // convergence measure (double bits)
   int* kout = nullptr;                             // device-side truncation rank
   std::map<int, int*> tables;                      // round-robin pair tables per block count
+  // QR preconditioner (two GEMM-based QR factorisations: A = Q1 R1, R1^H = Q2 R2, Jacobi on X = R2^H)
+  cplx* Q1 = nullptr; size_t Q1_cap = 0;           // rows x ncols_pad
+  cplx* Q2 = nullptr; size_t Q2_cap = 0;           // ncols_pad x ncols_pad
+  cplx* Ra = nullptr; size_t Ra_cap = 0;           // R of the current factorisation (ncols_pad^2)
+  cplx* Rb = nullptr; size_t Rb_cap = 0;           // second-pass R / scratch
+  cplx* Rc = nullptr; size_t Rc_cap = 0;           // product scratch
+  cplx* small = nullptr;                           // 3 x 64x64: Rinv, Rtot, scratch
+  cplx* Cpart = nullptr; size_t Cpart_cap = 0;     // split-K partials of the projection coefficients
+  cplx* Tg = nullptr; size_t Tg_cap = 0;           // gathered / scaled singular-vector block (ncols_pad x k)
+  bool precond = false; int jrows = 0;             // Jacobi ran on an jrows x ncols_pad matrix
   // description of the last factorisation
   int m = 0, n = 0, rows = 0, ncols = 0, ncols_pad = 0, ldz = 0, nsv = 0, k = 0, sweeps = 0;
   bool transposed = false;
@@ -33,5 +43,6 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
 // first k singular values (device -> device copy)
 void svd_copy_S(SvdWork& w, double* S, cudaStream_t s);
 void svd_free(SvdWork& w);
+void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn

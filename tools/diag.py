@@ -16,6 +16,32 @@ def crandn(*s):
     return rng.standard_normal(s) + 1j * rng.standard_normal(s)
 
 what = sys.argv[1:] or ["svd", "matvec"]
+if "svdmodes" in what:
+    def mk(kind, n):
+        if kind == "randn": return crandn(n, n)
+        if kind == "hidden":
+            u, _ = np.linalg.qr(crandn(n, n)); v, _ = np.linalg.qr(crandn(n, n)); return (u * np.exp(-np.arange(n) * 30.0 / n)) @ v.conj().T
+        if kind == "visible":
+            lam = np.exp(-np.arange(n // 2) * 28.0 / (n // 2)); return (np.tile(lam, 2)[:, None] * crandn(n, n)) * np.tile(lam, 2)[None, :]
+        if kind == "rankdef": return crandn(n, n // 2) @ crandn(n // 2, n)
+        if kind == "tall": return crandn(2 * n, n) * np.exp(-np.arange(n) * 20.0 / n)[None, :]
+    for n in [int(a) for a in os.environ.get("SVD_N", "256,1024").split(",")]:
+        for kind in ("randn", "hidden", "visible", "rankdef", "tall"):
+            x = mk(kind, n)
+            so = np.linalg.svd(x, compute_uv=False)
+            for mode in (1, 0):
+                if mode == 0 and kind in ("hidden", "visible") and n > 512: continue
+                ctx.lib.tn_svd_set_precond(mode)
+                tnb200.svd(x, 2)
+                t1 = time.perf_counter()
+                U, S, V, sw = tnb200.svd(x, 2, return_sweeps=True)
+                t2 = time.perf_counter()
+                s = np.real(np.diag(S)); k = int(np.sum(so > 1e-13 * so[0]))
+                print(dict(kind=kind, n=n, precond=mode, sweeps=sw, wall_s=round(t2 - t1, 4), sv_err=float(np.max(np.abs(s - so)) / so[0]),
+                           recon=float(np.linalg.norm(U @ S @ V - x) / np.linalg.norm(x)),
+                           orthU=float(np.linalg.norm(U[:, :k].conj().T @ U[:, :k] - np.eye(k))), orthV=float(np.linalg.norm(V[:k] @ V[:k].conj().T - np.eye(k)))), flush=True)
+    ctx.lib.tn_svd_set_precond(1)
+
 if "svd" in what:
     for n in [int(a) for a in os.environ.get("SVD_N", "256,512,1024,2048").split(",")]:
         x = crandn(n, n)
