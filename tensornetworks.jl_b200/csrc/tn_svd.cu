@@ -34,8 +34,12 @@ __device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) 
   p = min(a, b); q = max(a, b);
 }
 
-__global__ void __launch_bounds__(256, 1) jacobi_evd64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
-                                                               cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner) {
+// One CTA (1024 threads) per column-block pair.  Per rotation step: 32 threads compute the 32 disjoint
+// rotations, then every thread applies both the row- and the column-rotation to one 2x2 block of G
+// (G' = R_a^H G_ab R_b) and the column rotation to two (row, pair) items of J: two barriers per step.
+constexpr int EVD_THREADS = 1024;
+__global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
+                                                                       cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cplx* G = reinterpret_cast<cplx*>(sm_raw);     // G[row*LDS_ + col]
   cplx* J = G + JP * LDS_;
@@ -43,10 +47,10 @@ __global__ void __launch_bounds__(256, 1) jacobi_evd64_kernel(const cplx* __rest
   __shared__ cplx r_s[JB];
   __shared__ int r_p[JB], r_q[JB];
   __shared__ int rotated;
-  __shared__ double red[8];
+  __shared__ double red[32];
   const int tid = threadIdx.x;
   const cplx* gp = Gpart + (long long)blockIdx.x * JP * JP;
-  for (int e = tid; e < JP * JP; e += 256) {
+  for (int e = tid; e < JP * JP; e += EVD_THREADS) {
     int row = e % JP, col = e / JP;
     double xr = 0, xi = 0;
     for (int s = 0; s < nsplit; ++s) { cplx v = gp[s * split_stride + e]; xr += v.x; xi += v.y; }
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(256, 1) jacobi_evd64_kernel(const cplx* __rest
   __syncthreads();
   // symmetrise (the two triangles come from different DMMA accumulation orders) and measure off-diagonals
   double mx = 0;
-  for (int e = tid; e < JP * JP; e += 256) {
+  for (int e = tid; e < JP * JP; e += EVD_THREADS) {
     int row = e % JP, col = e / JP;
     if (row < col) {
       cplx a = G[row * LDS_ + col], b = G[col * LDS_ + row];
@@ -64,23 +68,24 @@ __global__ void __launch_bounds__(256, 1) jacobi_evd64_kernel(const cplx* __rest
       G[row * LDS_ + col] = h;
       G[col * LDS_ + row] = make_double2(h.x, -h.y);
       double dd = G[row * LDS_ + row].x * G[col * LDS_ + col].x;
-      double off = sqrt(h.x * h.x + h.y * h.y);
-      if (dd > 0) mx = fmax(mx, off / sqrt(dd));
-      else if (off > 0) mx = fmax(mx, 1.0);
+      double off2 = h.x * h.x + h.y * h.y;
+      if (dd > 0) mx = fmax(mx, off2 / dd);
+      else if (off2 > 0) mx = fmax(mx, 1.0);
     }
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((tid & 31) == 0) red[tid >> 5] = mx;
   __syncthreads();
   mx = red[0];
-  for (int i = 1; i < 8; ++i) mx = fmax(mx, red[i]);
+  for (int i = 1; i < EVD_THREADS / 32; ++i) mx = fmax(mx, red[i]);
+  mx = sqrt(mx);
   if (tid == 0) atomicMax(offmax, (unsigned long long)__double_as_longlong(mx));
   cplx* jo = Jout + (long long)blockIdx.x * JP * JP;
   if (mx <= tol) {   // already orthogonal: identity rotation
-    for (int e = tid; e < JP * JP; e += 256) jo[e] = make_double2((e % JP) == (e / JP) ? 1.0 : 0.0, 0.0);
+    for (int e = tid; e < JP * JP; e += EVD_THREADS) jo[e] = make_double2((e % JP) == (e / JP) ? 1.0 : 0.0, 0.0);
     return;
   }
-  __syncthreads();
+  const double tol2 = tol * tol;
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     if (tid == 0) rotated = 0;
     __syncthreads();
@@ -89,63 +94,57 @@ __global__ void __launch_bounds__(256, 1) jacobi_evd64_kernel(const cplx* __rest
         int p, q; rr_pair(JP, step, tid, p, q);
         double a = G[p * LDS_ + p].x, b = G[q * LDS_ + q].x;
         cplx c = G[p * LDS_ + q];
-        double absc = hypot(c.x, c.y);
+        double absc2 = c.x * c.x + c.y * c.y;
         double cs = 1.0; cplx s = make_double2(0, 0);
-        if (absc > tol * sqrt(fabs(a * b)) && absc > 0) {
-          double zeta = (b - a) / (2.0 * absc);
+        if (absc2 > tol2 * fabs(a * b) && absc2 > 0) {
+          double iabs = rsqrt(absc2), absc = absc2 * iabs;
+          double zeta = (b - a) * 0.5 * iabs;
           double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          cs = 1.0 / sqrt(1.0 + t * t);
-          double sn = cs * t;
-          s = make_double2(sn * c.x / absc, sn * c.y / absc);
+          cs = rsqrt(1.0 + t * t);
+          double sn = cs * t * iabs;
+          s = make_double2(sn * c.x, sn * c.y);
+          (void)absc;
           rotated = 1;
         }
         r_cs[tid] = cs; r_s[tid] = s; r_p[tid] = p; r_q[tid] = q;
       }
       __syncthreads();
-      // phase 1: columns p,q of G and J:  [x y] <- [x y] * R,  R = [[cs, s], [-conj(s), cs]]
-#pragma unroll 4
-      for (int it = 0; it < (JB * JP * 2) / 256; ++it) {
-        int item = tid + it * 256;
-        int k = item >> 7, rem = item & 127, row = rem & 63;
-        cplx* Mx = (rem >> 6) ? J : G;
-        double cs = r_cs[k]; cplx s = r_s[k];
-        if (s.x == 0.0 && s.y == 0.0) continue;
-        int p = r_p[k], q = r_q[k];
-        cplx x = Mx[row * LDS_ + p], y = Mx[row * LDS_ + q];
-        cplx ys = cmulc(y, s), xs = cmul(x, s);
-        Mx[row * LDS_ + p] = make_double2(cs * x.x - ys.x, cs * x.y - ys.y);
-        Mx[row * LDS_ + q] = make_double2(xs.x + cs * y.x, xs.y + cs * y.y);
-      }
-      __syncthreads();
-      // phase 2: rows p,q of G:  [x; y] <- R^H [x; y] = [cs*x - s*y ; conj(s)*x + cs*y]
-#pragma unroll 4
-      for (int it = 0; it < (JB * JP) / 256; ++it) {
-        int item = tid + it * 256;
-        int k = item >> 6, col = item & 63;
-        double cs = r_cs[k]; cplx s = r_s[k];
-        if (s.x == 0.0 && s.y == 0.0) continue;
-        int p = r_p[k], q = r_q[k];
-        cplx x = G[p * LDS_ + col], y = G[q * LDS_ + col];
-        cplx sy = cmul(s, y), cx = cmulc(x, s);   // cx = x*conj(s)
-        G[p * LDS_ + col] = make_double2(cs * x.x - sy.x, cs * x.y - sy.y);
-        G[q * LDS_ + col] = make_double2(cx.x + cs * y.x, cx.y + cs * y.y);
-      }
-      __syncthreads();
-      if (tid < JB) {
-        cplx s = r_s[tid];
-        if (!(s.x == 0.0 && s.y == 0.0)) {
-          int p = r_p[tid], q = r_q[tid];
-          G[p * LDS_ + q] = make_double2(0, 0);
-          G[q * LDS_ + p] = make_double2(0, 0);
-          G[p * LDS_ + p].y = 0; G[q * LDS_ + q].y = 0;
+      {
+        // G block (pair a rows, pair b cols): G' = R_a^H (G R_b),  R = [[cs, s], [-conj(s), cs]]
+        int a = tid >> 5, b = tid & 31;
+        double ca = r_cs[a], cb = r_cs[b]; cplx sa = r_s[a], sb = r_s[b];
+        bool ra = !(sa.x == 0.0 && sa.y == 0.0), rb = !(sb.x == 0.0 && sb.y == 0.0);
+        if (ra || rb) {
+          int pa = r_p[a], qa = r_q[a], pb = r_p[b], qb = r_q[b];
+          cplx g00 = G[pa * LDS_ + pb], g01 = G[pa * LDS_ + qb], g10 = G[qa * LDS_ + pb], g11 = G[qa * LDS_ + qb];
+          // T = G R_b
+          cplx t00, t01, t10, t11;
+          { cplx y = cmulc(g01, sb), x = cmul(g00, sb); t00 = make_double2(cb * g00.x - y.x, cb * g00.y - y.y); t01 = make_double2(x.x + cb * g01.x, x.y + cb * g01.y); }
+          { cplx y = cmulc(g11, sb), x = cmul(g10, sb); t10 = make_double2(cb * g10.x - y.x, cb * g10.y - y.y); t11 = make_double2(x.x + cb * g11.x, x.y + cb * g11.y); }
+          // G' = R_a^H T : row0 = ca*T0 - sa*T1 ; row1 = conj(sa)*T0 + ca*T1
+          { cplx y = cmul(sa, t10), x = cmulc(t00, sa); G[pa * LDS_ + pb] = make_double2(ca * t00.x - y.x, ca * t00.y - y.y); G[qa * LDS_ + pb] = make_double2(x.x + ca * t10.x, x.y + ca * t10.y); }
+          { cplx y = cmul(sa, t11), x = cmulc(t01, sa); G[pa * LDS_ + qb] = make_double2(ca * t01.x - y.x, ca * t01.y - y.y); G[qa * LDS_ + qb] = make_double2(x.x + ca * t11.x, x.y + ca * t11.y); }
+        }
+        // J columns: 64 rows x 32 pairs = 2048 items, two per thread
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          int item = tid + it * EVD_THREADS;
+          int k = item >> 6, row = item & 63;
+          double cs = r_cs[k]; cplx s = r_s[k];
+          if (s.x == 0.0 && s.y == 0.0) continue;
+          int p = r_p[k], q = r_q[k];
+          cplx x = J[row * LDS_ + p], y = J[row * LDS_ + q];
+          cplx ys = cmulc(y, s), xs = cmul(x, s);
+          J[row * LDS_ + p] = make_double2(cs * x.x - ys.x, cs * x.y - ys.y);
+          J[row * LDS_ + q] = make_double2(xs.x + cs * y.x, xs.y + cs * y.y);
         }
       }
       __syncthreads();
     }
     if (!rotated) break;
-    __syncthreads();
   }
-  for (int e = tid; e < JP * JP; e += 256) jo[e] = J[(e % JP) * LDS_ + (e / JP)];
+  __syncthreads();
+  for (int e = tid; e < JP * JP; e += EVD_THREADS) jo[e] = J[(e % JP) * LDS_ + (e / JP)];
 }
 
 // ---- preparation / finalisation kernels -----------------------------------------------------
@@ -257,8 +256,8 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
                                                              cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot, int pass, int last_pass,
                                                              double shift_factor) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);
-  cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));
+  cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);                                    // G, then R in its upper triangle
+  cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1, then old Rtot
   __shared__ double red[8];
   __shared__ int nullcol[JP];
   __shared__ double piv;
@@ -278,8 +277,7 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
   if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
   __syncthreads();
-  // symmetrise + shift
-  for (int e = tid; e < JP * JP; e += 256) {
+  for (int e = tid; e < JP * JP; e += 256) {   // symmetrise + shift
     int row = e % JP, col = e / JP;
     if (row < col) {
       cplx a = G[row][col], b = G[col][row];
@@ -288,53 +286,45 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
     } else if (row == col) { G[row][col].x += shift; G[row][col].y = 0; }
   }
   __syncthreads();
-  // right-looking Cholesky, upper factor stored in the upper triangle of G (row j = R(j, j:))
+  // Left-looking Cholesky G = R^H R: thread c owns column c; per column j one dot product of length j per
+  // thread (R(k,j) is a broadcast read, R(k,c) is unit-stride across threads), two barriers.
   for (int j = 0; j < JP; ++j) {
-    if (tid == 0) {
-      double dd = G[j][j].x;
-      if (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) { piv = 0.0; }
-      else piv = sqrt(dd);
+    cplx v = make_double2(0, 0);
+    const int c = tid;
+    if (c < JP && c >= j) {
+      v = G[j][c];
+      for (int k = 0; k < j; ++k) { cplx a = G[k][j], b = G[k][c]; v.x -= a.x * b.x + a.y * b.y; v.y -= a.x * b.y - a.y * b.x; }   // conj(R(k,j)) R(k,c)
+      if (c == j) {
+        double dd = v.x;
+        piv = (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) ? 0.0 : sqrt(dd);
+      }
     }
     __syncthreads();
     double r = piv;
-    if (r == 0.0) {   // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0, no trailing update
-      if (tid == 0) G[j][j] = make_double2(1.0, 0.0);
-      for (int c = j + 1 + tid; c < JP; c += 256) G[j][c] = make_double2(0, 0);
-      __syncthreads();
-      continue;
-    }
-    if (tid == 0) G[j][j] = make_double2(r, 0.0);
-    for (int c = j + 1 + tid; c < JP; c += 256) { cplx v = G[j][c]; G[j][c] = make_double2(v.x / r, v.y / r); }
-    __syncthreads();
-    int nt = JP - 1 - j;
-    for (int e = tid; e < nt * nt; e += 256) {
-      int i = j + 1 + e / nt, c = j + 1 + e % nt;
-      if (c >= i) { cplx a = G[j][i], b = G[j][c]; cplx pr = make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);   // conj(R(j,i)) R(j,c)
-        G[i][c].x -= pr.x; G[i][c].y -= pr.y; }
+    if (c < JP && c >= j) {
+      if (r == 0.0) G[j][c] = make_double2(c == j ? 1.0 : 0.0, 0.0);          // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0
+      else G[j][c] = (c == j) ? make_double2(r, 0.0) : make_double2(v.x / r, v.y / r);
     }
     __syncthreads();
   }
-  // zero the strictly lower triangle (R is upper triangular)
   for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; if (row > col) G[row][col] = make_double2(0, 0); }
   __syncthreads();
-  // Rinv by back substitution, one column per thread
-  if (tid < JP) {
-    int c = tid;
-    for (int i = JP - 1; i >= 0; --i) {
+  if (tid < JP) {   // R^-1 by back substitution, one column per thread
+    const int c = tid;
+    for (int i = JP - 1; i > c; --i) Ri[i][c] = make_double2(0, 0);
+    for (int i = c; i >= 0; --i) {
       cplx acc = make_double2(i == c ? 1.0 : 0.0, 0.0);
-      if (i > c) { Ri[i][c] = make_double2(0, 0); continue; }
       for (int k = i + 1; k <= c; ++k) { cplx a = G[i][k], b = Ri[k][c]; acc.x -= a.x * b.x - a.y * b.y; acc.y -= a.x * b.y + a.y * b.x; }
-      double d = G[i][i].x;
-      Ri[i][c] = make_double2(acc.x / d, acc.y / d);
+      double dinv = 1.0 / G[i][i].x;
+      Ri[i][c] = make_double2(acc.x * dinv, acc.y * dinv);
     }
   }
   __syncthreads();
   for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
-  // Rtot <- R * Rtot  (Ri reused as the old Rtot)
   __syncthreads();
   for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Ri[row][col] = pass == 0 ? make_double2(row == col ? 1.0 : 0.0, 0.0) : Rtot[e]; }
   __syncthreads();
-  for (int e = tid; e < JP * JP; e += 256) {
+  for (int e = tid; e < JP * JP; e += 256) {   // Rtot <- R * Rtot
     int row = e % JP, col = e / JP;
     double xr = 0, xi = 0;
     for (int k = row; k < JP; ++k) { cplx a = G[row][k], b = Ri[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
@@ -447,7 +437,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       g.batch = np; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)np * JP * JP;
       zgemm_auto(g, s);
-      jacobi_evd64_kernel<<<np, 256, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps);
+      jacobi_evd64_kernel<<<np, EVD_THREADS, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
       GemmDesc a{};
@@ -482,7 +472,7 @@ static GemmDesc gd(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int con
 // One pass of right-looking block Gram-Schmidt QR with shifted-CholeskyQR3 panels (64 columns):
 //   Q (rows x npad, ld = ldq) is overwritten by the orthonormal factor, R (npad x npad, ld = npad) receives the
 //   upper-triangular factor.  Everything is GEMM-shaped (tn_zgemm.cu) plus the 64x64 Cholesky kernel.
-static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, cudaStream_t s) {
+static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, int chol_passes, cudaStream_t s) {
   static bool cfg = false;
   const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
   if (!cfg) { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); cfg = true; }
@@ -496,11 +486,12 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
   const int npanels = npad / JP;
   for (int pk = 0; pk < npanels; ++pk) {
     cplx* P = Q + (long long)pk * JP * ldq;
-    for (int it = 0; it < 3; ++it) {
+    for (int it = 0; it < chol_passes; ++it) {
       GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)JP * JP;
       zgemm_auto(g, s);
-      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, ksplit, (long long)JP * JP, Rinv, Rtot, it, it == 2 ? 1 : 0, shift_factor);
+      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, ksplit, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
+                                                  chol_passes == 3 ? shift_factor : 0.0);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
       // P <- P * Rinv (in place: each CTA owns 128 rows x all 64 columns)
@@ -532,8 +523,8 @@ static void bgs_qr(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cudaS
   ensure(w.Ra, w.Ra_cap, (size_t)npad * npad, s);
   ensure(w.Rb, w.Rb_cap, (size_t)npad * npad, s);
   ensure(w.Rc, w.Rc_cap, (size_t)npad * npad, s);
-  bgs_pass(w, Q, ldq, rows, npad, w.Rc, s);       // R'
-  bgs_pass(w, Q, ldq, rows, npad, w.Rb, s);       // R''
+  bgs_pass(w, Q, ldq, rows, npad, w.Rc, 3, s);    // R'  : shifted CholeskyQR3 panels (any conditioning)
+  bgs_pass(w, Q, ldq, rows, npad, w.Rb, 2, s);    // R'' : input already nearly orthonormal -> CholeskyQR2 panels
   zgemm_auto(gd(npad, npad, npad, w.Rb, idx1(1), idx1(npad), 0, w.Rc, idx1(1), idx1(npad), 0, w.Ra, idx1(1), idx1(npad)), s);
 }
 

@@ -15,6 +15,7 @@
 // bank groups on fragment loads.
 #include "tn_common.cuh"
 #include <atomic>
+#include <cstdlib>
 
 namespace tn {
 
@@ -69,7 +70,7 @@ struct TileCfg {
 // SIMPLE_K: both operands' k index is single-level without a lookup table, so each load slot just
 // advances a pointer by BK * stride per k-tile (no index arithmetic inside the pipeline).
 template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, 1) zgemm_kernel(const GemmDesc d) {
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_kernel(const GemmDesc d) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
   constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB;
@@ -294,10 +295,29 @@ void zgemm_auto(GemmDesc d, cudaStream_t stream) {
   if (d.batch <= 0) d.batch = 1;
   d.a_kfast = (d.ak.s0 == 1 && d.am.s0 != 1) ? 1 : 0;
   d.b_kfast = (d.bk.s0 == 1 && d.bn.s0 != 1) ? 1 : 0;
+  // In-place updates (C aliases an operand: Jacobi / CholeskyQR panel rotations Z(:,pair) <- Z(:,pair) * J) are only
+  // safe when one CTA owns every column of its row block, i.e. a single n-tile of 64.
+  const bool inplace = (d.C == d.A || d.C == d.B);
+  if (inplace) {
+    TN_CHECK(d.N <= 64, "zgemm: in-place update needs N <= 64");
+    launch<4, 2, 4, 4>(d, stream);
+    return;
+  }
   if (d.M <= 64 && d.N <= 64)      launch<2, 4, 4, 2>(d, stream);   // 64 x 64   (Gram blocks, tiny bonds)
   else if (d.N <= 32)              launch<8, 1, 4, 4>(d, stream);   // 256 x 32  (skinny right operand)
   else if (d.M <= 64)              launch<2, 4, 4, 4>(d, stream);   // 64 x 128
-  else                             launch<4, 2, 4, 4>(d, stream);   // 128 x 64
+  else {
+    // Large problems.  Default: 128 x 32 tiles, 4 warps, 2 CTAs per SM -- the two CTAs' k-tile barriers
+    // de-synchronise so the DMMA pipe does not drain at every barrier (measured 29.8 vs 27.4 TFLOP/s for the
+    // chi=1024 matvec against the single-CTA 128 x 64 tile).  TN_GEMM_VARIANT selects alternatives for A/B runs.
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("TN_GEMM_VARIANT"); variant = e ? atoi(e) : 2; }
+    if (variant == 0) launch<4, 2, 4, 4>(d, stream);                 // 128 x 64, 1 CTA / SM
+    else if (variant == 1) launch<2, 2, 4, 4>(d, stream);            // 64 x 64, 2 CTAs / SM
+    else if (variant == 3) launch<2, 1, 4, 4>(d, stream);            // 64 x 32, 4 CTAs / SM
+    else if (variant == 4) launch<1, 2, 4, 4>(d, stream);            // 32 x 64, 4 CTAs / SM
+    else launch<4, 1, 4, 4>(d, stream);                              // 128 x 32, 2 CTAs / SM
+  }
 }
 
 }  // namespace tn

@@ -42,6 +42,12 @@ if "svdmodes" in what:
                            orthU=float(np.linalg.norm(U[:, :k].conj().T @ U[:, :k] - np.eye(k))), orthV=float(np.linalg.norm(V[:k] @ V[:k].conj().T - np.eye(k)))), flush=True)
     ctx.lib.tn_svd_set_precond(1)
 
+if "svdone" in what:
+    n = int(os.environ.get("SVD_N", "1024"))
+    u, _ = np.linalg.qr(crandn(n, n)); v, _ = np.linalg.qr(crandn(n, n)); x = (u * np.exp(-np.arange(n) * 30.0 / n)) @ v.conj().T
+    tnb200.svd(x, 2)
+    t1 = time.perf_counter(); U, S, V, sw = tnb200.svd(x, 2, return_sweeps=True); print("svdone", n, sw, time.perf_counter() - t1, flush=True)
+
 if "svd" in what:
     for n in [int(a) for a in os.environ.get("SVD_N", "256,512,1024,2048").split(",")]:
         x = crandn(n, n)
