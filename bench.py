@@ -12,7 +12,7 @@ src/structures/mps/projmps.jl:107-134) = 3 contraction launches on the GPU.
   e2e        same metric through the public API call ProjMPS.product(A) with HOST buffers (pinned):
              Theta H2D and result D2H inside the timed region, environments resident (they are the
              state the reference's ProjMPS object carries between calls).
-  roofline   dominant kernel tn::zgemm_kernel<4,2,4,4,true> (the two chi^3 contractions), live CUDA events.
+  roofline   dominant kernel tn::zgemm_kernel<4,1,4,4,true> (the two chi^3 contractions), live CUDA events.
   cpu_baseline / --impl reference: the oracle's restatement of the reference's product() in the
              REFERENCE contraction order, NumPy/OpenBLAS with all host threads, bounded sample.
 N > 1: the chi = 1024 matvec does not shard: N independent replicas, scaling "weak".
@@ -256,7 +256,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                     "api": "tnb200.ProjMPS.product(A_host) -> tn_env_product", "matches_resident_path_rel": same},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": zgemm_peak, "unit": "TFLOP/s", "frac": achieved / zgemm_peak,
-                         "traffic": None, "kernel": "tn::zgemm_kernel<4,2,4,4,true> (DMMA.8x8x4), 2 launches per matvec",
+                         "traffic": None, "kernel": "tn::zgemm_kernel<4,1,4,4,true> (128x32 tile, 2 CTAs/SM, DMMA.8x8x4), 2 launches per matvec",
                          "flops_per_launch": big_flops, "ms_per_launch": (stage_ms[0] + stage_ms[2]) / 2,
                          "peak_source": "cuBLAS ZGEMM 4096^3 via torch.matmul measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "DMMA issue peak measured 37.17 TFLOP/s, profiles/r01_probe_fp64.jsonl)",

@@ -97,13 +97,15 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
         double absc2 = c.x * c.x + c.y * c.y;
         double cs = 1.0; cplx s = make_double2(0, 0);
         if (absc2 > tol2 * fabs(a * b) && absc2 > 0) {
-          double iabs = rsqrt(absc2), absc = absc2 * iabs;
-          double zeta = (b - a) * 0.5 * iabs;
-          double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          cs = rsqrt(1.0 + t * t);
-          double sn = cs * t * iabs;
-          s = make_double2(sn * c.x, sn * c.y);
-          (void)absc;
+          // t = sign(dl)|c| / (|dl| + sqrt(dl^2 + |c|^2)), dl = (b-a)/2;  with h = |dl| + sqrt(dl^2+|c|^2):
+          // cs = h / sqrt(h^2 + |c|^2),  s = sign(dl) c / sqrt(h^2 + |c|^2)   (one sqrt, one rsqrt, no division:
+          // FP64 latency on this part is ~50 cycles per dependent op, so the length of this chain sets the step time)
+          double dl = 0.5 * (b - a);
+          double h = fabs(dl) + sqrt(fma(dl, dl, absc2));
+          double q = rsqrt(fma(h, h, absc2));
+          cs = h * q;
+          double sg = dl >= 0 ? q : -q;
+          s = make_double2(sg * c.x, sg * c.y);
           rotated = 1;
         }
         r_cs[tid] = cs; r_s[tid] = s; r_p[tid] = p; r_q[tid] = q;
@@ -260,7 +262,8 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1, then old Rtot
   __shared__ double red[8];
   __shared__ int nullcol[JP];
-  __shared__ double piv;
+  __shared__ double piv;            // 1 / R(j,j) of the current column (0 = null / failed pivot)
+  __shared__ double rdinv[JP];      // reciprocal diagonal of R (divisions cost ~600 cycles of FP64 latency: do each once)
   const int tid = threadIdx.x;
   double fro = 0;
   for (int e = tid; e < JP * JP; e += 256) {
@@ -286,37 +289,63 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
     } else if (row == col) { G[row][col].x += shift; G[row][col].y = 0; }
   }
   __syncthreads();
-  // Left-looking Cholesky G = R^H R: thread c owns column c; per column j one dot product of length j per
-  // thread (R(k,j) is a broadcast read, R(k,c) is unit-stride across threads), two barriers.
+  // Left-looking Cholesky G = R^H R.  FP64 dependent-issue latency (~60 cycles) bounds this kernel, so every column's
+  // dot product is split over 4 threads x 2 partial sums and combined with shuffles: lane = part*8 + (c % 8),
+  // i.e. a quarter-warp reads 8 consecutive columns of one row (conflict-free LDS.128); two barriers per column.
+  const int lane = tid & 31, wrp = tid >> 5;
+  const int cc = (lane & 7) + 8 * wrp, part = lane >> 3;
   for (int j = 0; j < JP; ++j) {
+    double ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;
+    if (cc >= j) {
+      int k = part;
+      for (; k + 4 < j; k += 8) {
+        cplx a = G[k][j], b = G[k][cc], a2 = G[k + 4][j], b2 = G[k + 4][cc];
+        ar0 += a.x * b.x + a.y * b.y; ai0 += a.x * b.y - a.y * b.x;       // conj(R(k,j)) R(k,c)
+        ar1 += a2.x * b2.x + a2.y * b2.y; ai1 += a2.x * b2.y - a2.y * b2.x;
+      }
+      if (k < j) { cplx a = G[k][j], b = G[k][cc]; ar0 += a.x * b.x + a.y * b.y; ai0 += a.x * b.y - a.y * b.x; }
+    }
+    double sr = ar0 + ar1, si = ai0 + ai1;
+    sr += __shfl_xor_sync(0xffffffffu, sr, 8); si += __shfl_xor_sync(0xffffffffu, si, 8);
+    sr += __shfl_xor_sync(0xffffffffu, sr, 16); si += __shfl_xor_sync(0xffffffffu, si, 16);
     cplx v = make_double2(0, 0);
-    const int c = tid;
-    if (c < JP && c >= j) {
-      v = G[j][c];
-      for (int k = 0; k < j; ++k) { cplx a = G[k][j], b = G[k][c]; v.x -= a.x * b.x + a.y * b.y; v.y -= a.x * b.y - a.y * b.x; }   // conj(R(k,j)) R(k,c)
-      if (c == j) {
+    if (part == 0 && cc >= j) {
+      v = G[j][cc]; v.x -= sr; v.y -= si;
+      if (cc == j) {
         double dd = v.x;
-        piv = (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) ? 0.0 : sqrt(dd);
+        double ri = (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) ? 0.0 : rsqrt(dd);
+        piv = ri;
+        rdinv[j] = ri == 0.0 ? 1.0 : ri;
       }
     }
     __syncthreads();
-    double r = piv;
-    if (c < JP && c >= j) {
-      if (r == 0.0) G[j][c] = make_double2(c == j ? 1.0 : 0.0, 0.0);          // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0
-      else G[j][c] = (c == j) ? make_double2(r, 0.0) : make_double2(v.x / r, v.y / r);
+    double ri = piv;
+    if (part == 0 && cc >= j) {
+      if (ri == 0.0) G[j][cc] = make_double2(cc == j ? 1.0 : 0.0, 0.0);          // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0
+      else G[j][cc] = (cc == j) ? make_double2(v.x * ri, 0.0) : make_double2(v.x * ri, v.y * ri);
     }
     __syncthreads();
   }
   for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; if (row > col) G[row][col] = make_double2(0, 0); }
   __syncthreads();
-  if (tid < JP) {   // R^-1 by back substitution, one column per thread
-    const int c = tid;
-    for (int i = JP - 1; i > c; --i) Ri[i][c] = make_double2(0, 0);
-    for (int i = c; i >= 0; --i) {
-      cplx acc = make_double2(i == c ? 1.0 : 0.0, 0.0);
-      for (int k = i + 1; k <= c; ++k) { cplx a = G[i][k], b = Ri[k][c]; acc.x -= a.x * b.x - a.y * b.y; acc.y -= a.x * b.y + a.y * b.x; }
-      double dinv = 1.0 / G[i][i].x;
-      Ri[i][c] = make_double2(acc.x * dinv, acc.y * dinv);
+  // R^-1 by back substitution: column cc of the inverse, rows i = cc .. 0; the row's dot product is split over the 4
+  // threads of the column group.  Each warp owns 8 columns, so only warp-level synchronisation is needed.
+  {
+    for (int i = JP - 1 - part; i > cc; i -= 4) Ri[i][cc] = make_double2(0, 0);
+    __syncwarp();
+    const int cmax = 8 * wrp + 7;                       // largest column handled by this warp
+    for (int i = cmax; i >= 0; --i) {
+      double ar0 = 0, ai0 = 0;
+      if (i <= cc) {
+        for (int k = i + 1 + part; k <= cc; k += 4) { cplx a = G[i][k], b = Ri[k][cc]; ar0 += a.x * b.x - a.y * b.y; ai0 += a.x * b.y + a.y * b.x; }
+      }
+      ar0 += __shfl_xor_sync(0xffffffffu, ar0, 8); ai0 += __shfl_xor_sync(0xffffffffu, ai0, 8);
+      ar0 += __shfl_xor_sync(0xffffffffu, ar0, 16); ai0 += __shfl_xor_sync(0xffffffffu, ai0, 16);
+      if (part == 0 && i <= cc) {
+        double dinv = rdinv[i];
+        Ri[i][cc] = make_double2(((i == cc ? 1.0 : 0.0) - ar0) * dinv, -ai0 * dinv);
+      }
+      __syncwarp();
     }
   }
   __syncthreads();
@@ -327,7 +356,15 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   for (int e = tid; e < JP * JP; e += 256) {   // Rtot <- R * Rtot
     int row = e % JP, col = e / JP;
     double xr = 0, xi = 0;
-    for (int k = row; k < JP; ++k) { cplx a = G[row][k], b = Ri[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+    double yr = 0, yi = 0;
+    int k = row;
+    for (; k + 1 < JP; k += 2) {
+      cplx a = G[row][k], b = Ri[k][col], a2 = G[row][k + 1], b2 = Ri[k + 1][col];
+      xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x;
+      yr += a2.x * b2.x - a2.y * b2.y; yi += a2.x * b2.y + a2.y * b2.x;
+    }
+    if (k < JP) { cplx a = G[row][k], b = Ri[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+    xr += yr; xi += yi;
     if (last_pass && nullcol[row]) { xr = 0; xi = 0; }
     Rtot[e] = make_double2(xr, xi);
   }
