@@ -64,6 +64,7 @@ int32_t tn_ctx_destroy(tn_ctx* ctx) {
     svd_free(ctx->c.svd);
     for (auto& b : ctx->c.scratch) b.release();
     cudaFree(ctx->c.dscal); cudaFreeHost(ctx->c.hscal); cudaFree(ctx->c.partials);
+    if (ctx->c.copy_stream) { cudaStreamDestroy(ctx->c.copy_stream); for (auto& ev : ctx->c.copy_ev) cudaEventDestroy(ev); }
     cudaStreamDestroy(ctx->c.stream);
     delete ctx;
   });
@@ -256,15 +257,9 @@ static int product_site(Env* e, int direction) {   // projmps.jl:109
 }
 int32_t tn_env_product(tn_env* eh, const tn_cplx* theta, int32_t direction, tn_cplx* out) {
   return guard([&] {
-    Env* e = eh->e; Ctx* c = e->ctx; cudaStream_t s = c->stream;
+    Env* e = eh->e;
     int site = product_site(e, direction);
-    long long n = e->ket->chiL(site) * e->ket->d * e->ket->d * e->ket->chiR(site + 1);
-    cplx* din = c->scratch[13].get((size_t)n, s);
-    cplx* dout = c->scratch[14].get((size_t)n, s);
-    TN_CUDA(cudaMemcpyAsync(din, theta, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, s));
-    env_product_dev(e, din, site, dout);
-    TN_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
-    c->sync();
+    env_product_host(e, C(theta), site, C(out));
   });
 }
 int32_t tn_env_product_dev(tn_env* eh, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps) {

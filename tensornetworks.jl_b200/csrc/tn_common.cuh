@@ -56,6 +56,7 @@ struct GemmDesc {
   int ksplit;              // split-K factor; split s handles k in [s*kchunk, (s+1)*kchunk)
   int kchunk;
   long long ssC;           // C stride between k-splits (partials are summed by the consumer)
+  int swap_raster;         // set by the launcher
   int a_kfast, b_kfast;    // global-load thread mapping: 1 = consecutive threads walk k (k is the unit-stride index)
 };
 

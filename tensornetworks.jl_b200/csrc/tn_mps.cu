@@ -333,41 +333,121 @@ __global__ void build_w2_kernel(const cplx* __restrict__ M1, const cplx* __restr
 }
 
 // H_eff * theta for sites (site, site+1):  out(a,s1,s2,a') = coeff * sum L M1 M2 theta R   (projmps.jl:107-134, :144)
-void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4) {
-  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+// The matvec is split into two pieces so that the host-buffer entry point can pipeline PCIe copies with compute:
+//   stage 1+2 for a slice b' in [b0,b1) of theta's right bond (theta, T1 and T2 all have b' as their slowest index, so a
+//   slice is a contiguous chunk of each), stage 3 for a slice a' in [a0,a1) of the output's right bond.
+struct HeffDims { int d, d2, ca, w, cb, ca2, w2, cb2, w1; };
+static HeffDims heff_dims(Env* e, int site) {
   TN_CHECK(e->mpo != nullptr, "product: the rank-2 branch needs an MPO layer");
   TN_CHECK(site >= 1 && site + 1 <= e->ket->N, "product: site out of range");
   const Tensor& L = env_block(e, site - 1);
   const Tensor& R = env_block(e, site + 2);
   const Tensor& M1 = e->mpo->sites[site - 1];
   const Tensor& M2 = e->mpo->sites[site];
-  int d = e->ket->d, d2 = d * d;
-  int ca = (int)L.dims[0], w = (int)L.dims[1], cb = (int)L.dims[2];
-  int ca2 = (int)R.dims[0], w2 = (int)R.dims[1], cb2 = (int)R.dims[2];
-  int w1 = (int)M1.dims[3];
-  TN_CHECK(M1.dims[0] == w && M2.dims[0] == w1 && M2.dims[3] == w2, "product: MPO / block bond mismatch");
-  cplx* W = c->scratch[3].get((size_t)w * d2 * d2 * w2, s);
-  {
-    int tot = w * d2 * d2 * w2;
-    build_w2_kernel<<<(tot + 127) / 128, 128, 0, s>>>(M1.p, M2.p, W, w, w1, w2, d);
-    count_launch(1);
-  }
-  if (ev4) TN_CUDA(cudaEventRecord(ev4[0], s));
+  HeffDims h;
+  h.d = e->ket->d; h.d2 = h.d * h.d;
+  h.ca = (int)L.dims[0]; h.w = (int)L.dims[1]; h.cb = (int)L.dims[2];
+  h.ca2 = (int)R.dims[0]; h.w2 = (int)R.dims[1]; h.cb2 = (int)R.dims[2];
+  h.w1 = (int)M1.dims[3];
+  TN_CHECK(M1.dims[0] == h.w && M2.dims[0] == h.w1 && M2.dims[3] == h.w2, "product: MPO / block bond mismatch");
+  return h;
+}
+void heff_prepare(Env* e, int site) {   // W = M1.M2 and the intermediates' storage
+  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  HeffDims h = heff_dims(e, site);
+  cplx* W = c->scratch[3].get((size_t)h.w * h.d2 * h.d2 * h.w2, s);
+  int tot = h.w * h.d2 * h.d2 * h.w2;
+  build_w2_kernel<<<(tot + 127) / 128, 128, 0, s>>>(e->mpo->sites[site - 1].p, e->mpo->sites[site].p, W, h.w, h.w1, h.w2, h.d);
+  count_launch(1);
+  c->scratch[4].get((size_t)h.ca * h.w * h.d2 * h.cb2, s);
+  c->scratch[5].get((size_t)h.ca * h.d2 * h.w2 * h.cb2, s);
+}
+void heff_stage12(Env* e, const cplx* theta, int site, int b0, int b1, cudaEvent_t* ev_mid) {
+  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  HeffDims h = heff_dims(e, site);
+  const Tensor& L = env_block(e, site - 1);
+  const int nb = b1 - b0, ca = h.ca, w = h.w, d2 = h.d2, cb = h.cb, w2 = h.w2;
+  cplx* W = c->scratch[3].p;
+  cplx* T1 = c->scratch[4].p + (size_t)ca * w * d2 * b0;
+  cplx* T2 = c->scratch[5].p + (size_t)ca * d2 * w2 * b0;
+  const cplx* th = theta + (size_t)cb * d2 * b0;
   // T1[(a,w),(s1',s2',b')] = L[(a,w),b] theta[b,(s1',s2',b')]
-  cplx* T1 = c->scratch[4].get((size_t)ca * w * d2 * cb2, s);
-  zgemm_auto(mk(ca * w, d2 * cb2, cb, L.p, idx1(1), idx1((long long)ca * w), 0, theta, idx1(1), idx1(cb), 0, T1, idx1(1), idx1((long long)ca * w)), s);
-  if (ev4) TN_CUDA(cudaEventRecord(ev4[1], s));
+  zgemm_auto(mk(ca * w, d2 * nb, cb, L.p, idx1(1), idx1((long long)ca * w), 0, th, idx1(1), idx1(cb), 0, T1, idx1(1), idx1((long long)ca * w)), s);
+  if (ev_mid) TN_CUDA(cudaEventRecord(*ev_mid, s));
   // T2(a,s1,s2,w2,b') = sum_{(w,s1',s2')} T1(a,(w,s1',s2'),b') W; rows m = (a,b')
-  cplx* T2 = c->scratch[5].get((size_t)ca * d2 * w2 * cb2, s);
-  zgemm_auto(mk(ca * cb2, d2 * w2, w * d2, T1, idx2(ca, 1, (long long)ca * w * d2), idx1(ca), 0,
+  zgemm_auto(mk(ca * nb, d2 * w2, w * d2, T1, idx2(ca, 1, (long long)ca * w * d2), idx1(ca), 0,
                 W, idx1(1), idx1((long long)w * d2), 0,
                 T2, idx2(ca, 1, (long long)ca * d2 * w2), idx1(ca)), s);
-  if (ev4) TN_CUDA(cudaEventRecord(ev4[2], s));
+}
+void heff_stage3(Env* e, int site, int a0, int a1, cplx* out) {
+  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  HeffDims h = heff_dims(e, site);
+  const Tensor& R = env_block(e, site + 2);
+  const int ca = h.ca, d2 = h.d2;
   // out[(a,s1,s2),a'] = coeff * sum_{(w2,b')} T2[(a,s1,s2),(w2,b')] R[a',(w2,b')]
-  zgemm_auto(mk(ca * d2, ca2, w2 * cb2, T2, idx1(1), idx1((long long)ca * d2), 0, R.p, idx1(ca2), idx1(1), 0,
-                out, idx1(1), idx1((long long)ca * d2), e->coeff), s);
+  zgemm_auto(mk(ca * d2, a1 - a0, h.w2 * h.cb2, c->scratch[5].p, idx1(1), idx1((long long)ca * d2), 0, R.p + a0, idx1(h.ca2), idx1(1), 0,
+                out + (size_t)ca * d2 * a0, idx1(1), idx1((long long)ca * d2), e->coeff), s);
+}
+
+// H_eff * theta for sites (site, site+1):  out(a,s1,s2,a') = coeff * sum L M1 M2 theta R   (projmps.jl:107-134, :144)
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4) {
+  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  HeffDims h = heff_dims(e, site);
+  heff_prepare(e, site);
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[0], s));
+  heff_stage12(e, theta, site, 0, h.cb2, ev4 ? &ev4[1] : nullptr);
+  if (ev4) TN_CUDA(cudaEventRecord(ev4[2], s));
+  heff_stage3(e, site, 0, h.ca2, out);
   if (ev4) TN_CUDA(cudaEventRecord(ev4[3], s));
   c->matvecs++;
+}
+
+// Host-buffer matvec with the PCIe copies pipelined against the contractions: theta is uploaded in slices of its right
+// bond on a copy stream while stage 1+2 of the previous slice runs; the result is downloaded slice by slice while
+// stage 3 computes the next one.  (theta_host / out_host should be pinned for the copies to be asynchronous.)
+void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host) {
+  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  HeffDims h = heff_dims(e, site);
+  const long long n_in = (long long)h.cb * h.d2 * h.cb2, n_out = (long long)h.ca * h.d2 * h.ca2;
+  cplx* din = c->scratch[13].get((size_t)n_in, s);
+  cplx* dout = c->scratch[14].get((size_t)n_out, s);
+  const int nchunk = (n_in >= (1 << 20) && h.cb2 >= 64 && h.ca2 >= 64) ? 4 : 1;
+  if (nchunk == 1) {
+    TN_CUDA(cudaMemcpyAsync(din, theta_host, (size_t)n_in * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    env_product_dev(e, din, site, dout, nullptr);
+    TN_CUDA(cudaMemcpyAsync(out_host, dout, (size_t)n_out * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+    return;
+  }
+  if (!c->copy_stream) {
+    TN_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : c->copy_ev) TN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  heff_prepare(e, site);
+  TN_CUDA(cudaEventRecord(c->copy_ev[8], s));                       // scratch (re)allocation is ordered on the main stream
+  TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[8], 0));
+  for (int k = 0; k < nchunk; ++k) {
+    int b0 = (int)((long long)h.cb2 * k / nchunk), b1 = (int)((long long)h.cb2 * (k + 1) / nchunk);
+    size_t off = (size_t)h.cb * h.d2 * b0, cnt = (size_t)h.cb * h.d2 * (b1 - b0);
+    TN_CUDA(cudaMemcpyAsync(din + off, theta_host + off, cnt * sizeof(cplx), cudaMemcpyHostToDevice, c->copy_stream));
+    TN_CUDA(cudaEventRecord(c->copy_ev[k], c->copy_stream));
+  }
+  for (int k = 0; k < nchunk; ++k) {
+    int b0 = (int)((long long)h.cb2 * k / nchunk), b1 = (int)((long long)h.cb2 * (k + 1) / nchunk);
+    TN_CUDA(cudaStreamWaitEvent(s, c->copy_ev[k], 0));
+    heff_stage12(e, din, site, b0, b1, nullptr);
+  }
+  for (int k = 0; k < nchunk; ++k) {
+    int a0 = (int)((long long)h.ca2 * k / nchunk), a1 = (int)((long long)h.ca2 * (k + 1) / nchunk);
+    heff_stage3(e, site, a0, a1, dout);
+    TN_CUDA(cudaEventRecord(c->copy_ev[4 + k], s));
+    TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[4 + k], 0));
+    size_t off = (size_t)h.ca * h.d2 * a0, cnt = (size_t)h.ca * h.d2 * (a1 - a0);
+    TN_CUDA(cudaMemcpyAsync(out_host + off, dout + off, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, c->copy_stream));
+  }
+  c->matvecs++;
+  TN_CUDA(cudaStreamSynchronize(c->copy_stream));
+  c->sync();
 }
 
 cplx env_calculate(Env* e) {   // projmps.jl:192-216

@@ -30,6 +30,8 @@ struct Ctx {
   cplx* hscal = nullptr;     // 64 pinned host scalars
   cplx* partials = nullptr;  // dot-product partial sums
   long long matvecs = 0, svds = 0;
+  cudaStream_t copy_stream = nullptr;   // H2D / D2H pipeline of the host-buffer matvec
+  cudaEvent_t copy_ev[9] = {};
   void alloc(Tensor& t, const std::vector<long long>& dims);
   void free(Tensor& t);
   void swap(Tensor& a, Tensor& b) { std::swap(a, b); }
@@ -77,6 +79,7 @@ void env_buildright(Env* e, int idx);
 void env_movecenter(Env* e, int idx);
 const Tensor& env_block(Env* e, int idx);
 void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4 = nullptr);   // sites (site, site+1)
+void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host);   // pipelined PCIe copies
 cplx env_calculate(Env* e);
 
 // --- drivers ------------------------------------------------------------------------------------

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 
   const int g = lane >> 2, t = lane & 3;
   const int z = blockIdx.z;
   const int batch = z / d.ksplit, split = z - batch * d.ksplit;
-  const int m_blk = blockIdx.x * BM, n_blk = blockIdx.y * BN;
+  // raster: consecutive CTAs walk m (default) or n (swap_raster) so that the LARGER operand is streamed from DRAM once
+  const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * BN;
   const int k_begin = split * d.kchunk;
   const int k_end = min(d.K, k_begin + d.kchunk);
   const cplx* __restrict__ Ab = d.A + (long long)batch * d.bsA;
@@ -272,9 +273,14 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
     configured = true;
   }
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return;
-  dim3 grid((d.M + Cfg::BM - 1) / Cfg::BM, (d.N + Cfg::BN - 1) / Cfg::BN, d.batch * d.ksplit);
+  unsigned tm = (d.M + Cfg::BM - 1) / Cfg::BM, tn_ = (d.N + Cfg::BN - 1) / Cfg::BN;
+  GemmDesc dd = d;
+  // Within a wave the CTAs share the operand indexed by the slow raster direction through L2; across waves the other
+  // operand is re-read from DRAM.  Stream the operand with more bytes (A: M*K, B: K*N) only once.
+  dd.swap_raster = (d.batch * d.ksplit == 1 && (long long)d.M > (long long)d.N && tm <= 65535 && tn_ > 1) ? 1 : 0;
+  dim3 grid(dd.swap_raster ? tn_ : tm, dd.swap_raster ? tm : tn_, d.batch * d.ksplit);
   TN_CHECK(grid.y <= 65535 && grid.z <= 65535, "zgemm: grid too large");
-  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(d);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd);
   TN_CUDA(cudaGetLastError());
   count_launch(1);
 }

@@ -73,6 +73,8 @@ class GMPS:
         self.lib = self.ctx.lib
         ts = [_f(t) for t in tensors]
         N = len(ts)
+        if rank not in (1, 2) or any(t.ndim != rank + 2 for t in ts):
+            raise _lib.TNError("GMPS rank must be 1 (MPS) or 2 (MPO) and every site tensor must have rank+2 indices")
         dims = np.array([t.shape for t in ts], dtype=np.int64).reshape(N, rank + 2)
         ptrs = (C.c_void_p * N)(*[t.ctypes.data for t in ts])
         h = C.c_void_p()
