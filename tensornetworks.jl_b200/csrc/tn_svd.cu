@@ -39,7 +39,9 @@ __device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) 
 // (G' = R_a^H G_ab R_b) and the column rotation to two (row, pair) items of J: two barriers per step.
 constexpr int EVD_THREADS = 1024;
 __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
-                                                                       cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner) {
+                                                                       cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner, int nact) {
+  // nact (even, <= 64): only the leading nact columns of the pair can be non-zero (a single zero-padded pair); the
+  // round-robin then runs over nact columns (nact-1 steps) instead of 64
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cplx* G = reinterpret_cast<cplx*>(sm_raw);     // G[row*LDS_ + col]
   cplx* J = G + JP * LDS_;
@@ -89,14 +91,15 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
   for (int sweep = 0; sweep < max_inner; ++sweep) {
     if (tid == 0) rotated = 0;
     __syncthreads();
-    for (int step = 0; step < JP - 1; ++step) {
+    for (int step = 0; step < nact - 1; ++step) {
       if (tid < JB) {
-        int p, q; rr_pair(JP, step, tid, p, q);
+        int p = 0, q = 0;
+        if (tid < nact / 2) rr_pair(nact, step, tid, p, q);
         double a = G[p * LDS_ + p].x, b = G[q * LDS_ + q].x;
         cplx c = G[p * LDS_ + q];
         double absc2 = c.x * c.x + c.y * c.y;
         double cs = 1.0; cplx s = make_double2(0, 0);
-        if (absc2 > tol2 * fabs(a * b) && absc2 > 0) {
+        if (tid < nact / 2 && absc2 > tol2 * fabs(a * b) && absc2 > 0) {
           // t = sign(dl)|c| / (|dl| + sqrt(dl^2 + |c|^2)), dl = (b-a)/2;  with h = |dl| + sqrt(dl^2+|c|^2):
           // cs = h / sqrt(h^2 + |c|^2),  s = sign(dl) c / sqrt(h^2 + |c|^2)   (one sqrt, one rsqrt, no division:
           // FP64 latency on this part is ~50 cycles per dependent op, so the length of this chain sets the step time)
@@ -116,7 +119,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
         int a = tid >> 5, b = tid & 31;
         double ca = r_cs[a], cb = r_cs[b]; cplx sa = r_s[a], sb = r_s[b];
         bool ra = !(sa.x == 0.0 && sa.y == 0.0), rb = !(sb.x == 0.0 && sb.y == 0.0);
-        if (ra || rb) {
+        if ((ra || rb) && a < nact / 2 && b < nact / 2) {
           int pa = r_p[a], qa = r_q[a], pb = r_p[b], qb = r_q[b];
           cplx g00 = G[pa * LDS_ + pb], g01 = G[pa * LDS_ + qb], g10 = G[qa * LDS_ + pb], g11 = G[qa * LDS_ + qb];
           // T = G R_b
@@ -459,6 +462,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   // (tools/jacobi_emul.py) at 1/8 of the cost and with less rounding accumulated in V; a single pair
   // (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
   const int inner_sweeps = (np == 1) ? 12 : 1;
+  const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
   w.sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
@@ -474,7 +478,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       g.batch = np; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)np * JP * JP;
       zgemm_auto(g, s);
-      jacobi_evd64_kernel<<<np, EVD_THREADS, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps);
+      jacobi_evd64_kernel<<<np, EVD_THREADS, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps, nact);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
       GemmDesc a{};

@@ -92,3 +92,29 @@ if "matvec" in what:
         dt = (time.perf_counter() - t0) / reps
         flops = 8.0 * (2 * chi ** 3 * d * d * w + 2 * chi ** 2 * d ** 3 * w * w)
         print(dict(chi=chi, ms=round(dt * 1e3, 3), tflops=round(flops / dt / 1e12, 2)), flush=True)
+
+if "smallsvd" in what:
+    for n in (4, 8, 16, 32, 64, 128):
+        x = crandn(n, n)
+        tnb200.svd(x, 2)
+        t1 = time.perf_counter()
+        for _ in range(20):
+            U, S, V, sw = tnb200.svd(x, 2, return_sweeps=True)
+        dt = (time.perf_counter() - t1) / 20
+        so = np.linalg.svd(x, compute_uv=False)
+        print(dict(n=n, ms=round(dt * 1e3, 3), sweeps=sw, sv_err=float(np.max(np.abs(np.real(np.diag(S)) - so)) / so[0])), flush=True)
+
+if "qjmcstep" in what:
+    import oracle
+    N, chi = 32, 64
+    X, Z, SM = tnb200.models.X, tnb200.models.Z, tnb200.models.SM
+    onsite = -1j * (1.0 * X + 20.0 * Z) - 0.5 * 0.1 * (SM.conj().T @ SM)
+    ss, gg = tnb200.models.trotter_gates(N, onsite, -1j * 10.0 * np.kron(Z, Z), 5e-3, evol="imag", order=2)
+    psi = tnb200.GMPS(1, 2, tnb200.models.random_canonical_mps(N, 2, chi, seed=1), 1)
+    gl = tnb200.GateList(2, ss, gg)
+    for label, fn in (("applygates", lambda: tnb200.applygates(psi, gl, cutoff=0.0, maxdim=chi)),
+                      ("normalize", lambda: psi.normalize()),
+                      ("expect_local", lambda: psi.expect([SM.conj().T @ SM] * N, list(range(1, N + 1))))):
+        fn()
+        c0 = ctx.counters(); t1 = time.perf_counter(); fn(); dt = time.perf_counter() - t1; c1 = ctx.counters()
+        print(dict(op=label, N=N, chi=chi, ms=round(dt * 1e3, 2), launches=c1["launches"] - c0["launches"], svds=c1["svds"] - c0["svds"]), flush=True)
