@@ -14,6 +14,7 @@
 // dimension padded to == 2 (mod 8) 16-byte units so the 8 lanes of a quarter-warp hit 8 distinct
 // bank groups on fragment loads.
 #include "tn_common.cuh"
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 
@@ -69,24 +70,18 @@ struct TileCfg {
 
 // SIMPLE_K: both operands' k index is single-level without a lookup table, so each load slot just
 // advances a pointer by BK * stride per k-tile (no index arithmetic inside the pipeline).
+// One CTA tile: C[m_blk.., n_blk..] (+)= alpha * sum_{k in [k_begin, k_end)} op(A) op(B).
+// ATOMIC = false: C = alpha*acc + beta*C (plain stores); ATOMIC = true: C += alpha*acc with red.global.add.f64
+// (stream-K partial tiles; C was zeroed by the launcher).
 template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_kernel(const GemmDesc d) {
+__device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs, const int m_blk, const int n_blk, const int batch,
+                                          const int split, const int k_begin, const int k_end, const bool atomic) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, THREADS = Cfg::THREADS;
   constexpr int LDA = Cfg::LDA, LDB = Cfg::LDB;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* As = reinterpret_cast<cplx*>(smem_raw);
-  cplx* Bs = As + STAGES * Cfg::A_STAGE;
-
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp % WARPS_M, wn = warp / WARPS_M;
   const int g = lane >> 2, t = lane & 3;
-  const int z = blockIdx.z;
-  const int batch = z / d.ksplit, split = z - batch * d.ksplit;
-  // raster: consecutive CTAs walk m (default) or n (swap_raster) so that the LARGER operand is streamed from DRAM once
-  const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * BN;
-  const int k_begin = split * d.kchunk;
-  const int k_end = min(d.K, k_begin + d.kchunk);
   const cplx* __restrict__ Ab = d.A + (long long)batch * d.bsA;
   const cplx* __restrict__ Bb = d.B + (long long)batch * d.bsB;
 
@@ -172,6 +167,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 
     for (int j = 0; j < TN; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
 
   const int ktiles = (k_end - k_begin + BK - 1) / BK;
+  __syncthreads();   // persistent CTAs: the previous tile's last stages may still be being read
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < ktiles) load_stage(s);
@@ -253,6 +249,11 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 
         o.x = d.alpha.x * xr - d.alpha.y * xi;
         o.y = d.alpha.x * xi + d.alpha.y * xr;
         cplx* p = Cb + moff + noff[j][q];
+        if (atomic) {
+          atomicAdd(&p->x, o.x);
+          atomicAdd(&p->y, o.y);
+          continue;
+        }
         if (has_beta) {
           cplx c = *p;
           o.x += d.beta.x * c.x - d.beta.y * c.y;
@@ -260,6 +261,58 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 
         }
         *p = o;
       }
+  }
+}
+
+template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_kernel(const GemmDesc d) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* As = reinterpret_cast<cplx*>(smem_raw);
+  cplx* Bs = As + Cfg::STAGES * Cfg::A_STAGE;
+  const int z = blockIdx.z;
+  const int batch = z / d.ksplit, split = z - batch * d.ksplit;
+  // raster: consecutive CTAs walk m (default) or n (swap_raster) so that the LARGER operand is streamed from DRAM once
+  const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * Cfg::BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * Cfg::BN;
+  const int k_begin = split * d.kchunk;
+  const int k_end = min(d.K, k_begin + d.kchunk);
+  gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, false);
+}
+
+// Persistent stream-K variant (batch == 1, no split-K, beta == 0, dense C zeroed by the launcher).  The tile space is
+// walked in raster order.  The first dp_tiles tiles (whole waves) are processed one tile per CTA per wave; the remaining
+// sk_tiles tiles (the last full wave + the partial wave) are cut into sk_units k-tile units that are divided evenly
+// over the first sk_ctas CTAs, so every SM finishes at the same time instead of idling through a partial last wave.
+// A tile whose k range is shared by several CTAs is accumulated with red.global.add.f64.
+struct SkPlan { int tiles_fast, dp_tiles, sk_tiles, kt, sk_ctas; long long sk_units; };
+template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
+  using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* As = reinterpret_cast<cplx*>(smem_raw);
+  cplx* Bs = As + Cfg::STAGES * Cfg::A_STAGE;
+  auto origin = [&](int tile, int& m_blk, int& n_blk) {
+    int fast = tile % pl.tiles_fast, slow = tile / pl.tiles_fast;
+    m_blk = (d.swap_raster ? slow : fast) * Cfg::BM;
+    n_blk = (d.swap_raster ? fast : slow) * Cfg::BN;
+  };
+  const int c = blockIdx.x;
+  if (c < pl.sk_ctas) {
+    long long u = pl.sk_units * c / pl.sk_ctas;
+    const long long u_end = pl.sk_units * (c + 1) / pl.sk_ctas;
+    while (u < u_end) {
+      int tile = (int)(u / pl.kt), k0 = (int)(u - (long long)tile * pl.kt);
+      int k1 = (int)min((long long)pl.kt, k0 + (u_end - u));
+      int m_blk, n_blk;
+      origin(pl.dp_tiles + tile, m_blk, n_blk);
+      gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), !(k0 == 0 && k1 == pl.kt));
+      u += k1 - k0;
+    }
+  }
+  for (int tile = c; tile < pl.dp_tiles; tile += gridDim.x) {
+    int m_blk, n_blk;
+    origin(tile, m_blk, n_blk);
+    gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, 0, 0, 0, d.K, false);
   }
 }
 
@@ -278,6 +331,40 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
   // Within a wave the CTAs share the operand indexed by the slow raster direction through L2; across waves the other
   // operand is re-read from DRAM.  Stream the operand with more bytes (A: M*K, B: K*N) only once.
   dd.swap_raster = (d.batch * d.ksplit == 1 && (long long)d.M > (long long)d.N && tm <= 65535 && tn_ > 1) ? 1 : 0;
+  if (d.streamk) {
+    // stream-K: only when the plain launch would leave a partial last wave (or less than one wave) of CTAs
+    static int slots = 0;
+    auto kern_sk = zgemm_sk_kernel<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>;
+    if (slots == 0) {
+      TN_CUDA(cudaFuncSetAttribute(kern_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      int per_sm = 0, dev = 0, sms = 0;
+      TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_sk, Cfg::THREADS, Cfg::SMEM_BYTES));
+      TN_CUDA(cudaGetDevice(&dev));
+      TN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      slots = std::max(1, per_sm * sms);
+    }
+    const long long T = (long long)tm * tn_;
+    const int KT = (d.K + Cfg::BK - 1) / Cfg::BK;
+    const long long waves = (T + slots - 1) / slots;
+    const double eff = (double)T / (double)(waves * slots);
+    if (eff < 0.94 && KT >= 16 && T < (1ll << 30)) {
+      SkPlan pl;
+      const long long full = T / slots;
+      pl.tiles_fast = dd.swap_raster ? (int)tn_ : (int)tm;
+      pl.dp_tiles = full >= 1 ? (int)((full - 1) * slots) : 0;
+      pl.sk_tiles = (int)(T - pl.dp_tiles);
+      pl.kt = KT;
+      pl.sk_units = (long long)pl.sk_tiles * KT;
+      pl.sk_ctas = (int)std::max<long long>(1, std::min<long long>(slots, pl.sk_units / 16));
+      const int grid = pl.dp_tiles > 0 ? slots : pl.sk_ctas;
+      // partial tiles are accumulated atomically: zero the (dense, possibly pitched) output first
+      TN_CUDA(cudaMemset2DAsync(d.C, (size_t)d.cn.s0 * sizeof(cplx), 0, (size_t)d.M * sizeof(cplx), (size_t)d.N, stream));
+      kern_sk<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd, pl);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      return;
+    }
+  }
   dim3 grid(dd.swap_raster ? tn_ : tm, dd.swap_raster ? tm : tn_, d.batch * d.ksplit);
   TN_CHECK(grid.y <= 65535 && grid.z <= 65535, "zgemm: grid too large");
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd);
@@ -316,8 +403,13 @@ void zgemm_auto(GemmDesc d, cudaStream_t stream) {
     // Large problems.  Default: 128 x 32 tiles, 4 warps, 2 CTAs per SM -- the two CTAs' k-tile barriers
     // de-synchronise so the DMMA pipe does not drain at every barrier (measured 29.8 vs 27.4 TFLOP/s for the
     // chi=1024 matvec against the single-CTA 128 x 64 tile).  TN_GEMM_VARIANT selects alternatives for A/B runs.
-    static int variant = -1;
+    static int variant = -1, use_sk = -1;
     if (variant < 0) { const char* e = getenv("TN_GEMM_VARIANT"); variant = e ? atoi(e) : 2; }
+    if (use_sk < 0) { const char* e = getenv("TN_GEMM_STREAMK"); use_sk = (e && e[0] == '0') ? 0 : 1; }
+    // stream-K needs a dense single-level C it may zero (leading dimension cn.s0 >= M), beta == 0 and a single problem
+    d.streamk = (use_sk && d.batch == 1 && d.ksplit == 1 && d.beta.x == 0.0 && d.beta.y == 0.0 && !d.cm.tab && !d.cn.tab &&
+                 d.cm.s0 == 1 && d.cm.n0 >= d.M && d.cn.n0 >= d.N && d.cn.s0 >= d.M && d.C != d.A && d.C != d.B &&
+                 (double)d.M * d.N * d.K >= 8.0e6) ? 1 : 0;
     if (variant == 0) launch<4, 2, 4, 4>(d, stream);                 // 128 x 64, 1 CTA / SM
     else if (variant == 1) launch<2, 2, 4, 4>(d, stream);            // 64 x 64, 2 CTAs / SM
     else if (variant == 3) launch<2, 1, 4, 4>(d, stream);            // 64 x 32, 4 CTAs / SM

@@ -45,3 +45,27 @@ def test_fused_two_level_indices():
                                 np.asfortranarray(Mo).reshape(-1, order='F'), (w, 1, w * d), (d, w, w * d * d), 0,
                                 ca * d * w2 * cb, (ca, 1, ca * d * w2), (BIG, ca, 0))
     assert relerr(C.reshape(ca, d, w2, cb, order='F'), want) < 1e-13
+
+
+def test_streamk_partial_waves_and_small_grids():
+    """Shapes that take the persistent stream-K path (partial last wave / less than one wave of 128x32 tiles on 296 CTA
+    slots, ragged edges, K not a multiple of 8): partial tiles are summed with red.global.add.f64 into a zeroed C."""
+    import tnb200
+    rng = np.random.default_rng(3)
+    for (M, N, K) in [(512, 128, 640), (1000, 250, 333), (2048, 512, 300), (1283, 997, 129), (4096, 1024, 136), (130, 4100, 200)]:
+        A, B = crandn(rng, M, K), crandn(rng, K, N)
+        C = tnb200.contract_strided(M, N, K, np.asfortranarray(A).reshape(-1, order='F'), (BIG, 1, 0), (BIG, M, 0), 0,
+                                    np.asfortranarray(B).reshape(-1, order='F'), (BIG, 1, 0), (BIG, K, 0), 0, M * N, (BIG, 1, 0), (BIG, M, 0))
+        assert relerr(C.reshape(M, N, order='F'), A @ B) < 1e-13, (M, N, K)
+
+
+def test_streamk_conj_kfast_operands():
+    """Stream-K with both operands k-contiguous and conjugated (the environment-update form conj(A)^T X)."""
+    import tnb200
+    rng = np.random.default_rng(4)
+    M, N, K = 700, 300, 520
+    A, B = crandn(rng, K, M), crandn(rng, N, K)
+    C = tnb200.contract_strided(M, N, K, np.asfortranarray(A).reshape(-1, order='F'), (BIG, K, 0), (BIG, 1, 0), 1,
+                                np.asfortranarray(B).reshape(-1, order='F'), (BIG, N, 0), (BIG, 1, 0), 1,
+                                M * N, (BIG, 1, 0), (BIG, M, 0), alpha=1.5 + 0.25j)
+    assert relerr(C.reshape(M, N, order='F'), (1.5 + 0.25j) * (A.conj().T @ B.conj().T)) < 1e-13

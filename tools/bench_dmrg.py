@@ -20,10 +20,12 @@ from tnb200._lib import check, tn_lanczos_t  # noqa: E402
 what = sys.argv[1:] or ["c1", "c2"]
 CHI_MAX = int(os.environ.get("CHI_MAX", "512"))
 ORACLE_CHI = int(os.environ.get("ORACLE_CHI", "64"))
+CUTOFF = float(os.environ.get("CUTOFF", "1e-12"))
+CHI_MIN = int(os.environ.get("CHI_MIN", "64"))
 ctx = tnb200.Context.default()
 
 
-def gpu_sweeps(psi, Hs, nsweeps, direction, maxdim, cutoff=1e-12):
+def gpu_sweeps(psi, Hs, nsweeps, direction, maxdim, cutoff=CUTOFF):
     out = []
     for _ in range(nsweeps):
         e, mb = C.c_double(), C.c_int64()
@@ -72,14 +74,14 @@ if "c2" in what:
     po.movecenter(1)
     oHs = oracle.ProjMPSSum([oracle.ProjMPS([po, oH, po], rank=2)])
     direction = False
-    chi = 64
+    chi = CHI_MIN
     while chi <= CHI_MAX:
         res, direction2 = gpu_sweeps(g, Hs, 2, direction, chi)
-        line = dict(config="C2 XXZ N=100 w=5 two-site DMRG", maxdim=chi, gpu=res)
+        line = dict(config="C2 XXZ N=100 w=5 two-site DMRG", maxdim=chi, cutoff=CUTOFF, gpu=res)
         if chi <= ORACLE_CHI:
             ho = []
             t0 = time.perf_counter()
-            dmrg_sweeps(po, oHs, maxdim=chi, cutoff=1e-12, minsweeps=2, maxsweeps=2, history=ho)   # 2 sweeps, reference contraction order
+            dmrg_sweeps(po, oHs, maxdim=chi, cutoff=CUTOFF, minsweeps=2, maxsweeps=2, history=ho)   # 2 sweeps, reference contraction order
             line["oracle"] = [dict(energy=h[1], maxbond=h[2]) for h in ho]
             line["oracle_s_per_sweep"] = (time.perf_counter() - t0) / 2
             line["energy_rel_diff"] = abs(res[-1]["energy"] - ho[-1][1]) / abs(ho[-1][1])
