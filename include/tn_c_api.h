@@ -150,6 +150,22 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
                     uint64_t seed, uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out,
                     int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out);
 
+/* Ensemble of independent QJMC trajectories (the caller's loop around qjmc_simulation, examples/qjmc.jl:52; SURVEY 8(e)
+ * trajectory-level parallelism).  All trajectories start from the same host MPS (dims: N x 3, site_ptrs) and the same gate
+ * list (arguments as tn_gates_upload).  They are handed out dynamically to `nworkers` host threads, each owning a CUDA
+ * stream + workspace on `device`, so that the small kernels of different trajectories overlap on the GPU.  Random numbers
+ * come from the counter-based generator keyed by (seed, traj_ids[t], step) (traj_ids == NULL: t), i.e. the result of a
+ * trajectory does not depend on the worker count or on which GPU / rank ran it.
+ * Outputs for the trajectory at position t: obs_out[(t * (steps / save_every) + s) * N + i], njumps_out[t],
+ * jumps_out / jumptimes_out[t * jump_cap + j] (any of the last three may be NULL). */
+int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const uint64_t* traj_ids,
+                         int32_t d, int32_t N, const int64_t* dims, const tn_cplx* const* site_ptrs, int32_t center,
+                         int32_t nrows, const int32_t* counts, const int32_t* gate_sites, const int32_t* gate_nsites,
+                         const tn_cplx* const* gate_ptrs, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
+                         const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t trunc, uint64_t seed,
+                         const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* njumps_out,
+                         int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap);
+
 #ifdef __cplusplus
 }
 #endif

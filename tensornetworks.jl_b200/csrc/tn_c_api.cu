@@ -1,7 +1,10 @@
 // extern "C" boundary of libtnb200 (declared in include/tn_c_api.h).
 #include "../../include/tn_c_api.h"
 #include "tn_mps.cuh"
+#include <atomic>
 #include <cstring>
+#include <mutex>
+#include <thread>
 
 namespace tn {
 int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,
@@ -10,6 +13,35 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
 }
 
 using namespace tn;
+
+// One context = one GPU + one stream + its workspaces (also used by the worker threads of tn_qjmc_ensemble).
+static void ctx_init(Ctx& c, int device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw tn::Error(TN_ERR_CUDA, "no CUDA device available: libtnb200 has no CPU fallback");
+  TN_CHECK(device >= 0 && device < ndev, "device index out of range");
+  TN_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop; TN_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) throw tn::Error(TN_ERR_CUDA, std::string("libtnb200 is built for sm_100a (B200) only; found ") + prop.name);
+  c.device = device;
+  TN_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool; TN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX; TN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  TN_CUDA(cudaMalloc((void**)&c.dscal, 64 * sizeof(cplx)));
+  TN_CUDA(cudaMemset(c.dscal, 0, 64 * sizeof(cplx)));
+  TN_CUDA(cudaMallocHost((void**)&c.hscal, 64 * sizeof(cplx)));
+  TN_CUDA(cudaMalloc((void**)&c.partials, 4 * (DOT_BLOCKS + 8) * sizeof(cplx)));
+}
+static void ctx_release(Ctx& c) {
+  cudaSetDevice(c.device);
+  if (c.stream) cudaStreamSynchronize(c.stream);
+  svd_free(c.svd);
+  for (auto& b : c.scratch) b.release();
+  cudaFree(c.dscal); cudaFreeHost(c.hscal); cudaFree(c.partials);
+  if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); for (auto& ev : c.copy_ev) cudaEventDestroy(ev); }
+  if (c.stream) cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+}
 
 struct tn_ctx { Ctx c; };
 struct tn_mps { Mps* m; };
@@ -37,35 +69,15 @@ int32_t tn_version(void) { return 100; }
 int32_t tn_ctx_create(int32_t device, tn_ctx** out) {
   return guard([&] {
     TN_CHECK(out != nullptr, "null output pointer");
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) throw tn::Error(TN_ERR_CUDA, "no CUDA device available: libtnb200 has no CPU fallback");
-    TN_CHECK(device >= 0 && device < ndev, "device index out of range");
-    TN_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop; TN_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) throw tn::Error(TN_ERR_CUDA, std::string("libtnb200 is built for sm_100a (B200) only; found ") + prop.name);
     auto* c = new tn_ctx();
-    c->c.device = device;
-    TN_CUDA(cudaStreamCreateWithFlags(&c->c.stream, cudaStreamNonBlocking));
-    cudaMemPool_t pool; TN_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX; TN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    TN_CUDA(cudaMalloc((void**)&c->c.dscal, 64 * sizeof(cplx)));
-    TN_CUDA(cudaMemset(c->c.dscal, 0, 64 * sizeof(cplx)));
-    TN_CUDA(cudaMallocHost((void**)&c->c.hscal, 64 * sizeof(cplx)));
-    TN_CUDA(cudaMalloc((void**)&c->c.partials, 4 * (DOT_BLOCKS + 8) * sizeof(cplx)));
+    try { ctx_init(c->c, device); } catch (...) { delete c; throw; }
     *out = c;
   });
 }
 int32_t tn_ctx_destroy(tn_ctx* ctx) {
   return guard([&] {
     if (!ctx) return;
-    cudaSetDevice(ctx->c.device);
-    cudaStreamSynchronize(ctx->c.stream);
-    svd_free(ctx->c.svd);
-    for (auto& b : ctx->c.scratch) b.release();
-    cudaFree(ctx->c.dscal); cudaFreeHost(ctx->c.hscal); cudaFree(ctx->c.partials);
-    if (ctx->c.copy_stream) { cudaStreamDestroy(ctx->c.copy_stream); for (auto& ev : ctx->c.copy_ev) cudaEventDestroy(ev); }
-    cudaStreamDestroy(ctx->c.stream);
+    ctx_release(ctx->c);
     delete ctx;
   });
 }
@@ -331,6 +343,57 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
     int nj = qjmc_run(psi->m, gates->g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), uniforms, seed, trajectory,
                       obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap);
     if (njumps_out) *njumps_out = nj;
+  });
+}
+
+int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const uint64_t* traj_ids,
+                         int32_t d, int32_t N, const int64_t* dims, const tn_cplx* const* site_ptrs, int32_t center,
+                         int32_t nrows, const int32_t* counts, const int32_t* gate_sites, const int32_t* gate_nsites,
+                         const tn_cplx* const* gate_ptrs, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
+                         const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, uint64_t seed, const tn_cplx* obs_op,
+                         int32_t save_every, tn_cplx* obs_out, int32_t* njumps_out, int32_t* jumps_out, double* jumptimes_out,
+                         int32_t jump_cap) {
+  return guard([&] {
+    TN_CHECK(ntraj >= 0 && nworkers >= 1 && dims && site_ptrs && counts && gate_sites && gate_nsites && gate_ptrs, "qjmc_ensemble: bad arguments");
+    TN_CHECK(!obs_op || (obs_out && save_every > 0), "qjmc_ensemble: obs_out / save_every missing");
+    std::vector<long long> dd((size_t)N * 3);
+    for (size_t i = 0; i < dd.size(); ++i) dd[i] = dims[i];
+    const int nsaves = (obs_op && save_every > 0) ? steps / save_every : 0;
+    const int nw = std::min<int>(nworkers, std::max(1, ntraj));
+    std::atomic<int> next{0};
+    std::mutex err_mu; std::string err; int err_code = 0;
+    auto worker = [&]() {
+      Ctx c;
+      Gates* g = nullptr; Mps* psi = nullptr;
+      try {
+        ctx_init(c, device);
+        g = gates_create(&c, d, nrows, counts, gate_sites, gate_nsites, reinterpret_cast<const cplx* const*>(gate_ptrs));
+        for (;;) {
+          { std::lock_guard<std::mutex> lk(err_mu); if (err_code) break; }
+          const int i = next.fetch_add(1);
+          if (i >= ntraj) break;
+          psi = mps_create(&c, 1, d, N, dd.data(), reinterpret_cast<const cplx* const*>(site_ptrs), center);
+          int nj = qjmc_run(psi, g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), nullptr, seed,
+                            traj_ids ? traj_ids[i] : (uint64_t)i, obs_op ? C(obs_op) : nullptr, save_every,
+                            obs_op ? C(obs_out) + (size_t)i * nsaves * N : nullptr,
+                            jumps_out ? jumps_out + (size_t)i * jump_cap : nullptr,
+                            jumptimes_out ? jumptimes_out + (size_t)i * jump_cap : nullptr, jump_cap);
+          if (njumps_out) njumps_out[i] = nj;
+          mps_free(psi); psi = nullptr;
+        }
+      } catch (const tn::Error& e) {
+        std::lock_guard<std::mutex> lk(err_mu); if (!err_code) { err_code = e.code; err = e.what(); }
+      } catch (const std::exception& e) {
+        std::lock_guard<std::mutex> lk(err_mu); if (!err_code) { err_code = TN_ERR_INTERNAL; err = e.what(); }
+      }
+      if (psi) mps_free(psi);
+      if (g) gates_free(g);
+      ctx_release(c);
+    };
+    std::vector<std::thread> pool;
+    for (int k = 0; k < nw; ++k) pool.emplace_back(worker);
+    for (auto& t : pool) t.join();
+    if (err_code) throw tn::Error(err_code, "qjmc_ensemble: " + err);
   });
 }
 

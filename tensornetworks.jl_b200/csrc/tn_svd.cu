@@ -34,6 +34,18 @@ __device__ __forceinline__ void rr_pair(int n, int step, int k, int& p, int& q) 
   p = min(a, b); q = max(a, b);
 }
 
+// Hermitian storage of the Gram matrix: only G[r][c] with r <= c is kept up to date
+__device__ __forceinline__ cplx herm_get(const cplx* G, int r, int c) {
+  if (r < c) return G[r * LDS_ + c];
+  cplx v = G[c * LDS_ + r];
+  return make_double2(v.x, -v.y);
+}
+__device__ __forceinline__ void herm_put(cplx* G, int r, int c, cplx v) {
+  if (r < c) G[r * LDS_ + c] = v;
+  else G[c * LDS_ + r] = make_double2(v.x, -v.y);
+}
+constexpr int NBLK = JB * (JB + 1) / 2;   // 2x2-block pairs (a <= b) of the 32 rotations of a step
+
 // One CTA (1024 threads) per column-block pair.  Per rotation step: 32 threads compute the 32 disjoint
 // rotations, then every thread applies both the row- and the column-rotation to one 2x2 block of G
 // (G' = R_a^H G_ab R_b) and the column rotation to two (row, pair) items of J: two barriers per step.
@@ -50,7 +62,9 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
   __shared__ int r_p[JB], r_q[JB];
   __shared__ int rotated;
   __shared__ double red[32];
+  __shared__ unsigned char blk_a[NBLK], blk_b[NBLK];
   const int tid = threadIdx.x;
+  { int a = tid >> 5, b = tid & 31; if (a <= b) { int i = a * JB - a * (a - 1) / 2 + (b - a); blk_a[i] = (unsigned char)a; blk_b[i] = (unsigned char)b; } }
   const cplx* gp = Gpart + (long long)blockIdx.x * JP * JP;
   for (int e = tid; e < JP * JP; e += EVD_THREADS) {
     int row = e % JP, col = e / JP;
@@ -114,22 +128,39 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
         r_cs[tid] = cs; r_s[tid] = s; r_p[tid] = p; r_q[tid] = q;
       }
       __syncthreads();
-      {
-        // G block (pair a rows, pair b cols): G' = R_a^H (G R_b),  R = [[cs, s], [-conj(s), cs]]
-        int a = tid >> 5, b = tid & 31;
+      if (tid < NBLK) {
+        // G block (pair a rows, pair b cols), a <= b only: G' = R_a^H (G R_b),  R = [[cs, s], [-conj(s), cs]].  G is
+        // Hermitian, so only the blocks on or above the block diagonal are updated (528 of 1024: the FP64 issue rate of
+        // the one SM bounds this kernel); element (r, c) lives at G[min][max], conjugated when r > c.
+        const int a = blk_a[tid], b = blk_b[tid];
         double ca = r_cs[a], cb = r_cs[b]; cplx sa = r_s[a], sb = r_s[b];
         bool ra = !(sa.x == 0.0 && sa.y == 0.0), rb = !(sb.x == 0.0 && sb.y == 0.0);
-        if ((ra || rb) && a < nact / 2 && b < nact / 2) {
+        if ((ra || rb) && b < nact / 2) {
           int pa = r_p[a], qa = r_q[a], pb = r_p[b], qb = r_q[b];
-          cplx g00 = G[pa * LDS_ + pb], g01 = G[pa * LDS_ + qb], g10 = G[qa * LDS_ + pb], g11 = G[qa * LDS_ + qb];
+          cplx g00, g01, g10, g11;
+          if (a == b) {
+            g00 = make_double2(G[pa * LDS_ + pa].x, 0.0); g11 = make_double2(G[qa * LDS_ + qa].x, 0.0);
+            g01 = G[pa * LDS_ + qa]; g10 = make_double2(g01.x, -g01.y);
+          } else {
+            g00 = herm_get(G, pa, pb); g01 = herm_get(G, pa, qb); g10 = herm_get(G, qa, pb); g11 = herm_get(G, qa, qb);
+          }
           // T = G R_b
           cplx t00, t01, t10, t11;
           { cplx y = cmulc(g01, sb), x = cmul(g00, sb); t00 = make_double2(cb * g00.x - y.x, cb * g00.y - y.y); t01 = make_double2(x.x + cb * g01.x, x.y + cb * g01.y); }
           { cplx y = cmulc(g11, sb), x = cmul(g10, sb); t10 = make_double2(cb * g10.x - y.x, cb * g10.y - y.y); t11 = make_double2(x.x + cb * g11.x, x.y + cb * g11.y); }
           // G' = R_a^H T : row0 = ca*T0 - sa*T1 ; row1 = conj(sa)*T0 + ca*T1
-          { cplx y = cmul(sa, t10), x = cmulc(t00, sa); G[pa * LDS_ + pb] = make_double2(ca * t00.x - y.x, ca * t00.y - y.y); G[qa * LDS_ + pb] = make_double2(x.x + ca * t10.x, x.y + ca * t10.y); }
-          { cplx y = cmul(sa, t11), x = cmulc(t01, sa); G[pa * LDS_ + qb] = make_double2(ca * t01.x - y.x, ca * t01.y - y.y); G[qa * LDS_ + qb] = make_double2(x.x + ca * t11.x, x.y + ca * t11.y); }
+          cplx n00, n01, n10, n11;
+          { cplx y = cmul(sa, t10), x = cmulc(t00, sa); n00 = make_double2(ca * t00.x - y.x, ca * t00.y - y.y); n10 = make_double2(x.x + ca * t10.x, x.y + ca * t10.y); }
+          { cplx y = cmul(sa, t11), x = cmulc(t01, sa); n01 = make_double2(ca * t01.x - y.x, ca * t01.y - y.y); n11 = make_double2(x.x + ca * t11.x, x.y + ca * t11.y); }
+          if (a == b) {
+            G[pa * LDS_ + pa] = make_double2(n00.x, 0.0); G[qa * LDS_ + qa] = make_double2(n11.x, 0.0);
+            G[pa * LDS_ + qa] = n01;
+          } else {
+            herm_put(G, pa, pb, n00); herm_put(G, pa, qb, n01); herm_put(G, qa, pb, n10); herm_put(G, qa, qb, n11);
+          }
         }
+      }
+      {
         // J columns: 64 rows x 32 pairs = 2048 items, two per thread
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
@@ -446,11 +477,13 @@ static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<lon
 // Jacobi sweeps on Z = [W ; V] (W: jrows x ncols_pad, V: ncols_pad x ncols_pad), leading dimension ldz.
 static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
-  int ksplit = std::max(1, std::min(16, (2 * 148 + np - 1) / np));
+  // Gram GEMM grid = np pairs x ksplit: fill the 2 x 148 CTA slots of the 64 x 64 kernel once (no partial second wave)
+  int ksplit = std::max(1, std::min(std::min(16, jrows / 64), (2 * 148) / np));
   int kchunk = ((jrows + ksplit - 1) / ksplit + 7) / 8 * 8;
   ksplit = (jrows + kchunk - 1) / kchunk;
-  ensure(w.Gpart, w.G_cap, (size_t)std::max(ksplit, 16) * np * JP * JP, s);
+  ensure(w.Gpart, w.G_cap, (size_t)std::max(ksplit, 32) * np * JP * JP, s);
   ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
+  ensure(w.Z2, w.Z2_cap, (size_t)w.ldz * w.ncols_pad, s);   // ping-pong partner of Z for the rotation GEMM
   const int* tab = pair_table(w, nb, s);
   static bool evd_cfg = false;
   const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
@@ -485,11 +518,14 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       a.M = w.ldz; a.N = JP; a.K = JP;
       a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
       a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
-      a.C = w.Z; a.cm = idx1(1); a.cn = cols;
+      // out of place (Z2(:,pair) = Z(:,pair) J; the pairs of a step cover every column), so the GEMM is free to use the
+      // 128 x 32 tile / 2 CTAs per SM configuration instead of the in-place 128 x 64 one
+      a.C = w.Z2; a.cm = idx1(1); a.cn = cols;
       a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
       a.batch = np; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
       a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
       zgemm_auto(a, s);
+      std::swap(w.Z, w.Z2); std::swap(w.Z_cap, w.Z2_cap);
     }
     unsigned long long bits = 0;
     TN_CUDA(cudaMemcpyAsync(&bits, w.offmax, 8, cudaMemcpyDeviceToHost, s));
@@ -518,8 +554,8 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
   const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
   if (!cfg) { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); cfg = true; }
   TN_CUDA(cudaMemsetAsync(R, 0, (size_t)npad * npad * sizeof(cplx), s));
-  ensure(w.Gpart, w.G_cap, (size_t)16 * JP * JP, s);
-  int ksplit = std::max(1, std::min(16, rows / 256));
+  ensure(w.Gpart, w.G_cap, (size_t)32 * JP * JP, s);
+  int ksplit = std::max(1, std::min(32, rows / 64));   // one 64 x 64 tile per panel: spread its K range over many SMs
   int kchunk = ((rows + ksplit - 1) / ksplit + 7) / 8 * 8;
   ksplit = (rows + kchunk - 1) / kchunk;
   cplx* Rinv = w.small; cplx* Rtot = w.small + JP * JP;
@@ -545,13 +581,17 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
     if (nt > 0) {
       cplx* T = Q + (long long)(pk + 1) * JP * ldq;
       // C = P^H T  (64 x nt), split-K partials -> R(pk, trail)
-      ensure(w.Cpart, w.Cpart_cap, (size_t)ksplit * JP * nt, s);
+      // 64 x 128 tiles, one CTA per SM: pick the split that fills one wave of 148 CTAs
+      int csplit = std::max(1, std::min(std::min(16, rows / 64), 148 / ((nt + 127) / 128)));
+      int cchunk = ((rows + csplit - 1) / csplit + 7) / 8 * 8;
+      csplit = (rows + cchunk - 1) / cchunk;
+      ensure(w.Cpart, w.Cpart_cap, (size_t)csplit * JP * nt, s);
       GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, w.Cpart, idx1(1), idx1(JP));
-      c.ksplit = ksplit; c.kchunk = kchunk; c.ssC = (long long)JP * nt;
+      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = (long long)JP * nt;
       zgemm_auto(c, s);
       cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
       int blocks; launch_1d((long long)JP * nt, blocks);
-      reduce_partials_kernel<<<blocks, 256, 0, s>>>(w.Cpart, ksplit, (long long)JP * nt, JP, nt, Rrow, npad, 0);
+      reduce_partials_kernel<<<blocks, 256, 0, s>>>(w.Cpart, csplit, (long long)JP * nt, JP, nt, Rrow, npad, 0);
       count_launch(1);
       // T <- T - P C
       zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
@@ -681,6 +721,7 @@ void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
 }
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
+  if (w.Z2) cudaFree(w.Z2);
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }

@@ -10,6 +10,7 @@ struct Trunc { double cutoff; long long maxdim; long long mindim; };
 // Workspace + state of one factorisation (owned by a Ctx; reused across calls).
 struct SvdWork {
   cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld = rows + ncols
+  cplx* Z2 = nullptr; size_t Z2_cap = 0;          // ping-pong partner of Z (rotation GEMM writes out of place)
   cplx* Gpart = nullptr; size_t G_cap = 0;        // split-K Gram partials
   cplx* J = nullptr; size_t J_cap = 0;            // per-pair 64x64 rotations
   double* sig = nullptr; int* perm = nullptr; size_t s_cap = 0;   // sorted singular values + permutation

@@ -68,6 +68,10 @@ struct TileCfg {
   static constexpr int B_PER_THR = BN * BK / THREADS;
 };
 
+// resident CTAs per SM the register allocation must allow: 4 / 2 for 2- / 4-warp CTAs, 2 for 8 warps with small warp tiles
+template <int WARPS_M, int WARPS_N, int TM, int TN>
+struct MinBlocks { static constexpr int value = (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : ((TM * TN <= 8) ? 2 : 1)); };
+
 // SIMPLE_K: both operands' k index is single-level without a lookup table, so each load slot just
 // advances a pointer by BK * stride per k-tile (no index arithmetic inside the pipeline).
 // One CTA tile: C[m_blk.., n_blk..] (+)= alpha * sum_{k in [k_begin, k_end)} op(A) op(B).
@@ -265,7 +269,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
 }
 
 template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_kernel(const GemmDesc d) {
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_kernel(const GemmDesc d) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* As = reinterpret_cast<cplx*>(smem_raw);
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 
 // A tile whose k range is shared by several CTAs is accumulated with red.global.add.f64.
 struct SkPlan { int tiles_fast, dp_tiles, sk_tiles, kt, sk_ctas; long long sk_units; };
 template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
-__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : 1)) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
+__global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* As = reinterpret_cast<cplx*>(smem_raw);

@@ -436,3 +436,40 @@ def qjmc_simulation(psi, gates, jump_sites, jump_ops, jump_coeffs, steps, dt, un
                           times.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(njumps)))
     n = min(njumps.value, cap)
     return list(jumps[:n]), list(times[:n]), obs[:nsaves]
+
+
+def qjmc_ensemble(tensors, center, gate_sites, gate_tensors, jump_sites, jump_ops, jump_coeffs, steps, dt, traj_ids, workers=8,
+                  device=0, seed=0, obs_op=None, save_every=1, cutoff=1e-12, maxdim=0, mindim=1):
+    """Many independent ``qjmc_simulation`` trajectories (the loop a user writes around algorithms/mps/qjmc.jl:28) from one
+    initial MPS, distributed over ``workers`` host threads / CUDA streams inside the library (tn_qjmc_ensemble).
+    Returns (njumps [T], jumps [T, steps+1], jumptimes [T, steps+1], observable [T, nsaves, N])."""
+    lib = _lib.load()
+    ts = [_f(t) for t in tensors]
+    N, d = len(ts), ts[0].shape[1]
+    dims = np.array([t.shape for t in ts], dtype=np.int64).reshape(N, 3)
+    sptr = (C.c_void_p * N)(*[t.ctypes.data for t in ts])
+    flat = [(int(s), _f(g)) for rs, rg in zip(gate_sites, gate_tensors) for s, g in zip(rs, rg)]
+    counts = np.array([len(r) for r in gate_sites], dtype=np.int32)
+    gs = np.array([s for s, _ in flat], dtype=np.int32)
+    gn = np.array([g.ndim // 2 for _, g in flat], dtype=np.int32)
+    gptr = (C.c_void_p * len(flat))(*[g.ctypes.data for _, g in flat])
+    js = np.asarray(jump_sites, dtype=np.int32)
+    jo = np.ascontiguousarray(np.stack([_f(o).T for o in jump_ops]))
+    jc = np.asarray(jump_coeffs, dtype=np.float64)
+    ids = np.ascontiguousarray(traj_ids, dtype=np.uint64)
+    T = len(ids)
+    nsaves = steps // save_every if obs_op is not None else 0
+    obs = np.zeros((T, max(nsaves, 1), N), dtype=np.complex128)
+    oo = None if obs_op is None else np.ascontiguousarray(_f(obs_op).T)
+    cap = steps + 1
+    njumps = np.zeros(T, dtype=np.int32)
+    jumps = np.zeros((T, cap), dtype=np.int32)
+    times = np.zeros((T, cap))
+    i32p, f64p = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    check(lib.tn_qjmc_ensemble(int(device), int(workers), T, ids.ctypes.data_as(C.POINTER(C.c_uint64)), d, N,
+                               dims.ctypes.data_as(C.POINTER(C.c_int64)), sptr, int(center), len(counts), counts.ctypes.data_as(i32p),
+                               gs.ctypes.data_as(i32p), gn.ctypes.data_as(i32p), gptr, len(js), js.ctypes.data_as(i32p), _ptr(jo),
+                               jc.ctypes.data_as(f64p), int(steps), float(dt), Trunc(cutoff, maxdim, mindim), int(seed),
+                               None if oo is None else _ptr(oo), int(save_every), _ptr(obs), njumps.ctypes.data_as(i32p),
+                               jumps.ctypes.data_as(i32p), times.ctypes.data_as(f64p), cap))
+    return njumps, jumps, times, obs[:, :nsaves]

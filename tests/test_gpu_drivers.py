@@ -159,3 +159,29 @@ def test_qjmc_trajectory_matches_oracle():
     assert gj == jumps and len(jumps) > 0
     assert np.allclose(gt, times)
     assert np.max(np.abs(np.real(obs) - np.array(ob.m[1:]))) < 1e-8
+
+
+def test_qjmc_ensemble_equals_single_trajectories():
+    """tn_qjmc_ensemble (worker threads / streams inside the library, dynamic trajectory hand-out) reproduces
+    tn_qjmc_run for the same (seed, trajectory id) keys, independently of the worker count."""
+    import tnb200
+    from tnb200 import models
+    N, d, dt, steps, chi = 8, 2, 0.02, 30, 8
+    gamma = 0.9
+    onsite = -1j * (1.0 * models.X + 2.0 * models.Z) - 0.5 * gamma * (models.SM.conj().T @ models.SM)
+    bond = -1j * 1.0 * np.kron(models.Z, models.Z)
+    ss, gg = models.trotter_gates(N, onsite, bond, dt, evol="imag", order=2)
+    tens = models.random_canonical_mps(N, d, chi, seed=5)
+    ids = [3, 11, 7, 0, 42]
+    kw = dict(cutoff=1e-12, maxdim=chi)
+    nj, jumps, times, obs = tnb200.qjmc_ensemble(tens, 1, ss, gg, list(range(1, N + 1)), [models.SM] * N, [np.sqrt(gamma)] * N, steps, dt,
+                                                 ids, workers=3, seed=9, obs_op=models.Z, save_every=5, **kw)
+    assert obs.shape == (len(ids), steps // 5, N)
+    gl = tnb200.GateList(d, ss, gg)
+    for k, t in enumerate(ids):
+        psi = tnb200.GMPS(1, d, tens, 1)
+        j1, t1, o1 = tnb200.qjmc_simulation(psi, gl, list(range(1, N + 1)), [models.SM] * N, [np.sqrt(gamma)] * N, steps, dt,
+                                            seed=9, trajectory=t, obs_op=models.Z, save_every=5, **kw)
+        assert list(jumps[k, :nj[k]]) == j1 and np.allclose(times[k, :nj[k]], t1)
+        assert np.max(np.abs(obs[k] - o1)) < 1e-9
+    assert nj.sum() > 0
