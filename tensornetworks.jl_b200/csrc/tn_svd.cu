@@ -15,6 +15,8 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <vector>
+#include <cstdlib>
 
 namespace tn {
 void count_launch(int n);
@@ -474,6 +476,35 @@ static bool precond_enabled() {
 
 static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
 
+// Optional phase timing (TN_SVD_PROFILE=1): CUDA events at the phase boundaries, summed per factorisation and printed
+// to stderr as one JSON line.  Diagnostics only; never enabled in tests or benches.
+struct SvdProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev; size_t used = 0;
+  std::vector<int> tag;                 // phase tag of the interval ENDING at event i
+  double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void mark(int t, cudaStream_t s) {
+    if (!on) return;
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); tag.push_back(0); }
+    tag[used] = t; cudaEventRecord(ev[used++], s);
+  }
+  void flush(cudaStream_t s) {
+    if (!on || used == 0) return;
+    cudaStreamSynchronize(s);
+    for (size_t i = 1; i < used; ++i) { float m = 0; cudaEventElapsedTime(&m, ev[i - 1], ev[i]); ms[tag[i]] += m; }
+    // keep the last event as the start of the next interval
+    std::swap(ev[0], ev[used - 1]); used = 1;
+  }
+};
+static SvdProf& prof() {
+  static thread_local SvdProf p;
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("TN_SVD_PROFILE"); on = (e && e[0] == '1') ? 1 : 0; }
+  p.on = on == 1;
+  return p;
+}
+enum { PH_START = 0, PH_GRAM = 1, PH_EVD = 2, PH_ROT = 3, PH_QR = 4, PH_FIN = 5, PH_MISC = 6 };
+
 // Jacobi sweeps on Z = [W ; V] (W: jrows x ncols_pad, V: ncols_pad x ncols_pad), leading dimension ldz.
 static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
@@ -511,9 +542,11 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       g.batch = np; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)np * JP * JP;
       zgemm_auto(g, s);
+      prof().mark(PH_GRAM, s);
       jacobi_evd64_kernel<<<np, EVD_THREADS, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps, nact);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
+      prof().mark(PH_EVD, s);
       GemmDesc a{};
       a.M = w.ldz; a.N = JP; a.K = JP;
       a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
@@ -526,7 +559,9 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
       zgemm_auto(a, s);
       std::swap(w.Z, w.Z2); std::swap(w.Z_cap, w.Z2_cap);
+      prof().mark(PH_ROT, s);
     }
+    prof().flush(s);
     unsigned long long bits = 0;
     TN_CUDA(cudaMemcpyAsync(&bits, w.offmax, 8, cudaMemcpyDeviceToHost, s));
     TN_CUDA(cudaStreamSynchronize(s));
@@ -629,6 +664,8 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   }
   if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
   int blocks;
+  SvdProf& pf = prof();
+  if (pf.on) { for (double& m : pf.ms) m = 0; pf.used = 0; pf.mark(PH_START, s); }
   if (!w.precond) {
     w.jrows = w.rows;
     w.ldz = w.rows + npad;
@@ -657,6 +694,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
     set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
     TN_CUDA(cudaGetLastError());
     count_launch(2);
+    pf.mark(PH_QR, s);
     jacobi_sweeps(w, npad, s);
   }
   colnorm2_kernel<<<npad, 128, 0, s>>>(w.Z, w.jrows, w.ldz, w.sig2);
@@ -670,6 +708,12 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   TN_CUDA(cudaMemcpyAsync(&k, w.kout, 4, cudaMemcpyDeviceToHost, s));
   TN_CUDA(cudaStreamSynchronize(s));
   w.k = k;
+  if (pf.on) {
+    pf.mark(PH_FIN, s); pf.flush(s);
+    fprintf(stderr, "{\"svd_profile\": {\"m\": %d, \"n\": %d, \"npad\": %d, \"precond\": %d, \"sweeps\": %d, \"qr_ms\": %.3f, \"gram_ms\": %.3f, "
+            "\"evd_ms\": %.3f, \"rot_ms\": %.3f, \"finish_ms\": %.3f}}\n", m, n, npad, (int)w.precond, w.sweeps, pf.ms[PH_QR], pf.ms[PH_GRAM],
+            pf.ms[PH_EVD], pf.ms[PH_ROT], pf.ms[PH_FIN]);
+  }
   return k;
 }
 
