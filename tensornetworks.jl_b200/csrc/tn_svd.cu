@@ -640,7 +640,11 @@ static void bgs_qr(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cudaS
   ensure(w.Rb, w.Rb_cap, (size_t)npad * npad, s);
   ensure(w.Rc, w.Rc_cap, (size_t)npad * npad, s);
   bgs_pass(w, Q, ldq, rows, npad, w.Rc, 3, s);    // R'  : shifted CholeskyQR3 panels (any conditioning)
-  bgs_pass(w, Q, ldq, rows, npad, w.Rb, 2, s);    // R'' : input already nearly orthonormal -> CholeskyQR2 panels
+  // R'' : the panels are orthonormal already and only lose O(delta) to the re-projection -> one (TN_SVD_REORTH_CHOL, default 2)
+  // Cholesky pass per panel restores orthonormality to O(eps)
+  static int reorth = -1;
+  if (reorth < 0) { const char* e = getenv("TN_SVD_REORTH_CHOL"); reorth = (e && e[0] == '1') ? 1 : 2; }
+  bgs_pass(w, Q, ldq, rows, npad, w.Rb, reorth, s);
   zgemm_auto(gd(npad, npad, npad, w.Rb, idx1(1), idx1(npad), 0, w.Rc, idx1(1), idx1(npad), 0, w.Ra, idx1(1), idx1(npad)), s);
 }
 

@@ -92,16 +92,24 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
   // ---- per-thread global->shared load assignment (fixed m/n, walking k) ------------------------
   // Each slot keeps its running k position as (k0, k1) = (k mod n0, k div n0) so that advancing by BK
   // needs no integer division inside the pipeline.
-  struct KPos { int k, k0, k1; };
-  auto kpos_init = [&](const Idx2& ix, int k) { KPos p; p.k = k; p.k1 = k / ix.n0; p.k0 = k - p.k1 * ix.n0; return p; };
-  auto kpos_off = [&](const Idx2& ix, const KPos& p) -> long long {
-    int l1 = p.k1;
-    if (ix.tab) l1 = ix.tab[(long long)ix.tab_bs * batch + p.k1];
-    return (long long)p.k0 * ix.s0 + (long long)l1 * ix.s1;
+  // (base = offset of the current level-1 block, looked up / multiplied only when k1 changes: the table lives in global
+  // memory and a lookup in front of every cp.async would put an L2 round trip into the load-issue path)
+  struct KPos { int k, k0, k1; long long base; };
+  auto kpos_base = [&](const Idx2& ix, int k1) -> long long {
+    int l1 = k1;
+    if (ix.tab) l1 = ix.tab[(long long)ix.tab_bs * batch + k1];
+    return (long long)l1 * ix.s1;
   };
-  auto kpos_adv = [&](const Idx2& ix, KPos& p) {
+  auto kpos_init = [&](const Idx2& ix, int k, int kend) {
+    KPos p; p.k = k; p.k1 = k / ix.n0; p.k0 = k - p.k1 * ix.n0; p.base = (!SIMPLE_K && k < kend) ? kpos_base(ix, p.k1) : 0; return p;
+  };
+  auto kpos_off = [&](const Idx2& ix, const KPos& p) -> long long { return (long long)p.k0 * ix.s0 + p.base; };
+  auto kpos_adv = [&](const Idx2& ix, KPos& p, int kend) {
     p.k += BK; p.k0 += BK;
-    while (p.k0 >= ix.n0) { p.k0 -= ix.n0; p.k1++; }
+    if (p.k0 >= ix.n0) {
+      while (p.k0 >= ix.n0) { p.k0 -= ix.n0; p.k1++; }
+      if (p.k < kend) p.base = kpos_base(ix, p.k1);
+    }
   };
   int a_m[Cfg::A_PER_THR], a_k[Cfg::A_PER_THR];
   const cplx* a_base[Cfg::A_PER_THR]; bool a_ok[Cfg::A_PER_THR]; KPos a_pos[Cfg::A_PER_THR];
@@ -112,7 +120,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     int m = m_blk + a_m[i];
     a_ok[i] = m < d.M;
     a_base[i] = Ab + (a_ok[i] ? idx_off_t(d.am, m, batch) : 0);
-    a_pos[i] = kpos_init(d.ak, k_begin + a_k[i]);
+    a_pos[i] = kpos_init(d.ak, k_begin + a_k[i], k_end);
     if (SIMPLE_K) a_base[i] += (long long)(k_begin + a_k[i]) * d.ak.s0;
   }
   int b_n[Cfg::B_PER_THR], b_k[Cfg::B_PER_THR];
@@ -124,7 +132,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     int n = n_blk + b_n[i];
     b_ok[i] = n < d.N;
     b_base[i] = Bb + (b_ok[i] ? idx_off_t(d.bn, n, batch) : 0);
-    b_pos[i] = kpos_init(d.bk, k_begin + b_k[i]);
+    b_pos[i] = kpos_init(d.bk, k_begin + b_k[i], k_end);
     if (SIMPLE_K) b_base[i] += (long long)(k_begin + b_k[i]) * d.bk.s0;
   }
 
@@ -153,14 +161,14 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
       bool p = a_ok[i] && (a_pos[i].k < k_end);
       long long off = p ? kpos_off(d.ak, a_pos[i]) : 0;
       cp_async16(as + a_k[i] * LDA + a_m[i], a_base[i] + off, p);
-      kpos_adv(d.ak, a_pos[i]);
+      kpos_adv(d.ak, a_pos[i], k_end);
     }
 #pragma unroll
     for (int i = 0; i < Cfg::B_PER_THR; ++i) {
       bool p = b_ok[i] && (b_pos[i].k < k_end);
       long long off = p ? kpos_off(d.bk, b_pos[i]) : 0;
       cp_async16(bs + b_k[i] * LDB + b_n[i], b_base[i] + off, p);
-      kpos_adv(d.bk, b_pos[i]);
+      kpos_adv(d.bk, b_pos[i], k_end);
     }
   };
 
