@@ -12,7 +12,8 @@ src/structures/mps/projmps.jl:107-134) = 3 contraction launches on the GPU.
   e2e        same metric through the public API call ProjMPS.product(A) with HOST buffers (pinned):
              Theta H2D and result D2H inside the timed region, environments resident (they are the
              state the reference's ProjMPS object carries between calls).
-  roofline   dominant kernel tn::zgemm_kernel<4,1,4,4,true> (the two chi^3 contractions), live CUDA events.
+  roofline   dominant kernel tn::zgemm_sk_kernel<4,1,4,4,true> (the two chi^3 contractions), live CUDA events.
+  extras     DMRG sweep wall time on the C2 chain at maxdim 64/128/256 (the other half of BASELINE.json's metric).
   cpu_baseline / --impl reference: the oracle's restatement of the reference's product() in the
              REFERENCE contraction order, NumPy/OpenBLAS with all host threads, bounded sample.
 N > 1: the chi = 1024 matvec does not shard: N independent replicas, scaling "weak".
@@ -81,6 +82,34 @@ def cpu_reference_arm(chi, budget_s=20.0, max_calls=6):
     return flops_matvec(chi, D, W) * calls / t_tot / 1e12, calls, t_tot, cores, out
 
 
+def dmrg_sweep_sample(ctx, N=100, chis=(64, 128, 256)):
+    """The other half of BASELINE.json's metric: wall time of full two-site DMRG sweeps (tn_dmrg_sweep: environments,
+    Lanczos with <=5 H_eff applications per bond, truncated Jacobi SVD, all on the device) on the C2 chain
+    (XXZ N=100, w=5, cutoff=1e-12), ramping maxdim; 2 sweeps per maxdim, the second one is reported."""
+    import tnb200
+    from tnb200._lib import check, tn_lanczos_t
+    rng = np.random.default_rng(1234)
+    dims = [1] + [min(2 ** min(i, N - i), 8) for i in range(1, N)] + [1]
+    tens = [rng.standard_normal((dims[i], D, dims[i + 1])) for i in range(N)]
+    g = tnb200.GMPS(1, D, tens, 0, ctx=ctx)
+    gH = tnb200.GMPS(2, D, tnb200.models.xxz_mpo(N, 1.0), ctx=ctx)
+    g.movecenter(1)
+    Hs = tnb200.ProjMPS(g, gH, g, center=1)
+    out, direction = [], False
+    for chi in chis:
+        for rep in range(2):
+            e, mb = C.c_double(), C.c_int64()
+            c0 = ctx.counters()
+            t0 = time.perf_counter()
+            check(ctx.lib.tn_dmrg_sweep(g.h, Hs.h, int(direction), tn_lanczos_t(3, 2, 1e-14), tnb200.Trunc(1e-12, chi, 1), C.byref(e), C.byref(mb)))
+            dt = time.perf_counter() - t0
+            c1 = ctx.counters()
+            direction = not direction
+        out.append({"maxdim": chi, "maxbond": mb.value, "seconds_per_sweep": dt, "energy": e.value, "gpu_launches": c1["launches"] - c0["launches"],
+                    "heff_applications": c1["matvecs"] - c0["matvecs"], "svds": c1["svds"] - c0["svds"]})
+    return {"config": "C2 XXZ chain N=100 w=5 two-site DMRG, cutoff=1e-12, random chi=8 start, 2 sweeps per maxdim (2nd timed)", "sweeps": out}
+
+
 class ClockSampler:
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -139,6 +168,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--chi", type=int, default=CHI)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the DMRG sweep-time sample")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -256,12 +286,23 @@ def main():
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                     "api": "tnb200.ProjMPS.product(A_host) -> tn_env_product", "matches_resident_path_rel": same},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": zgemm_peak, "unit": "TFLOP/s", "frac": achieved / zgemm_peak,
-                         "traffic": None, "kernel": "tn::zgemm_kernel<4,1,4,4,true> (128x32 tile, 2 CTAs/SM, DMMA.8x8x4), 2 launches per matvec",
+                         "traffic": None, "kernel": "tn::zgemm_sk_kernel<4,1,4,4,true> (persistent stream-K, 128x32 tile, 2 CTAs/SM, DMMA.8x8x4), 2 launches per matvec",
                          "flops_per_launch": big_flops, "ms_per_launch": (stage_ms[0] + stage_ms[2]) / 2,
                          "peak_source": "cuBLAS ZGEMM 4096^3 via torch.matmul measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "DMMA issue peak measured 37.17 TFLOP/s, profiles/r01_probe_fp64.jsonl)",
                          "stage_ms": {"L.Theta": stage_ms[0], ".W": stage_ms[1], ".R": stage_ms[2]}},
         }
+        # DRAM traffic of the dominant kernel from the committed ncu --set full capture (per launch, same shapes)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "zgemm_traffic.json")))
+            if tr.get("chi") == chi:
+                line["roofline"]["traffic"] = tr["dram_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = tr["source"]
+                line["roofline"]["algorithmic_bytes_per_launch"] = tr.get("algorithmic_bytes_per_launch")
+        except Exception:
+            pass
+        if world == 1 and not args.no_extras:
+            line["extras"] = {"dmrg_sweep": dmrg_sweep_sample(ctx)}
         if world == 1 and not args.no_cpu_baseline:
             tf, calls, secs, cores, ref_out = cpu_reference_arm(chi, budget_s=20.0)
             err = float(np.linalg.norm(ref_out.reshape(-1, order='F') - dev_out) / np.linalg.norm(dev_out))

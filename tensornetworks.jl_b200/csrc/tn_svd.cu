@@ -548,7 +548,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
       count_launch(1);
       prof().mark(PH_EVD, s);
       GemmDesc a{};
-      a.M = w.ldz; a.N = JP; a.K = JP;
+      a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;   // W rows + V rows (ldz may carry padding rows)
       a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
       a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
       // out of place (Z2(:,pair) = Z(:,pair) J; the pairs of a step cover every column), so the GEMM is free to use the
@@ -640,12 +640,20 @@ static void bgs_qr(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cudaS
   ensure(w.Rb, w.Rb_cap, (size_t)npad * npad, s);
   ensure(w.Rc, w.Rc_cap, (size_t)npad * npad, s);
   bgs_pass(w, Q, ldq, rows, npad, w.Rc, 3, s);    // R'  : shifted CholeskyQR3 panels (any conditioning)
-  // R'' : the panels are orthonormal already and only lose O(delta) to the re-projection -> one (TN_SVD_REORTH_CHOL, default 2)
+  // R'' : the panels are orthonormal already and only lose O(delta) to the re-projection -> one (TN_SVD_REORTH_CHOL=2: two)
   // Cholesky pass per panel restores orthonormality to O(eps)
   static int reorth = -1;
-  if (reorth < 0) { const char* e = getenv("TN_SVD_REORTH_CHOL"); reorth = (e && e[0] == '1') ? 1 : 2; }
+  if (reorth < 0) { const char* e = getenv("TN_SVD_REORTH_CHOL"); reorth = (e && e[0] == '2') ? 2 : 1; }
   bgs_pass(w, Q, ldq, rows, npad, w.Rb, reorth, s);
   zgemm_auto(gd(npad, npad, npad, w.Rb, idx1(1), idx1(npad), 0, w.Rc, idx1(1), idx1(npad), 0, w.Ra, idx1(1), idx1(npad)), s);
+}
+
+// Leading dimension of Z: a column stride that is a large power of two (2*npad*16 B = 64 KiB at n = 2048) maps the
+// k-walk of the Gram / rotation GEMMs onto few DRAM channels; 8 padding rows (128 B) break the pattern.
+static int pad_ld(int rows) {
+  static int pad = -1;
+  if (pad < 0) { const char* e = getenv("TN_SVD_LDPAD"); pad = e ? atoi(e) : 8; }
+  return (rows % 64 == 0) ? rows + pad : rows;
 }
 
 int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
@@ -672,7 +680,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   if (pf.on) { for (double& m : pf.ms) m = 0; pf.used = 0; pf.mark(PH_START, s); }
   if (!w.precond) {
     w.jrows = w.rows;
-    w.ldz = w.rows + npad;
+    w.ldz = pad_ld(w.rows + npad);
     ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
     launch_1d((long long)w.ldz * npad, blocks);
     svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Z, w.rows, w.ncols, npad, w.ldz);
@@ -692,7 +700,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
     count_launch(1);
     bgs_qr(w, w.Q2, npad, npad, npad, s);                        // Ra = R2
     w.jrows = npad;
-    w.ldz = 2 * npad;
+    w.ldz = pad_ld(2 * npad);
     ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
     conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Z, w.ldz);   // W <- R2^H
     set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
