@@ -72,12 +72,16 @@ struct TileCfg {
 template <int WARPS_M, int WARPS_N, int TM, int TN>
 struct MinBlocks { static constexpr int value = (WARPS_M * WARPS_N <= 2) ? 4 : ((WARPS_M * WARPS_N <= 4) ? 2 : ((TM * TN <= 8) ? 2 : 1)); };
 
-// SIMPLE_K: both operands' k index is single-level without a lookup table, so each load slot just
-// advances a pointer by BK * stride per k-tile (no index arithmetic inside the pipeline).
+// KMODE selects how the load slots walk the k index:
+//   1 (simple)  both operands' k index is single-level without a lookup table: each slot advances a pointer by
+//               BK * stride per k-tile (no index arithmetic inside the pipeline);
+//   2 (aligned) two-level / table k index whose level-1 blocks are multiples of BK (Jacobi column-block pairs): the same
+//               pointer walk, plus one shared pointer correction per operand when a k-tile enters the next block;
+//   0 (general) any two-level index (e.g. k = (w, s') with w = 5): per-slot (k0, k1) bookkeeping.
 // One CTA tile: C[m_blk.., n_blk..] (+)= alpha * sum_{k in [k_begin, k_end)} op(A) op(B).
 // ATOMIC = false: C = alpha*acc + beta*C (plain stores); ATOMIC = true: C += alpha*acc with red.global.add.f64
 // (stream-K partial tiles; C was zeroed by the launcher).
-template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs, const int m_blk, const int n_blk, const int batch,
                                           const int split, const int k_begin, const int k_end, const bool atomic) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -101,7 +105,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     return (long long)l1 * ix.s1;
   };
   auto kpos_init = [&](const Idx2& ix, int k, int kend) {
-    KPos p; p.k = k; p.k1 = k / ix.n0; p.k0 = k - p.k1 * ix.n0; p.base = (!SIMPLE_K && k < kend) ? kpos_base(ix, p.k1) : 0; return p;
+    KPos p; p.k = k; p.k1 = k / ix.n0; p.k0 = k - p.k1 * ix.n0; p.base = (KMODE == 0 && k < kend) ? kpos_base(ix, p.k1) : 0; return p;
   };
   auto kpos_off = [&](const Idx2& ix, const KPos& p) -> long long { return (long long)p.k0 * ix.s0 + p.base; };
   auto kpos_adv = [&](const Idx2& ix, KPos& p, int kend) {
@@ -121,7 +125,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     a_ok[i] = m < d.M;
     a_base[i] = Ab + (a_ok[i] ? idx_off_t(d.am, m, batch) : 0);
     a_pos[i] = kpos_init(d.ak, k_begin + a_k[i], k_end);
-    if (SIMPLE_K) a_base[i] += (long long)(k_begin + a_k[i]) * d.ak.s0;
+    if (KMODE == 1) a_base[i] += (long long)(k_begin + a_k[i]) * d.ak.s0;
   }
   int b_n[Cfg::B_PER_THR], b_k[Cfg::B_PER_THR];
   const cplx* b_base[Cfg::B_PER_THR]; bool b_ok[Cfg::B_PER_THR]; KPos b_pos[Cfg::B_PER_THR];
@@ -133,7 +137,20 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     b_ok[i] = n < d.N;
     b_base[i] = Bb + (b_ok[i] ? idx_off_t(d.bn, n, batch) : 0);
     b_pos[i] = kpos_init(d.bk, k_begin + b_k[i], k_end);
-    if (SIMPLE_K) b_base[i] += (long long)(k_begin + b_k[i]) * d.bk.s0;
+    if (KMODE == 1) b_base[i] += (long long)(k_begin + b_k[i]) * d.bk.s0;
+  }
+  // KMODE 2: per-operand block state (k of the next tile, elements left in the current level-1 block, its index / offset)
+  int a_kt = k_begin, b_kt = k_begin, a_left = 0, b_left = 0, a_k1 = 0, b_k1 = 0;
+  long long a_cur = 0, b_cur = 0;
+  if (KMODE == 2) {
+    a_k1 = k_begin / d.ak.n0; b_k1 = k_begin / d.bk.n0;
+    const int a_k0 = k_begin - a_k1 * d.ak.n0, b_k0 = k_begin - b_k1 * d.bk.n0;
+    a_left = d.ak.n0 - a_k0; b_left = d.bk.n0 - b_k0;
+    if (k_begin < k_end) { a_cur = kpos_base(d.ak, a_k1); b_cur = kpos_base(d.bk, b_k1); }
+#pragma unroll
+    for (int i = 0; i < Cfg::A_PER_THR; ++i) a_base[i] += (long long)(a_k0 + a_k[i]) * d.ak.s0 + a_cur;
+#pragma unroll
+    for (int i = 0; i < Cfg::B_PER_THR; ++i) b_base[i] += (long long)(b_k0 + b_k[i]) * d.bk.s0 + b_cur;
   }
 
   // loads the next k-tile (tiles are always requested in increasing order)
@@ -141,7 +158,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
   auto load_stage = [&](int stage) {
     cplx* as = As + stage * Cfg::A_STAGE;
     cplx* bs = Bs + stage * Cfg::B_STAGE;
-    if (SIMPLE_K) {
+    if (KMODE == 1) {
 #pragma unroll
       for (int i = 0; i < Cfg::A_PER_THR; ++i) {
         bool p = a_ok[i] && (a_pos[i].k < k_end);
@@ -154,21 +171,48 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
         cp_async16(bs + b_k[i] * LDB + b_n[i], p ? b_base[i] : Bb, p);
         b_base[i] += b_step; b_pos[i].k += BK;
       }
-      return;
-    }
+    } else if (KMODE == 2) {
 #pragma unroll
-    for (int i = 0; i < Cfg::A_PER_THR; ++i) {
-      bool p = a_ok[i] && (a_pos[i].k < k_end);
-      long long off = p ? kpos_off(d.ak, a_pos[i]) : 0;
-      cp_async16(as + a_k[i] * LDA + a_m[i], a_base[i] + off, p);
-      kpos_adv(d.ak, a_pos[i], k_end);
-    }
+      for (int i = 0; i < Cfg::A_PER_THR; ++i) {
+        bool p = a_ok[i] && (a_kt + a_k[i] < k_end);
+        cp_async16(as + a_k[i] * LDA + a_m[i], p ? a_base[i] : Ab, p);
+        a_base[i] += a_step;
+      }
+      a_kt += BK; a_left -= BK;
+      if (a_left <= 0 && a_kt < k_end) {          // the next tile starts a new level-1 block: shift every slot's pointer
+        const long long nb = kpos_base(d.ak, ++a_k1), delta = nb - a_cur - (long long)d.ak.n0 * d.ak.s0;
 #pragma unroll
-    for (int i = 0; i < Cfg::B_PER_THR; ++i) {
-      bool p = b_ok[i] && (b_pos[i].k < k_end);
-      long long off = p ? kpos_off(d.bk, b_pos[i]) : 0;
-      cp_async16(bs + b_k[i] * LDB + b_n[i], b_base[i] + off, p);
-      kpos_adv(d.bk, b_pos[i], k_end);
+        for (int i = 0; i < Cfg::A_PER_THR; ++i) a_base[i] += delta;
+        a_cur = nb; a_left = d.ak.n0;
+      }
+#pragma unroll
+      for (int i = 0; i < Cfg::B_PER_THR; ++i) {
+        bool p = b_ok[i] && (b_kt + b_k[i] < k_end);
+        cp_async16(bs + b_k[i] * LDB + b_n[i], p ? b_base[i] : Bb, p);
+        b_base[i] += b_step;
+      }
+      b_kt += BK; b_left -= BK;
+      if (b_left <= 0 && b_kt < k_end) {
+        const long long nb = kpos_base(d.bk, ++b_k1), delta = nb - b_cur - (long long)d.bk.n0 * d.bk.s0;
+#pragma unroll
+        for (int i = 0; i < Cfg::B_PER_THR; ++i) b_base[i] += delta;
+        b_cur = nb; b_left = d.bk.n0;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < Cfg::A_PER_THR; ++i) {
+        bool p = a_ok[i] && (a_pos[i].k < k_end);
+        long long off = p ? kpos_off(d.ak, a_pos[i]) : 0;
+        cp_async16(as + a_k[i] * LDA + a_m[i], a_base[i] + off, p);
+        kpos_adv(d.ak, a_pos[i], k_end);
+      }
+#pragma unroll
+      for (int i = 0; i < Cfg::B_PER_THR; ++i) {
+        bool p = b_ok[i] && (b_pos[i].k < k_end);
+        long long off = p ? kpos_off(d.bk, b_pos[i]) : 0;
+        cp_async16(bs + b_k[i] * LDB + b_n[i], b_base[i] + off, p);
+        kpos_adv(d.bk, b_pos[i], k_end);
+      }
     }
   };
 
@@ -276,7 +320,7 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
   }
 }
 
-template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_kernel(const GemmDesc d) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -288,7 +332,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * Cfg::BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * Cfg::BN;
   const int k_begin = split * d.kchunk;
   const int k_end = min(d.K, k_begin + d.kchunk);
-  gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, false);
+  gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, false);
 }
 
 // Persistent stream-K variant (batch == 1, no split-K, beta == 0, dense C zeroed by the launcher).  The tile space is
@@ -297,7 +341,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 // over the first sk_ctas CTAs, so every SM finishes at the same time instead of idling through a partial last wave.
 // A tile whose k range is shared by several CTAs is accumulated with red.global.add.f64.
 struct SkPlan { int tiles_fast, dp_tiles, sk_tiles, kt, sk_ctas; long long sk_units; };
-template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,22 +361,22 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
       int k1 = (int)min((long long)pl.kt, k0 + (u_end - u));
       int m_blk, n_blk;
       origin(pl.dp_tiles + tile, m_blk, n_blk);
-      gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), !(k0 == 0 && k1 == pl.kt));
+      gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), !(k0 == 0 && k1 == pl.kt));
       u += k1 - k0;
     }
   }
   for (int tile = c; tile < pl.dp_tiles; tile += gridDim.x) {
     int m_blk, n_blk;
     origin(tile, m_blk, n_blk);
-    gemm_tile<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>(d, As, Bs, m_blk, n_blk, 0, 0, 0, d.K, false);
+    gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, 0, d.K, false);
   }
 }
 
-template <int WARPS_M, int WARPS_N, int TM, int TN, bool SIMPLE_K>
+template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 static void launch2(const GemmDesc& d, cudaStream_t stream) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
   static bool configured = false;
-  auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>;
+  auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN, KMODE>;
   if (!configured) {
     TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -346,7 +390,7 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
   if (d.streamk) {
     // stream-K: only when the plain launch would leave a partial last wave (or less than one wave) of CTAs
     static int slots = 0;
-    auto kern_sk = zgemm_sk_kernel<WARPS_M, WARPS_N, TM, TN, SIMPLE_K>;
+    auto kern_sk = zgemm_sk_kernel<WARPS_M, WARPS_N, TM, TN, KMODE>;
     if (slots == 0) {
       TN_CUDA(cudaFuncSetAttribute(kern_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
       int per_sm = 0, dev = 0, sms = 0;
@@ -386,9 +430,14 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
 
 template <int WARPS_M, int WARPS_N, int TM, int TN>
 static void launch(const GemmDesc& d, cudaStream_t stream) {
-  bool simple = d.ak.tab == nullptr && d.bk.tab == nullptr && d.ak.n0 >= d.K && d.bk.n0 >= d.K;
-  if (simple) launch2<WARPS_M, WARPS_N, TM, TN, true>(d, stream);
-  else launch2<WARPS_M, WARPS_N, TM, TN, false>(d, stream);
+  using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
+  const bool simple = d.ak.tab == nullptr && d.bk.tab == nullptr && d.ak.n0 >= d.K && d.bk.n0 >= d.K;
+  // level-1 blocks (or the whole index) are multiples of BK and every split starts on a tile boundary
+  auto blk_ok = [&](const Idx2& ix) { return ix.n0 >= d.K || ix.n0 % Cfg::BK == 0; };
+  const bool aligned = blk_ok(d.ak) && blk_ok(d.bk) && (d.ksplit <= 1 || d.kchunk % Cfg::BK == 0);
+  if (simple) launch2<WARPS_M, WARPS_N, TM, TN, 1>(d, stream);
+  else if (aligned) launch2<WARPS_M, WARPS_N, TM, TN, 2>(d, stream);
+  else launch2<WARPS_M, WARPS_N, TM, TN, 0>(d, stream);
 }
 
 void zgemm(const GemmDesc& d, cudaStream_t stream) { launch<4, 2, 4, 4>(d, stream); }

@@ -69,3 +69,16 @@ def test_streamk_conj_kfast_operands():
                                 np.asfortranarray(B).reshape(-1, order='F'), (BIG, N, 0), (BIG, 1, 0), 1,
                                 M * N, (BIG, 1, 0), (BIG, M, 0), alpha=1.5 + 0.25j)
     assert relerr(C.reshape(M, N, order='F'), (1.5 + 0.25j) * (A.conj().T @ B.conj().T)) < 1e-13
+
+
+def test_two_level_k_blocks_aligned_to_tile():
+    """k = (k0, k1) with the level-1 block a multiple of the 8-deep k-tile (pointer-walking load path, KMODE 2):
+    C[m,n] = sum_{k0,k1} A(k0,m,k1) B(n,k0,k1)."""
+    import tnb200
+    rng = np.random.default_rng(7)
+    for (k0, k1, M, N) in [(16, 6, 50, 40), (8, 9, 130, 70), (32, 2, 300, 64)]:
+        A, B = crandn(rng, k0, M, k1), crandn(rng, N, k0, k1)
+        want = np.einsum('amb,nab->mn', A, B)
+        C = tnb200.contract_strided(M, N, k0 * k1, np.asfortranarray(A).reshape(-1, order='F'), (BIG, k0, 0), (k0, 1, k0 * M), 0,
+                                    np.asfortranarray(B).reshape(-1, order='F'), (k0, N, N * k0), (BIG, 1, 0), 0, M * N, (BIG, 1, 0), (BIG, M, 0))
+        assert relerr(C.reshape(M, N, order='F'), want) < 1e-13, (k0, k1, M, N)
