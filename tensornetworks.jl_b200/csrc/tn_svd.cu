@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1, then old Rtot
   __shared__ double red[8];
   __shared__ int nullcol[JP];
-  __shared__ double piv;            // 1 / R(j,j) of the current column (0 = null / failed pivot)
+  __shared__ double rrow[JP];       // 1 / R(j,j) per row (0 = null / failed pivot)
   __shared__ double rdinv[JP];      // reciprocal diagonal of R (divisions cost ~600 cycles of FP64 latency: do each once)
   const int tid = threadIdx.x;
   double fro = 0;
@@ -325,44 +325,44 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
     } else if (row == col) { G[row][col].x += shift; G[row][col].y = 0; }
   }
   __syncthreads();
-  // Left-looking Cholesky G = R^H R.  FP64 dependent-issue latency (~60 cycles) bounds this kernel, so every column's
-  // dot product is split over 4 threads x 2 partial sums and combined with shuffles: lane = part*8 + (c % 8),
-  // i.e. a quarter-warp reads 8 consecutive columns of one row (conflict-free LDS.128); two barriers per column.
+  // Right-looking Cholesky G = R^H R, one barrier per column: step j only READS row j (final since step j-1) and
+  // applies the rank-1 update G(i,c) -= conj(G(j,i)) G(j,c) / G(j,j) to the trailing upper triangle, every thread
+  // deriving 1/G(j,j) itself (no broadcast barrier); the rows are scaled by 1/sqrt(G(j,j)) in one pass at the end.
+  // Thread t owns column c = t % 64 and rows (t / 64) + 4q.
   const int lane = tid & 31, wrp = tid >> 5;
   const int cc = (lane & 7) + 8 * wrp, part = lane >> 3;
-  for (int j = 0; j < JP; ++j) {
-    double ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;
-    if (cc >= j) {
-      int k = part;
-      for (; k + 4 < j; k += 8) {
-        cplx a = G[k][j], b = G[k][cc], a2 = G[k + 4][j], b2 = G[k + 4][cc];
-        ar0 += a.x * b.x + a.y * b.y; ai0 += a.x * b.y - a.y * b.x;       // conj(R(k,j)) R(k,c)
-        ar1 += a2.x * b2.x + a2.y * b2.y; ai1 += a2.x * b2.y - a2.y * b2.x;
+  {
+    const int c = tid & 63, i0 = tid >> 6;
+    for (int j = 0; j < JP; ++j) {
+      const double dd = G[j][j].x;
+      const bool bad = nullcol[j] || !(dd > 0.0) || !isfinite(dd);
+      const double ri = bad ? 0.0 : rsqrt(dd);
+      const double sc = ri * ri;
+      if (tid == 0) { rrow[j] = ri; rdinv[j] = bad ? 1.0 : ri; }
+      if (!bad && c > j) {
+        const cplx gjc = G[j][c];
+#pragma unroll
+        for (int q = 0; q < JP / 4; ++q) {
+          const int i = i0 + 4 * q;
+          if (i > j && i <= c) {
+            const cplx gji = G[j][i];
+            const double ar = gji.x * gjc.x + gji.y * gjc.y, ai = gji.x * gjc.y - gji.y * gjc.x;   // conj(G(j,i)) G(j,c)
+            cplx v = G[i][c];
+            v.x = fma(-sc, ar, v.x); v.y = fma(-sc, ai, v.y);
+            G[i][c] = v;
+          }
+        }
       }
-      if (k < j) { cplx a = G[k][j], b = G[k][cc]; ar0 += a.x * b.x + a.y * b.y; ai0 += a.x * b.y - a.y * b.x; }
+      __syncthreads();
     }
-    double sr = ar0 + ar1, si = ai0 + ai1;
-    sr += __shfl_xor_sync(0xffffffffu, sr, 8); si += __shfl_xor_sync(0xffffffffu, si, 8);
-    sr += __shfl_xor_sync(0xffffffffu, sr, 16); si += __shfl_xor_sync(0xffffffffu, si, 16);
-    cplx v = make_double2(0, 0);
-    if (part == 0 && cc >= j) {
-      v = G[j][cc]; v.x -= sr; v.y -= si;
-      if (cc == j) {
-        double dd = v.x;
-        double ri = (nullcol[j] || !(dd > 0.0) || !isfinite(dd)) ? 0.0 : rsqrt(dd);
-        piv = ri;
-        rdinv[j] = ri == 0.0 ? 1.0 : ri;
-      }
+    for (int e = tid; e < JP * JP; e += 256) {
+      const int row = e / JP, col = e % JP;
+      if (col < row) { G[row][col] = make_double2(0, 0); continue; }
+      const double ri = rrow[row];
+      if (ri == 0.0) G[row][col] = make_double2(col == row ? 1.0 : 0.0, 0.0);          // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0
+      else { cplx v = G[row][col]; G[row][col] = (col == row) ? make_double2(v.x * ri, 0.0) : make_double2(v.x * ri, v.y * ri); }
     }
-    __syncthreads();
-    double ri = piv;
-    if (part == 0 && cc >= j) {
-      if (ri == 0.0) G[j][cc] = make_double2(cc == j ? 1.0 : 0.0, 0.0);          // null / failed pivot: R(j,j) = 1, R(j,j+1:) = 0
-      else G[j][cc] = (cc == j) ? make_double2(v.x * ri, 0.0) : make_double2(v.x * ri, v.y * ri);
-    }
-    __syncthreads();
   }
-  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; if (row > col) G[row][col] = make_double2(0, 0); }
   __syncthreads();
   // R^-1 by back substitution: column cc of the inverse, rows i = cc .. 0; the row's dot product is split over the 4
   // threads of the column group.  Each warp owns 8 columns, so only warp-level synchronisation is needed.
