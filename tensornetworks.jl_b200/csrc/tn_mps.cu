@@ -493,7 +493,8 @@ static void eigh_sym3(int K, const double T[3][3], double* D, double U[3][3]) {
       }
   }
   int ord[3] = {0, 1, 2};
-  std::sort(ord, ord + K, [&](int a, int b) { return A[a][a] < A[b][b]; });
+  for (int i = 1; i < K; ++i)            // insertion sort of <= 3 indices by eigenvalue
+    for (int j = i; j > 0 && A[ord[j]][ord[j]] < A[ord[j - 1]][ord[j - 1]]; --j) std::swap(ord[j], ord[j - 1]);
   double Us[3][3];
   for (int j = 0; j < K; ++j) { D[j] = A[ord[j]][ord[j]]; for (int i = 0; i < K; ++i) Us[i][j] = U[i][ord[j]]; }
   for (int i = 0; i < K; ++i) for (int j = 0; j < K; ++j) U[i][j] = Us[i][j];

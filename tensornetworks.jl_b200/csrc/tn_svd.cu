@@ -527,37 +527,80 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   // (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
   const int inner_sweeps = (np == 1) ? 12 : 1;
   const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
+  // pair groups on separate streams (TN_SVD_GROUPS, default 4) once a step has enough pairs to split
+  static int want_groups = -1;
+  if (want_groups < 0) { const char* e = getenv("TN_SVD_GROUPS"); want_groups = e ? std::max(1, std::min(SvdWork::MAX_GROUPS, atoi(e))) : 4; }
+  const int ngroups = (np >= 4 * want_groups) ? want_groups : 1;
+  int gksplit = ksplit, gkchunk = kchunk;
+  if (ngroups > 1) {
+    if (!w.fork_ev) {
+      TN_CUDA(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
+      for (int gi = 0; gi < SvdWork::MAX_GROUPS; ++gi) {
+        TN_CUDA(cudaStreamCreateWithFlags(&w.gstream[gi], cudaStreamNonBlocking));
+        TN_CUDA(cudaEventCreateWithFlags(&w.gev[gi], cudaEventDisableTiming));
+      }
+    }
+    // a group's Gram GEMM should cover about half of the 296 CTA slots by itself
+    const int npg = (np + ngroups - 1) / ngroups;
+    gksplit = std::max(1, std::min(std::min(16, jrows / 64), 148 / npg));
+    gkchunk = ((jrows + gksplit - 1) / gksplit + 7) / 8 * 8;
+    gksplit = (jrows + gkchunk - 1) / gkchunk;
+  }
   w.sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
     for (int st = 0; st < steps; ++st) {
       const int* tb = tab + (size_t)st * np * 2;
-      Idx2 cols{JB, (long long)w.ldz, colblk, tb, 2};
-      GemmDesc g{};
-      g.M = JP; g.N = JP; g.K = jrows;
-      g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
-      g.B = w.Z; g.bk = idx1(1); g.bn = cols; g.conjB = 0;
-      g.C = w.Gpart; g.cm = idx1(1); g.cn = idx1(JP);
-      g.alpha = make_double2(1, 0); g.beta = make_double2(0, 0);
-      g.batch = np; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
-      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)np * JP * JP;
-      zgemm_auto(g, s);
-      prof().mark(PH_GRAM, s);
-      jacobi_evd64_kernel<<<np, EVD_THREADS, evd_smem, s>>>(w.Gpart, ksplit, (long long)np * JP * JP, w.J, tol, w.offmax, inner_sweeps, nact);
-      TN_CUDA(cudaGetLastError());
-      count_launch(1);
-      prof().mark(PH_EVD, s);
-      GemmDesc a{};
-      a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;   // W rows + V rows (ldz may carry padding rows)
-      a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
-      a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
-      // out of place (Z2(:,pair) = Z(:,pair) J; the pairs of a step cover every column), so the GEMM is free to use the
-      // 128 x 32 tile / 2 CTAs per SM configuration instead of the in-place 128 x 64 one
-      a.C = w.Z2; a.cm = idx1(1); a.cn = cols;
-      a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
-      a.batch = np; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
-      a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
-      zgemm_auto(a, s);
+      // one group of pairs [p0, p1) of this step on stream gs: Gram -> EVD -> rotation
+      auto run_group = [&](int p0, int p1, int gsplit, int gchunk, cudaStream_t gs, bool marks) {
+        const int npg = p1 - p0;
+        Idx2 cols{JB, (long long)w.ldz, colblk, tb + 2 * p0, 2};
+        cplx* Gg = w.Gpart + (size_t)p0 * JP * JP;
+        cplx* Jg = w.J + (size_t)p0 * JP * JP;
+        GemmDesc g{};
+        g.M = JP; g.N = JP; g.K = jrows;
+        g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
+        g.B = w.Z; g.bk = idx1(1); g.bn = cols; g.conjB = 0;
+        g.C = Gg; g.cm = idx1(1); g.cn = idx1(JP);
+        g.alpha = make_double2(1, 0); g.beta = make_double2(0, 0);
+        g.batch = npg; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
+        // split-K partial Gram blocks are accumulated with red.global.add.f64 into one zeroed buffer (the single-CTA
+        // consumers would otherwise spend tens of microseconds summing ksplit x 64 KiB partials through one SM)
+        g.ksplit = gsplit; g.kchunk = gchunk; g.ssC = 0; g.atomic_c = gsplit > 1 ? 1 : 0;
+        if (g.atomic_c) TN_CUDA(cudaMemsetAsync(Gg, 0, (size_t)npg * JP * JP * sizeof(cplx), gs));
+        zgemm_auto(g, gs);
+        if (marks) prof().mark(PH_GRAM, gs);
+        jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, gs>>>(Gg, 1, 0, Jg, tol, w.offmax, inner_sweeps, nact);
+        TN_CUDA(cudaGetLastError());
+        count_launch(1);
+        if (marks) prof().mark(PH_EVD, gs);
+        GemmDesc a{};
+        a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;   // W rows + V rows (ldz may carry padding rows)
+        a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
+        a.B = Jg; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
+        // out of place (Z2(:,pair) = Z(:,pair) J; the pairs of a step cover every column), so the GEMM is free to use the
+        // 128 x 32 tile / 2 CTAs per SM configuration instead of the in-place 128 x 64 one
+        a.C = w.Z2; a.cm = idx1(1); a.cn = cols;
+        a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
+        a.batch = npg; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
+        a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
+        zgemm_auto(a, gs);
+      };
+      if (ngroups == 1) {
+        run_group(0, np, ksplit, kchunk, s, true);
+      } else {
+        // The pairs of a step are independent: groups run on their own streams, each group's Gram / rotation GEMM is wide
+        // enough to fill the GPU, so the groups proceed staggered and the latency-bound single-SM EVD kernels of one
+        // group overlap the GEMMs of the others.  All groups join before the next step (its pairs mix the groups).
+        TN_CUDA(cudaEventRecord(w.fork_ev, s));
+        for (int gi = 0; gi < ngroups; ++gi) {
+          const int p0 = np * gi / ngroups, p1 = np * (gi + 1) / ngroups;
+          TN_CUDA(cudaStreamWaitEvent(w.gstream[gi], w.fork_ev, 0));
+          run_group(p0, p1, gksplit, gkchunk, w.gstream[gi], false);
+          TN_CUDA(cudaEventRecord(w.gev[gi], w.gstream[gi]));
+        }
+        for (int gi = 0; gi < ngroups; ++gi) TN_CUDA(cudaStreamWaitEvent(s, w.gev[gi], 0));
+      }
       std::swap(w.Z, w.Z2); std::swap(w.Z_cap, w.Z2_cap);
       prof().mark(PH_ROT, s);
     }
@@ -600,9 +643,10 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
     cplx* P = Q + (long long)pk * JP * ldq;
     for (int it = 0; it < chol_passes; ++it) {
       GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
-      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = (long long)JP * JP;
+      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
+      if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)JP * JP * sizeof(cplx), s));
       zgemm_auto(g, s);
-      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, ksplit, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
+      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, 1, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
                                                   chol_passes == 3 ? shift_factor : 0.0);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
@@ -620,14 +664,11 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       int csplit = std::max(1, std::min(std::min(16, rows / 64), 148 / ((nt + 127) / 128)));
       int cchunk = ((rows + csplit - 1) / csplit + 7) / 8 * 8;
       csplit = (rows + cchunk - 1) / cchunk;
-      ensure(w.Cpart, w.Cpart_cap, (size_t)csplit * JP * nt, s);
-      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, w.Cpart, idx1(1), idx1(JP));
-      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = (long long)JP * nt;
-      zgemm_auto(c, s);
+      // split-K contributions go straight into the block row of R (zeroed by the memset above) with red.global.add.f64
       cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
-      int blocks; launch_1d((long long)JP * nt, blocks);
-      reduce_partials_kernel<<<blocks, 256, 0, s>>>(w.Cpart, csplit, (long long)JP * nt, JP, nt, Rrow, npad, 0);
-      count_launch(1);
+      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
+      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
+      zgemm_auto(c, s);
       // T <- T - P C
       zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
     }
@@ -778,6 +819,10 @@ void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
   if (w.Z2) cudaFree(w.Z2);
+  if (w.fork_ev) {
+    cudaEventDestroy(w.fork_ev);
+    for (int gi = 0; gi < SvdWork::MAX_GROUPS; ++gi) { cudaStreamDestroy(w.gstream[gi]); cudaEventDestroy(w.gev[gi]); }
+  }
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }

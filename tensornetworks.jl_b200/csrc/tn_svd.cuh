@@ -11,6 +11,8 @@ struct Trunc { double cutoff; long long maxdim; long long mindim; };
 struct SvdWork {
   cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld = rows + ncols
   cplx* Z2 = nullptr; size_t Z2_cap = 0;          // ping-pong partner of Z (rotation GEMM writes out of place)
+  static constexpr int MAX_GROUPS = 8;             // pair groups of a Jacobi step run on their own streams
+  cudaStream_t gstream[MAX_GROUPS] = {}; cudaEvent_t gev[MAX_GROUPS] = {}; cudaEvent_t fork_ev = nullptr;
   cplx* Gpart = nullptr; size_t G_cap = 0;        // split-K Gram partials
   cplx* J = nullptr; size_t J_cap = 0;            // per-pair 64x64 rotations
   double* sig = nullptr; int* perm = nullptr; size_t s_cap = 0;   // sorted singular values + permutation

@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * Cfg::BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * Cfg::BN;
   const int k_begin = split * d.kchunk;
   const int k_end = min(d.K, k_begin + d.kchunk);
-  gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, false);
+  gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, d.atomic_c != 0);
 }
 
 // Persistent stream-K variant (batch == 1, no split-K, beta == 0, dense C zeroed by the launcher).  The tile space is
@@ -457,7 +457,12 @@ void zgemm_auto(GemmDesc d, cudaStream_t stream) {
     launch<4, 2, 4, 4>(d, stream);
     return;
   }
-  if (d.M <= 64 && d.N <= 64)      launch<2, 4, 4, 2>(d, stream);   // 64 x 64   (Gram blocks, tiny bonds)
+  static int small_variant = -1;
+  if (small_variant < 0) { const char* e = getenv("TN_GEMM_SMALL"); small_variant = e ? atoi(e) : 0; }
+  if (d.M <= 64 && d.N <= 64) {                                      // 64 x 64   (Gram blocks, tiny bonds)
+    if (small_variant == 1) launch<2, 2, 4, 4>(d, stream);          // 4 warps with 32 x 32 warp tiles, 2 CTAs / SM
+    else launch<2, 4, 4, 2>(d, stream);                             // 8 warps with 32 x 16 warp tiles, 2 CTAs / SM
+  }
   else if (d.N <= 32)              launch<8, 1, 4, 4>(d, stream);   // 256 x 32  (skinny right operand)
   else if (d.M <= 64)              launch<2, 4, 4, 4>(d, stream);   // 64 x 128
   else {
