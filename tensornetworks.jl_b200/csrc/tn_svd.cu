@@ -527,9 +527,9 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   // (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
   const int inner_sweeps = (np == 1) ? 12 : 1;
   const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
-  // pair groups on separate streams (TN_SVD_GROUPS, default 4) once a step has enough pairs to split
+  // pair groups on separate streams (TN_SVD_GROUPS, default 1 = off: measured gain on B200 was < 3 %, the groups run in lockstep) once a step has enough pairs to split
   static int want_groups = -1;
-  if (want_groups < 0) { const char* e = getenv("TN_SVD_GROUPS"); want_groups = e ? std::max(1, std::min(SvdWork::MAX_GROUPS, atoi(e))) : 4; }
+  if (want_groups < 0) { const char* e = getenv("TN_SVD_GROUPS"); want_groups = e ? std::max(1, std::min(SvdWork::MAX_GROUPS, atoi(e))) : 1; }
   const int ngroups = (np >= 4 * want_groups) ? want_groups : 1;
   int gksplit = ksplit, gkchunk = kchunk;
   if (ngroups > 1) {

@@ -52,7 +52,8 @@ def main():
             out = sh.apply(th)
         e1.record(); torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dev_s = e0.elapsed_time(e1) * 1e-3       # CUDA events on the device (every stage ends with a device sync, so the
+        t = torch.tensor([dev_s], dtype=torch.float64, device="cuda")   # events bracket all streams' work); max over ranks below
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item()) / a.steps
