@@ -65,4 +65,47 @@ function dmrg_sweep!(psi::CuGMPS, Hs::CuProjMPS, direction::Bool; krylovdim=3, k
                 psi.h, Hs.h, direction, LanczosT(krylovdim, kryloviter, 1e-14), TruncT(cutoff, maxdim, mindim), e, D))
     e[], D[]
 end
+
+# ---- TEBD / QJMC side: gatelist.jl:191-227, gmps.jl:29-51, qjmc.jl:59-164 -------------------------------------------
+mutable struct CuGateList; h::Ptr{Cvoid}; ctx::Ctx; end
+function CuGateList(ctx::Ctx, dim::Int, gates::GateList)          # after trotterize(): rows of (site, gate tensor)
+    counts = Int32[length(r) for r in gates.sites]
+    sites = Int32[s for r in gates.sites for s in r]
+    tens = [ComplexF64.(g) for r in gates.gates for g in r]
+    nsites = Int32[ndims(g) ÷ 2 for g in tens]
+    ptrs = [pointer(g) for g in tens]
+    h = Ref{Ptr{Cvoid}}()
+    GC.@preserve tens check(ccall((:tn_gates_upload, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{ComplexF64}}, Ref{Ptr{Cvoid}}),
+        ctx.h, dim, length(counts), counts, sites, nsites, ptrs, h))
+    g = CuGateList(h[], ctx); finalizer(x -> ccall((:tn_gates_free, lib), Int32, (Ptr{Cvoid},), x.h), g); g
+end
+applygates!(psi::CuGMPS, gates::CuGateList; cutoff=0.0, maxdim=0, mindim=1) =
+    check(ccall((:tn_apply_gates, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, TruncT), psi.h, gates.h, TruncT(cutoff, maxdim, mindim)))
+function norm(psi::CuGMPS)
+    v = Ref{ComplexF64}(); check(ccall((:tn_mps_norm, lib), Int32, (Ptr{Cvoid}, Ref{ComplexF64}), psi.h, v)); v[]
+end
+normalize!(psi::CuGMPS) = check(ccall((:tn_mps_normalize, lib), Int32, (Ptr{Cvoid},), psi.h))
+movecenter!(psi::CuGMPS, idx::Int; cutoff=0.0, maxdim=0, mindim=1) =
+    check(ccall((:tn_mps_movecenter, lib), Int32, (Ptr{Cvoid}, Int32, TruncT), psi.h, idx, TruncT(cutoff, maxdim, mindim)))
+
+# One trajectory (qjmc_simulation's loop) on the device; `uniforms` = 3 per step from Julia's RNG, or nothing for the
+# library's counter-based generator keyed by (seed, trajectory, step).
+function qjmc_run!(psi::CuGMPS, gates::CuGateList, jumpsites::Vector{Int32}, jumpops::Array{ComplexF64,3}, coeffs::Vector{Float64},
+                   steps::Int, dt::Float64; cutoff=1e-12, maxdim=0, mindim=1, uniforms=nothing, seed=0, trajectory=0,
+                   obsop=nothing, save_every=1)
+    nsave = obsop === nothing ? 0 : steps ÷ save_every
+    obs = zeros(ComplexF64, psi.N, max(nsave, 1)); jumps = zeros(Int32, steps + 1); times = zeros(Float64, steps + 1); nj = Ref{Int32}()
+    check(ccall((:tn_qjmc_run, lib), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{ComplexF64}, Ptr{Float64}, Int32, Float64, TruncT, Ptr{Float64}, UInt64, UInt64,
+         Ptr{ComplexF64}, Int32, Ptr{ComplexF64}, Ptr{Int32}, Ptr{Float64}, Int32, Ref{Int32}),
+        psi.h, gates.h, length(jumpsites), jumpsites, jumpops, coeffs, steps, dt, TruncT(cutoff, maxdim, mindim),
+        uniforms === nothing ? C_NULL : pointer(uniforms), seed, trajectory, obsop === nothing ? C_NULL : pointer(obsop), save_every,
+        obs, jumps, times, steps + 1, nj))
+    jumps[1:nj[]], times[1:nj[]], obs[:, 1:nsave]
+end
+# Many trajectories from one initial state (the loop a user writes around qjmc_simulation): tn_qjmc_ensemble hands them out to
+# `workers` host threads / CUDA streams inside the library; trajectory ids key the random numbers, so results do not depend on
+# the worker count or on which GPU ran them (shard ids over processes / GPUs as `ids = rank+1:world:ntraj`).
+# See include/tn_c_api.h for the argument list; the call mirrors qjmc_run! with host tensors instead of device handles.
 end # module
