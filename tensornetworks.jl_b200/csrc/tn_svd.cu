@@ -162,11 +162,10 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
           }
         }
       }
-      {
-        // J columns: 64 rows x 32 pairs = 2048 items, two per thread
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          int item = tid + it * EVD_THREADS;
+      else {
+        // J columns: 64 rows x 32 pairs = 2048 items, handled by the 496 threads that have no G block (about four
+        // items each, the same FP64 work as one G block: the two halves of the CTA finish the step together)
+        for (int item = tid - NBLK; item < JP * JB; item += EVD_THREADS - NBLK) {
           int k = item >> 6, row = item & 63;
           double cs = r_cs[k]; cplx s = r_s[k];
           if (s.x == 0.0 && s.y == 0.0) continue;
