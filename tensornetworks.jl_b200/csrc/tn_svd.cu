@@ -53,7 +53,8 @@ constexpr int NBLK = JB * (JB + 1) / 2;   // 2x2-block pairs (a <= b) of the 32 
 // (G' = R_a^H G_ab R_b) and the column rotation to two (row, pair) items of J: two barriers per step.
 constexpr int EVD_THREADS = 1024;
 __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
-                                                                       cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner, int nact) {
+                                                                       cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner, int nact,
+                                                                       int* __restrict__ skip_out) {
   // nact (even, <= 64): only the leading nact columns of the pair can be non-zero (a single zero-padded pair); the
   // round-robin then runs over nact columns (nact-1 steps) instead of 64
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
   mx = sqrt(mx);
   if (tid == 0) atomicMax(offmax, (unsigned long long)__double_as_longlong(mx));
   cplx* jo = Jout + (long long)blockIdx.x * JP * JP;
+  if (tid == 0 && skip_out) skip_out[blockIdx.x] = (mx <= tol) ? 1 : 0;   // the rotation GEMM skips converged pairs
   if (mx <= tol) {   // already orthogonal: identity rotation
     for (int e = tid; e < JP * JP; e += EVD_THREADS) jo[e] = make_double2((e % JP) == (e / JP) ? 1.0 : 0.0, 0.0);
     return;
@@ -513,7 +515,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   ksplit = (jrows + kchunk - 1) / kchunk;
   ensure(w.Gpart, w.G_cap, (size_t)std::max(ksplit, 32) * np * JP * JP, s);
   ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
-  ensure(w.Z2, w.Z2_cap, (size_t)w.ldz * w.ncols_pad, s);   // ping-pong partner of Z for the rotation GEMM
+  ensure(w.skip, w.skip_cap, (size_t)np, s);                // per-pair "already converged" flags
   const int* tab = pair_table(w, nb, s);
   static bool evd_cfg = false;
   const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
@@ -569,7 +571,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         if (g.atomic_c) TN_CUDA(cudaMemsetAsync(Gg, 0, (size_t)npg * JP * JP * sizeof(cplx), gs));
         zgemm_auto(g, gs);
         if (marks) prof().mark(PH_GRAM, gs);
-        jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, gs>>>(Gg, 1, 0, Jg, tol, w.offmax, inner_sweeps, nact);
+        jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, gs>>>(Gg, 1, 0, Jg, tol, w.offmax, inner_sweeps, nact, w.skip + p0);
         TN_CUDA(cudaGetLastError());
         count_launch(1);
         if (marks) prof().mark(PH_EVD, gs);
@@ -577,12 +579,13 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;   // W rows + V rows (ldz may carry padding rows)
         a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
         a.B = Jg; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
-        // out of place (Z2(:,pair) = Z(:,pair) J; the pairs of a step cover every column), so the GEMM is free to use the
-        // 128 x 32 tile / 2 CTAs per SM configuration instead of the in-place 128 x 64 one
-        a.C = w.Z2; a.cm = idx1(1); a.cn = cols;
+        // in place (each CTA owns 128 rows x all 64 columns of its pair); pairs whose Gram block was already diagonal
+        // (EVD wrote skip = 1, J = identity) are skipped, which makes the late / verification sweeps cheap
+        a.C = w.Z; a.cm = idx1(1); a.cn = cols;
         a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
         a.batch = npg; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
         a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
+        a.skip = w.skip + p0;
         zgemm_auto(a, gs);
       };
       if (ngroups == 1) {
@@ -600,7 +603,6 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         }
         for (int gi = 0; gi < ngroups; ++gi) TN_CUDA(cudaStreamWaitEvent(s, w.gev[gi], 0));
       }
-      std::swap(w.Z, w.Z2); std::swap(w.Z_cap, w.Z2_cap);
       prof().mark(PH_ROT, s);
     }
     prof().flush(s);
@@ -817,7 +819,7 @@ void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
 }
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
-  if (w.Z2) cudaFree(w.Z2);
+  if (w.skip) cudaFree(w.skip);
   if (w.fork_ev) {
     cudaEventDestroy(w.fork_ev);
     for (int gi = 0; gi < SvdWork::MAX_GROUPS; ++gi) { cudaStreamDestroy(w.gstream[gi]); cudaEventDestroy(w.gev[gi]); }

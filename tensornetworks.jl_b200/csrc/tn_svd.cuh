@@ -9,8 +9,8 @@ struct Trunc { double cutoff; long long maxdim; long long mindim; };
 
 // Workspace + state of one factorisation (owned by a Ctx; reused across calls).
 struct SvdWork {
-  cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld = rows + ncols
-  cplx* Z2 = nullptr; size_t Z2_cap = 0;          // ping-pong partner of Z (rotation GEMM writes out of place)
+  cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld >= rows + ncols
+  int* skip = nullptr; size_t skip_cap = 0;        // per-pair flags: Gram block already diagonal, rotation skipped
   static constexpr int MAX_GROUPS = 8;             // pair groups of a Jacobi step run on their own streams
   cudaStream_t gstream[MAX_GROUPS] = {}; cudaEvent_t gev[MAX_GROUPS] = {}; cudaEvent_t fork_ev = nullptr;
   cplx* Gpart = nullptr; size_t G_cap = 0;        // split-K Gram partials

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   cplx* Bs = As + Cfg::STAGES * Cfg::A_STAGE;
   const int z = blockIdx.z;
   const int batch = z / d.ksplit, split = z - batch * d.ksplit;
+  if (d.skip != nullptr && d.skip[batch] != 0) return;   // e.g. identity rotation of an already converged Jacobi pair
   // raster: consecutive CTAs walk m (default) or n (swap_raster) so that the LARGER operand is streamed from DRAM once
   const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * Cfg::BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * Cfg::BN;
   const int k_begin = split * d.kchunk;
