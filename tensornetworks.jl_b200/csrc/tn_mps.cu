@@ -411,7 +411,14 @@ void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host) 
   const long long n_in = (long long)h.cb * h.d2 * h.cb2, n_out = (long long)h.ca * h.d2 * h.ca2;
   cplx* din = c->scratch[13].get((size_t)n_in, s);
   cplx* dout = c->scratch[14].get((size_t)n_out, s);
-  const int nchunk = (n_in >= (1 << 20) && h.cb2 >= 64 && h.ca2 >= 64) ? 4 : 1;
+  // slices of Theta's / the result's right bond: enough of them that the first upload and the last download (the only
+  // copies not hidden behind a contraction stage) are short, but each slice still a few hundred columns wide
+  // (TN_MATVEC_CHUNKS overrides)
+  static int want_chunks = -1;
+  if (want_chunks < 0) { const char* e = getenv("TN_MATVEC_CHUNKS"); want_chunks = e ? std::max(1, std::min((int)Ctx::MAX_CHUNKS, atoi(e))) : 0; }
+  int nchunk = 1;
+  if (n_in >= (1 << 20) && h.cb2 >= 64 && h.ca2 >= 64) nchunk = want_chunks ? want_chunks : std::max(4, std::min(8, std::min(h.cb2, h.ca2) / 128));
+  nchunk = std::min(nchunk, std::min(h.cb2, h.ca2));
   if (nchunk == 1) {
     TN_CUDA(cudaMemcpyAsync(din, theta_host, (size_t)n_in * sizeof(cplx), cudaMemcpyHostToDevice, s));
     env_product_dev(e, din, site, dout, nullptr);
@@ -424,8 +431,8 @@ void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host) 
     for (auto& ev : c->copy_ev) TN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
   heff_prepare(e, site);
-  TN_CUDA(cudaEventRecord(c->copy_ev[8], s));                       // scratch (re)allocation is ordered on the main stream
-  TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[8], 0));
+  TN_CUDA(cudaEventRecord(c->copy_ev[2 * Ctx::MAX_CHUNKS], s));     // scratch (re)allocation is ordered on the main stream
+  TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[2 * Ctx::MAX_CHUNKS], 0));
   for (int k = 0; k < nchunk; ++k) {
     int b0 = (int)((long long)h.cb2 * k / nchunk), b1 = (int)((long long)h.cb2 * (k + 1) / nchunk);
     size_t off = (size_t)h.cb * h.d2 * b0, cnt = (size_t)h.cb * h.d2 * (b1 - b0);
@@ -440,8 +447,8 @@ void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host) 
   for (int k = 0; k < nchunk; ++k) {
     int a0 = (int)((long long)h.ca2 * k / nchunk), a1 = (int)((long long)h.ca2 * (k + 1) / nchunk);
     heff_stage3(e, site, a0, a1, dout);
-    TN_CUDA(cudaEventRecord(c->copy_ev[4 + k], s));
-    TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[4 + k], 0));
+    TN_CUDA(cudaEventRecord(c->copy_ev[Ctx::MAX_CHUNKS + k], s));
+    TN_CUDA(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[Ctx::MAX_CHUNKS + k], 0));
     size_t off = (size_t)h.ca * h.d2 * a0, cnt = (size_t)h.ca * h.d2 * (a1 - a0);
     TN_CUDA(cudaMemcpyAsync(out_host + off, dout + off, cnt * sizeof(cplx), cudaMemcpyDeviceToHost, c->copy_stream));
   }

@@ -31,7 +31,8 @@ struct Ctx {
   cplx* partials = nullptr;  // dot-product partial sums
   long long matvecs = 0, svds = 0;
   cudaStream_t copy_stream = nullptr;   // H2D / D2H pipeline of the host-buffer matvec
-  cudaEvent_t copy_ev[9] = {};
+  static constexpr int MAX_CHUNKS = 16;  // slices of the pipelined host-buffer matvec
+  cudaEvent_t copy_ev[2 * MAX_CHUNKS + 1] = {};
   void alloc(Tensor& t, const std::vector<long long>& dims);
   void free(Tensor& t);
   void swap(Tensor& a, Tensor& b) { std::swap(a, b); }
