@@ -150,6 +150,14 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
                     uint64_t seed, uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out,
                     int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out);
 
+/* inner(st, psi, oplist, phi): mps.jl:87-134.  out[t] = coeffs[t] * <psi| O_t |phi> for nterms operator strings
+ * O_t = product of nops[t] single-site operators; op_sites (1-based, strictly ascending inside a term) and ops_host
+ * (d x d each, column-major) are flattened over the terms in order.  Evaluated like the reference: overlap blocks
+ * ProjMPS(psi, phi), the left block carried through the sites of the string (identity on the gaps), closed with the
+ * right block -- no canonical-form shortcut.  tebd.jl:51,90 (energy) and the observers call this. */
+int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites,
+                        const tn_cplx* ops_host, const tn_cplx* coeffs, tn_cplx* out);
+
 /* Ensemble of independent QJMC trajectories (the caller's loop around qjmc_simulation, examples/qjmc.jl:52; SURVEY 8(e)
  * trajectory-level parallelism).  All trajectories start from the same host MPS (dims: N x 3, site_ptrs) and the same gate
  * list (arguments as tn_gates_upload).  They are handed out dynamically to `nworkers` host threads, each owning a CUDA

@@ -346,6 +346,15 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
   });
 }
 
+int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites, const tn_cplx* ops_host,
+                        const tn_cplx* coeffs, tn_cplx* out) {
+  return guard([&] {
+    TN_CHECK(psi && phi && (nterms == 0 || (nops && op_sites && ops_host && coeffs && out)), "inner: null pointer");
+    TN_CHECK(psi->m->ctx == phi->m->ctx, "inner: both MPSs must live in the same context");
+    inner_oplist(psi->m, phi->m, nterms, nops, op_sites, C(ops_host), C(coeffs), C(out));
+  });
+}
+
 int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const uint64_t* traj_ids,
                          int32_t d, int32_t N, const int64_t* dims, const tn_cplx* const* site_ptrs, int32_t center,
                          int32_t nrows, const int32_t* counts, const int32_t* gate_sites, const int32_t* gate_nsites,

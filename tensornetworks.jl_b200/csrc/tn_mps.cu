@@ -748,4 +748,77 @@ void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cp
   env_free(e);
 }
 
+// ================================================================================================
+// inner(st, psi, oplist, phi) (mps.jl:87-134): <psi| O_t |phi> for operator strings O_t = prod_k O_{t,k}(site_{t,k}),
+// evaluated exactly as the reference does -- overlap blocks ProjMPS(psi, phi), the left block carried through the sites
+// of the string, closed with the right block.  The energy measurement of tebd.jl:51,90 and the observers go through this.
+// ================================================================================================
+void inner_oplist(Mps* bra, Mps* ket, int nterms, const int* nops, const int* op_sites, const cplx* ops_host, const cplx* coeffs,
+                  cplx* out_host) {
+  Ctx* c = ket->ctx; cudaStream_t s = c->stream;
+  TN_CHECK(bra->rank == 1 && ket->rank == 1, "inner: rank-1 MPS only");
+  TN_CHECK(bra->N == ket->N && bra->d == ket->d, "inner: the MPSs must share length and physical dimension");
+  TN_CHECK(nterms >= 0 && nterms <= (1 << 24), "inner: bad term count");
+  if (nterms == 0) return;
+  const int d = ket->d, N = ket->N;
+  std::vector<long long> off(nterms + 1, 0);
+  for (int t = 0; t < nterms; ++t) {
+    TN_CHECK(nops[t] >= 1, "inner: every term needs at least one operator");
+    off[t + 1] = off[t] + nops[t];
+    for (long long k = off[t]; k < off[t + 1]; ++k) {
+      TN_CHECK(op_sites[k] >= 1 && op_sites[k] <= N, "inner: operator site out of range");
+      TN_CHECK(k == off[t] || op_sites[k] > op_sites[k - 1], "inner: operator sites of a term must be strictly ascending");
+    }
+  }
+  const long long nop = off[nterms];
+  cplx* ops = c->scratch[15].get((size_t)nop * d * d + 64, s);
+  TN_CUDA(cudaMemcpyAsync(ops, ops_host, (size_t)nop * d * d * sizeof(cplx), cudaMemcpyHostToDevice, s));
+  cplx* dall; TN_CUDA(cudaMallocAsync((void**)&dall, sizeof(cplx) * nterms, s));
+  Env* e = env_create(c, bra, nullptr, ket, ONE, 1);
+  for (int site = 1; site <= N; ++site) {
+    bool moved = false;
+    for (int t = 0; t < nterms; ++t) {
+      if (op_sites[off[t]] != site) continue;
+      if (!moved) { env_movecenter(e, site); moved = true; }
+      const int last = op_sites[off[t + 1] - 1];
+      const Tensor& L = env_block(e, site - 1);
+      const Tensor& R = env_block(e, last + 1);
+      const cplx* cur = L.p;                     // (chi_bra, chi_ket) overlap block left of the string
+      long long k = off[t];
+      int flip = 0;
+      for (int q = site; q <= last; ++q) {
+        const Tensor& A1 = bra->sites[q - 1];
+        const Tensor& A2 = ket->sites[q - 1];
+        const int ca = (int)A1.dims[0], ca2 = (int)A1.dims[2], cb = (int)A2.dims[0], cb2 = (int)A2.dims[2];
+        const cplx* B = A2.p;
+        if (k < off[t + 1] && op_sites[k] == q) {          // B = O A2 on the physical index (mps.jl:116-119)
+          cplx* OA = c->scratch[1].get((size_t)A2.size(), s);
+          op_apply1(A2.p, OA, ops + (size_t)k * d * d, cb, d, 1, cb2, s);
+          B = OA; ++k;
+        }
+        // X1[a,(s,b')] = cur[a,b] B[b,(s,b')] ;  new[a',b'] = sum_{(a,s)} conj(A1[(a,s),a']) X1[(a,s),b']
+        cplx* X1 = c->scratch[2].get((size_t)ca * d * cb2, s);
+        zgemm_auto(mk(ca, d * cb2, cb, cur, idx1(1), idx1(ca), 0, B, idx1(1), idx1(cb), 0, X1, idx1(1), idx1(ca)), s);
+        cplx* nxt = c->scratch[4 + flip].get((size_t)ca2 * cb2, s);
+        zgemm_auto(mk(ca2, cb2, ca * d, A1.p, idx1((long long)ca * d), idx1(1), 1, X1, idx1(1), idx1((long long)ca * d), 0, nxt, idx1(1), idx1(ca2)), s);
+        cur = nxt; flip ^= 1;
+      }
+      TN_CHECK(R.size() == (long long)bra->sites[last - 1].dims[2] * ket->sites[last - 1].dims[2], "inner: block size mismatch");
+      // un-conjugated sum cur .* R: zdots conjugates its first argument, so conjugate a copy of cur first
+      cplx* tmp = c->scratch[1].get((size_t)R.size(), s);
+      TN_CUDA(cudaMemcpyAsync(tmp, cur, (size_t)R.size() * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+      zconj_inplace(R.size(), tmp, s);
+      const cplx* xs[1] = {tmp};
+      zdots(R.size(), 1, xs, R.p, dall + t, c->partials, s);
+    }
+  }
+  std::vector<cplx> raw(nterms);
+  TN_CUDA(cudaMemcpyAsync(raw.data(), dall, sizeof(cplx) * nterms, cudaMemcpyDeviceToHost, s));
+  c->sync();
+  TN_CUDA(cudaFreeAsync(dall, s));
+  env_free(e);
+  for (int t = 0; t < nterms; ++t)
+    out_host[t] = cplx{coeffs[t].x * raw[t].x - coeffs[t].y * raw[t].y, coeffs[t].x * raw[t].y + coeffs[t].y * raw[t].x};
+}
+
 }  // namespace tn

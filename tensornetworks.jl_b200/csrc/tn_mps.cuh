@@ -90,5 +90,7 @@ Gates* gates_create(Ctx* c, int d, int nrows, const int* counts, const int* site
 void gates_free(Gates* g);
 void apply_gates(Mps* psi, Gates* g, Trunc tr);
 void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cplx* out_host);
+void inner_oplist(Mps* bra, Mps* ket, int nterms, const int* nops, const int* op_sites, const cplx* ops_host, const cplx* coeffs,
+                  cplx* out_host);
 
 }  // namespace tn

@@ -337,11 +337,13 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 }
 
 // Persistent stream-K variant (batch == 1, no split-K, beta == 0, dense C zeroed by the launcher).  The tile space is
-// walked in raster order.  The first dp_tiles tiles (whole waves) are processed one tile per CTA per wave; the remaining
-// sk_tiles tiles (the last full wave + the partial wave) are cut into sk_units k-tile units that are divided evenly
-// over the first sk_ctas CTAs, so every SM finishes at the same time instead of idling through a partial last wave.
-// A tile whose k range is shared by several CTAs is accumulated with red.global.add.f64.
-struct SkPlan { int tiles_fast, dp_tiles, sk_tiles, kt, sk_ctas; long long sk_units; };
+// walked in raster order.  Whole waves of tiles (dp_tiles) are processed one tile per CTA per wave.  The rem_tiles tiles
+// that would form a partial last wave (or a sub-wave problem) are each cut into nseg equal k-segments, chosen so that
+// the rem_tiles * nseg work items fill the CTA slots in as few rounds as possible; items are dealt so that the CTAs of a
+// round work on neighbouring tiles over the SAME k range (they share operand rows / columns through L2, exactly like
+// the tiles of a full wave -- a free-running unit split loses that reuse and cost 4x the DRAM reads).  Tiles with
+// nseg > 1 are accumulated with red.global.add.f64.
+struct SkPlan { int tiles_fast, dp_tiles, rem_tiles, nseg, kt; };
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -354,22 +356,18 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
     n_blk = (d.swap_raster ? fast : slow) * Cfg::BN;
   };
   const int c = blockIdx.x;
-  if (c < pl.sk_ctas) {
-    long long u = pl.sk_units * c / pl.sk_ctas;
-    const long long u_end = pl.sk_units * (c + 1) / pl.sk_ctas;
-    while (u < u_end) {
-      int tile = (int)(u / pl.kt), k0 = (int)(u - (long long)tile * pl.kt);
-      int k1 = (int)min((long long)pl.kt, k0 + (u_end - u));
-      int m_blk, n_blk;
-      origin(pl.dp_tiles + tile, m_blk, n_blk);
-      gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), !(k0 == 0 && k1 == pl.kt));
-      u += k1 - k0;
-    }
-  }
   for (int tile = c; tile < pl.dp_tiles; tile += gridDim.x) {
     int m_blk, n_blk;
     origin(tile, m_blk, n_blk);
     gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, 0, d.K, false);
+  }
+  const int items = pl.rem_tiles * pl.nseg;
+  for (int item = c; item < items; item += gridDim.x) {
+    const int seg = item / pl.rem_tiles, tile = pl.dp_tiles + (item - seg * pl.rem_tiles);
+    const int k0 = (int)((long long)pl.kt * seg / pl.nseg), k1 = (int)((long long)pl.kt * (seg + 1) / pl.nseg);
+    int m_blk, n_blk;
+    origin(tile, m_blk, n_blk);
+    gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), pl.nseg > 1);
   }
 }
 
@@ -406,20 +404,27 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
     const double eff = (double)T / (double)(waves * slots);
     if (eff < 0.94 && KT >= 16 && T < (1ll << 30)) {
       SkPlan pl;
-      const long long full = T / slots;
       pl.tiles_fast = dd.swap_raster ? (int)tn_ : (int)tm;
-      pl.dp_tiles = full >= 1 ? (int)((full - 1) * slots) : 0;
-      pl.sk_tiles = (int)(T - pl.dp_tiles);
+      pl.dp_tiles = (int)((T / slots) * slots);
+      pl.rem_tiles = (int)(T - pl.dp_tiles);
       pl.kt = KT;
-      pl.sk_units = (long long)pl.sk_tiles * KT;
-      pl.sk_ctas = (int)std::max<long long>(1, std::min<long long>(slots, pl.sk_units / 16));
-      const int grid = pl.dp_tiles > 0 ? slots : pl.sk_ctas;
-      // partial tiles are accumulated atomically: zero the (dense, possibly pitched) output first
-      TN_CUDA(cudaMemset2DAsync(d.C, (size_t)d.cn.s0 * sizeof(cplx), 0, (size_t)d.M * sizeof(cplx), (size_t)d.N, stream));
-      kern_sk<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd, pl);
-      TN_CUDA(cudaGetLastError());
-      count_launch(1);
-      return;
+      // segments per remainder tile: minimise the duration ceil(rem * nseg / slots) / nseg of the last phase
+      // (in units of one full tile), keeping at least 8 k-tiles per segment
+      pl.nseg = 1;
+      double best = 1e30;
+      for (int ns = 1; ns <= 16 && KT / ns >= 8; ++ns) {
+        const double dur = (double)(((long long)pl.rem_tiles * ns + slots - 1) / slots) / ns;
+        if (dur < best - 1e-9) { best = dur; pl.nseg = ns; }
+      }
+      if (pl.nseg > 1) {     // otherwise no split beats the plain partial wave: fall through to the ordinary launch
+        const int grid = (int)std::min<long long>(slots, std::max<long long>(pl.dp_tiles, (long long)pl.rem_tiles * pl.nseg));
+        // partial tiles are accumulated atomically: zero the (dense, possibly pitched) output first
+        TN_CUDA(cudaMemset2DAsync(d.C, (size_t)d.cn.s0 * sizeof(cplx), 0, (size_t)d.M * sizeof(cplx), (size_t)d.N, stream));
+        kern_sk<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd, pl);
+        TN_CUDA(cudaGetLastError());
+        count_launch(1);
+        return;
+      }
     }
   }
   dim3 grid(dd.swap_raster ? tn_ : tm, dd.swap_raster ? tm : tn_, d.batch * d.ksplit);

@@ -7,5 +7,5 @@ are NumPy complex128 in Julia's column-major order.  Tensors live in HBM between
 calls; only scalars, observables and explicitly downloaded tensors cross PCIe."""
 from ._lib import TNError, load, LIB_PATH  # noqa: F401
 from .api import (Context, GMPS, ProjMPS, GateList, svd, contract_strided, dmrg, tebd, applygates,  # noqa: F401
-                  qjmc_simulation, qjmc_ensemble, Trunc)
+                  qjmc_simulation, qjmc_ensemble, inner, Trunc)
 from . import models  # noqa: F401

@@ -473,3 +473,29 @@ def qjmc_ensemble(tensors, center, gate_sites, gate_tensors, jump_sites, jump_op
                                None if oo is None else _ptr(oo), int(save_every), _ptr(obs), njumps.ctypes.data_as(i32p),
                                jumps.ctypes.data_as(i32p), times.ctypes.data_as(f64p), cap))
     return njumps, jumps, times, obs[:, :nsaves]
+
+
+def inner(psi, terms, phi=None):
+    """inner(st, psi, oplist, phi): mps.jl:87-134.  ``terms`` is a list of (ops, sites, coeff) with ``ops`` a list of
+    d x d matrices and ``sites`` the matching 1-based sites (any order; sorted here like OpList.add does, oplist.jl:35-40).
+    Returns the complex array coeff_t * <psi| O_t |phi> (phi defaults to psi)."""
+    phi = psi if phi is None else phi
+    nops, sites, mats, coeffs = [], [], [], []
+    for ops, st, co in terms:
+        order = np.argsort(np.asarray(st))
+        nops.append(len(order))
+        for j in order:
+            sites.append(int(st[j]))
+            mats.append(np.ascontiguousarray(_f(ops[j]).T))      # d x d block, column-major
+        coeffs.append(complex(co))
+    n = len(nops)
+    out = np.zeros(n, dtype=np.complex128)
+    if n == 0:
+        return out
+    nn = np.asarray(nops, dtype=np.int32)
+    ss = np.asarray(sites, dtype=np.int32)
+    mm = np.ascontiguousarray(np.stack(mats))
+    cc = np.asarray(coeffs, dtype=np.complex128)
+    i32p = C.POINTER(C.c_int32)
+    check(psi.lib.tn_inner_oplist(psi.h, phi.h, n, nn.ctypes.data_as(i32p), ss.ctypes.data_as(i32p), _ptr(mm), _ptr(cc), _ptr(out)))
+    return out

@@ -185,3 +185,32 @@ def test_qjmc_ensemble_equals_single_trajectories():
         assert list(jumps[k, :nj[k]]) == j1 and np.allclose(times[k, :nj[k]], t1)
         assert np.max(np.abs(obs[k] - o1)) < 1e-9
     assert nj.sum() > 0
+
+
+def test_inner_oplist_matches_oracle():
+    """tn_inner_oplist (mps.jl:87-134): operator strings with gaps, one- to three-site terms, bra != ket, complex
+    coefficients; and the TEBD energy measurement inner(st, psi, H, psi) of tebd.jl:51."""
+    import tnb200
+    sh = oracle.spinhalf()
+    rng = np.random.default_rng(21)
+    N = 9
+    psi = random_complex_mps(rng, N, 2, 12, center=4)
+    phi = random_complex_mps(rng, N, 2, 7, center=7)
+    ol = oracle.OpList(N)
+    ol.add("z", 1, 0.5)
+    ol.add(["x", "x"], [3, 4], 1.2)
+    ol.add(["s+", "z", "s-"], [2, 5, 9], 0.3 - 0.4j)       # gaps between the operators
+    ol.add(["y", "n"], [8, 9], -2.0)
+    ol.add(["z", "z"], [6, 7])
+    ol.add("x", N, 1.5j)
+    g, h = tnb200.GMPS.from_host(psi), tnb200.GMPS.from_host(phi)
+    terms = [([sh.op(o) for o in ops], sites, co) for ops, sites, co in zip(ol.ops, ol.sites, ol.coeffs)]
+    want = oracle.inner(sh, psi, ol, phi)
+    got = tnb200.inner(g, terms, h)
+    assert np.max(np.abs(got - want)) < 1e-12 * max(1.0, np.max(np.abs(want)))
+    H = tfim(N, 1.0, 0.3, 1.1)
+    hterms = [([sh.op(o) for o in ops], sites, co) for ops, sites, co in zip(H.ops, H.sites, H.coeffs)]
+    e_want = np.sum(oracle.inner(sh, psi, H, psi))
+    e_got = np.sum(tnb200.inner(g, hterms))
+    assert abs(e_got - e_want) < 1e-11 * abs(e_want)
+    assert abs(e_got.imag) < 1e-11 * abs(e_want)
