@@ -407,18 +407,6 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   }
 }
 
-// out(rows x cols, leading dim ldo) (+)= sum_s part[s] ; part[s] is rows x cols contiguous
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const cplx* __restrict__ part, int nsplit, long long split_stride, int rows, int cols,
-                                                               cplx* __restrict__ out, long long ldo, int accumulate) {
-  long long total = (long long)rows * cols;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    double xr = 0, xi = 0;
-    for (int s = 0; s < nsplit; ++s) { cplx v = part[s * split_stride + e]; xr += v.x; xi += v.y; }
-    cplx* o = out + (e % rows) + (e / rows) * ldo;
-    if (accumulate) { xr += o->x; xi += o->y; }
-    *o = make_double2(xr, xi);
-  }
-}
 // dst(c, r) = conj(src(r, c)): dst is cols x rows (ldd), src rows x cols (lds); optional zero fill beyond (rows_valid, cols_valid)
 __global__ void __launch_bounds__(256) conj_transpose_kernel(const cplx* __restrict__ src, long long lds, int rows, int cols,
                                                               cplx* __restrict__ dst, long long ldd) {
@@ -534,31 +522,14 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   // (n <= 64) has no outer parallelism to trade, so it is diagonalised fully.
   const int inner_sweeps = (np == 1) ? 12 : 1;
   const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
-  // pair groups on separate streams (TN_SVD_GROUPS, default 1 = off: measured gain on B200 was < 3 %, the groups run in lockstep) once a step has enough pairs to split
-  static int want_groups = -1;
-  if (want_groups < 0) { const char* e = getenv("TN_SVD_GROUPS"); want_groups = e ? std::max(1, std::min(SvdWork::MAX_GROUPS, atoi(e))) : 1; }
-  const int ngroups = (np >= 4 * want_groups) ? want_groups : 1;
-  int gksplit = ksplit, gkchunk = kchunk;
-  if (ngroups > 1) {
-    if (!w.fork_ev) {
-      TN_CUDA(cudaEventCreateWithFlags(&w.fork_ev, cudaEventDisableTiming));
-      for (int gi = 0; gi < SvdWork::MAX_GROUPS; ++gi) {
-        TN_CUDA(cudaStreamCreateWithFlags(&w.gstream[gi], cudaStreamNonBlocking));
-        TN_CUDA(cudaEventCreateWithFlags(&w.gev[gi], cudaEventDisableTiming));
-      }
-    }
-    // a group's Gram GEMM should cover about half of the 296 CTA slots by itself
-    const int npg = (np + ngroups - 1) / ngroups;
-    gksplit = std::max(1, std::min(std::min(16, jrows / 64), 148 / npg));
-    gkchunk = ((jrows + gksplit - 1) / gksplit + 7) / 8 * 8;
-    gksplit = (jrows + gkchunk - 1) / gkchunk;
-  }
   w.sweeps = 0;
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
     for (int st = 0; st < steps; ++st) {
       const int* tb = tab + (size_t)st * np * 2;
-      // one group of pairs [p0, p1) of this step on stream gs: Gram -> EVD -> rotation
+      // the pairs [p0, p1) of this step on stream gs: Gram -> EVD -> rotation.  (Splitting a step into pair groups on
+      // separate streams, so that the EVD of one group overlaps the GEMMs of another, was measured: < 3 % -- the groups run
+      // in lockstep -- and removed.)
       auto run_group = [&](int p0, int p1, int gsplit, int gchunk, cudaStream_t gs, bool marks) {
         const int npg = p1 - p0;
         Idx2 cols{JB, (long long)w.ldz, colblk, tb + 2 * p0, 2};
@@ -594,21 +565,7 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         a.skip = w.skip + p0;
         zgemm_auto(a, gs);
       };
-      if (ngroups == 1) {
-        run_group(0, np, ksplit, kchunk, s, true);
-      } else {
-        // The pairs of a step are independent: groups run on their own streams, each group's Gram / rotation GEMM is wide
-        // enough to fill the GPU, so the groups proceed staggered and the latency-bound single-SM EVD kernels of one
-        // group overlap the GEMMs of the others.  All groups join before the next step (its pairs mix the groups).
-        TN_CUDA(cudaEventRecord(w.fork_ev, s));
-        for (int gi = 0; gi < ngroups; ++gi) {
-          const int p0 = np * gi / ngroups, p1 = np * (gi + 1) / ngroups;
-          TN_CUDA(cudaStreamWaitEvent(w.gstream[gi], w.fork_ev, 0));
-          run_group(p0, p1, gksplit, gkchunk, w.gstream[gi], false);
-          TN_CUDA(cudaEventRecord(w.gev[gi], w.gstream[gi]));
-        }
-        for (int gi = 0; gi < ngroups; ++gi) TN_CUDA(cudaStreamWaitEvent(s, w.gev[gi], 0));
-      }
+      run_group(0, np, ksplit, kchunk, s, true);
       prof().mark(PH_ROT, s);
     }
     prof().flush(s);
@@ -826,15 +783,11 @@ void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
   if (w.skip) cudaFree(w.skip);
-  if (w.fork_ev) {
-    cudaEventDestroy(w.fork_ev);
-    for (int gi = 0; gi < SvdWork::MAX_GROUPS; ++gi) { cudaStreamDestroy(w.gstream[gi]); cudaEventDestroy(w.gev[gi]); }
-  }
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
   if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); }
-  for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Cpart, w.Tg}) if (p) cudaFree(p);
+  for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
   w = SvdWork{};
 }

@@ -11,8 +11,6 @@ struct Trunc { double cutoff; long long maxdim; long long mindim; };
 struct SvdWork {
   cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld >= rows + ncols
   int* skip = nullptr; size_t skip_cap = 0;        // per-pair flags: Gram block already diagonal, rotation skipped
-  static constexpr int MAX_GROUPS = 8;             // pair groups of a Jacobi step run on their own streams
-  cudaStream_t gstream[MAX_GROUPS] = {}; cudaEvent_t gev[MAX_GROUPS] = {}; cudaEvent_t fork_ev = nullptr;
   cplx* Gpart = nullptr; size_t G_cap = 0;        // split-K Gram partials
   cplx* J = nullptr; size_t J_cap = 0;            // per-pair 64x64 rotations
   double* sig = nullptr; int* perm = nullptr; size_t s_cap = 0;   // sorted singular values + permutation
@@ -27,7 +25,6 @@ struct SvdWork {
   cplx* Rb = nullptr; size_t Rb_cap = 0;           // second-pass R / scratch
   cplx* Rc = nullptr; size_t Rc_cap = 0;           // product scratch
   cplx* small = nullptr;                           // 3 x 64x64: Rinv, Rtot, scratch
-  cplx* Cpart = nullptr; size_t Cpart_cap = 0;     // split-K partials of the projection coefficients
   cplx* Tg = nullptr; size_t Tg_cap = 0;           // gathered / scaled singular-vector block (ncols_pad x k)
   bool precond = false; int jrows = 0;             // Jacobi ran on an jrows x ncols_pad matrix
   // description of the last factorisation

@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 // round work on neighbouring tiles over the SAME k range (they share operand rows / columns through L2, exactly like
 // the tiles of a full wave -- a free-running unit split loses that reuse and cost 4x the DRAM reads).  Tiles with
 // nseg > 1 are accumulated with red.global.add.f64.
-struct SkPlan { int tiles_fast, dp_tiles, rem_tiles, nseg, kt; };
+// Sub-wave problems (fewer tiles than CTA slots; operands fit in L2 anyway) instead use one contiguous run of k-tile
+// units per CTA (unit_ctas > 0): fewer, longer runs amortise the pipeline ramp and the atomic epilogue better.
+struct SkPlan { int tiles_fast, dp_tiles, rem_tiles, nseg, kt, unit_ctas; };
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -360,6 +362,21 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
     int m_blk, n_blk;
     origin(tile, m_blk, n_blk);
     gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, 0, d.K, false);
+  }
+  if (pl.unit_ctas > 0) {
+    if (c >= pl.unit_ctas) return;
+    const long long units = (long long)pl.rem_tiles * pl.kt;
+    long long u = units * c / pl.unit_ctas;
+    const long long u_end = units * (c + 1) / pl.unit_ctas;
+    while (u < u_end) {
+      const int tile = (int)(u / pl.kt), k0 = (int)(u - (long long)tile * pl.kt);
+      const int k1 = (int)min((long long)pl.kt, k0 + (u_end - u));
+      int m_blk, n_blk;
+      origin(tile, m_blk, n_blk);
+      gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, 0, 0, k0 * Cfg::BK, min(d.K, k1 * Cfg::BK), !(k0 == 0 && k1 == pl.kt));
+      u += k1 - k0;
+    }
+    return;
   }
   const int items = pl.rem_tiles * pl.nseg;
   for (int item = c; item < items; item += gridDim.x) {
@@ -416,8 +433,14 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
         const double dur = (double)(((long long)pl.rem_tiles * ns + slots - 1) / slots) / ns;
         if (dur < best - 1e-9) { best = dur; pl.nseg = ns; }
       }
+      pl.unit_ctas = 0;
+      if (pl.dp_tiles == 0) {   // sub-wave problem: contiguous unit runs, at least 16 k-tiles per CTA
+        pl.unit_ctas = (int)std::max<long long>(1, std::min<long long>(slots, (long long)pl.rem_tiles * KT / 16));
+        pl.nseg = 2;            // (marks the launch as split)
+      }
       if (pl.nseg > 1) {     // otherwise no split beats the plain partial wave: fall through to the ordinary launch
-        const int grid = (int)std::min<long long>(slots, std::max<long long>(pl.dp_tiles, (long long)pl.rem_tiles * pl.nseg));
+        const int grid = pl.unit_ctas > 0 ? pl.unit_ctas
+                                          : (int)std::min<long long>(slots, std::max<long long>(pl.dp_tiles, (long long)pl.rem_tiles * pl.nseg));
         // partial tiles are accumulated atomically: zero the (dense, possibly pitched) output first
         TN_CUDA(cudaMemset2DAsync(d.C, (size_t)d.cn.s0 * sizeof(cplx), 0, (size_t)d.M * sizeof(cplx), (size_t)d.N, stream));
         kern_sk<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd, pl);
