@@ -121,8 +121,14 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
           // t = sign(dl)|c| / (|dl| + sqrt(dl^2 + |c|^2)), dl = (b-a)/2;  with h = |dl| + sqrt(dl^2+|c|^2):
           // cs = h / sqrt(h^2 + |c|^2),  s = sign(dl) c / sqrt(h^2 + |c|^2)   (one sqrt, one rsqrt, no division:
           // FP64 latency on this part is ~50 cycles per dependent op, so the length of this chain sets the step time)
+          // (h only steers the rotation ANGLE: the rotation stays unitary to FP64 accuracy for any h because cs and s share
+          // the accurate factor q below.  So the first square root is taken in FP32 when the argument is in range -- a
+          // 1e-7 relative angle error costs nothing in a Jacobi iteration and removes ~10 dependent FP64 operations from the
+          // 32-thread critical section of every step.)
           double dl = 0.5 * (b - a);
-          double h = fabs(dl) + sqrt(fma(dl, dl, absc2));
+          const double r2 = fma(dl, dl, absc2);
+          const double r = (r2 > 1e-30 && r2 < 1e30) ? (double)sqrtf((float)r2) : sqrt(r2);
+          double h = fabs(dl) + r;
           double q = rsqrt(fma(h, h, absc2));
           cs = h * q;
           double sg = dl >= 0 ? q : -q;
@@ -291,19 +297,20 @@ __global__ void __launch_bounds__(256) gather_kernel(const cplx* __restrict__ sr
 //   G (+ shift I) = R^H R ;  Rinv = R^-1 ;  Rtot <- R * Rtot      (pass 0: Rtot = R, with the shift)
 // Exactly-zero columns (padding, product states) are kept as null columns: pivot 1, row/column 0, and their
 // row of Rtot is zeroed after the last pass.  A failed pivot in later passes leaves that column untouched.
-__global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
+constexpr int CHOL_THREADS = 1024;
+__global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
                                                              cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot, int pass, int last_pass,
                                                              double shift_factor) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);                                    // G, then R in its upper triangle
   cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1, then old Rtot
-  __shared__ double red[8];
+  __shared__ double red[CHOL_THREADS / 32];
   __shared__ int nullcol[JP];
   __shared__ double rrow[JP];       // 1 / R(j,j) per row (0 = null / failed pivot)
   __shared__ double rdinv[JP];      // reciprocal diagonal of R (divisions cost ~600 cycles of FP64 latency: do each once)
   const int tid = threadIdx.x;
   double fro = 0;
-  for (int e = tid; e < JP * JP; e += 256) {
+  for (int e = tid; e < JP * JP; e += CHOL_THREADS) {
     int row = e % JP, col = e / JP;
     double xr = 0, xi = 0;
     for (int s = 0; s < nsplit; ++s) { cplx v = Gpart[s * split_stride + e]; xr += v.x; xi += v.y; }
@@ -313,11 +320,11 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
   if ((tid & 31) == 0) red[tid >> 5] = fro;
   __syncthreads();
-  fro = 0; for (int i = 0; i < 8; ++i) fro += red[i];
+  fro = 0; for (int i = 0; i < CHOL_THREADS / 32; ++i) fro += red[i];
   const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
   if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
   __syncthreads();
-  for (int e = tid; e < JP * JP; e += 256) {   // symmetrise + shift
+  for (int e = tid; e < JP * JP; e += CHOL_THREADS) {   // symmetrise + shift
     int row = e % JP, col = e / JP;
     if (row < col) {
       cplx a = G[row][col], b = G[col][row];
@@ -329,9 +336,10 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
   // Right-looking Cholesky G = R^H R, one barrier per column: step j only READS row j (final since step j-1) and
   // applies the rank-1 update G(i,c) -= conj(G(j,i)) G(j,c) / G(j,j) to the trailing upper triangle, every thread
   // deriving 1/G(j,j) itself (no broadcast barrier); the rows are scaled by 1/sqrt(G(j,j)) in one pass at the end.
-  // Thread t owns column c = t % 64 and rows (t / 64) + 4q.
+  // Thread t owns column c = t % 64 and rows (t / 64) + 16q.  1024 threads = 8 warps per scheduler: the ~50-cycle
+  // dependent-issue latency of FP64 on this part is hidden by the other warps instead of being paid per operation.
   const int lane = tid & 31, wrp = tid >> 5;
-  const int cc = (lane & 7) + 8 * wrp, part = lane >> 3;
+  const int cc = 2 * wrp + (lane >> 4), part = lane & 15;     // back substitution: 2 columns per warp, 16 threads per column
   {
     const int c = tid & 63, i0 = tid >> 6;
     for (int j = 0; j < JP; ++j) {
@@ -343,8 +351,8 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
       if (!bad && c > j) {
         const cplx gjc = G[j][c];
 #pragma unroll
-        for (int q = 0; q < JP / 4; ++q) {
-          const int i = i0 + 4 * q;
+        for (int q = 0; q < JP / (CHOL_THREADS / 64); ++q) {
+          const int i = i0 + (CHOL_THREADS / 64) * q;
           if (i > j && i <= c) {
             const cplx gji = G[j][i];
             const double ar = gji.x * gjc.x + gji.y * gjc.y, ai = gji.x * gjc.y - gji.y * gjc.x;   // conj(G(j,i)) G(j,c)
@@ -356,7 +364,7 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
       }
       __syncthreads();
     }
-    for (int e = tid; e < JP * JP; e += 256) {
+    for (int e = tid; e < JP * JP; e += CHOL_THREADS) {
       const int row = e / JP, col = e % JP;
       if (col < row) { G[row][col] = make_double2(0, 0); continue; }
       const double ri = rrow[row];
@@ -365,19 +373,19 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
     }
   }
   __syncthreads();
-  // R^-1 by back substitution: column cc of the inverse, rows i = cc .. 0; the row's dot product is split over the 4
-  // threads of the column group.  Each warp owns 8 columns, so only warp-level synchronisation is needed.
+  // R^-1 by back substitution: column cc of the inverse, rows i = cc .. 0; the row's dot product is split over the 16
+  // threads of the column group (<= 4 terms each).  Each warp owns 2 columns, so only warp-level synchronisation is needed.
   {
-    for (int i = JP - 1 - part; i > cc; i -= 4) Ri[i][cc] = make_double2(0, 0);
+    for (int i = JP - 1 - part; i > cc; i -= 16) Ri[i][cc] = make_double2(0, 0);
     __syncwarp();
-    const int cmax = 8 * wrp + 7;                       // largest column handled by this warp
+    const int cmax = 2 * wrp + 1;                       // largest column handled by this warp
     for (int i = cmax; i >= 0; --i) {
       double ar0 = 0, ai0 = 0;
       if (i <= cc) {
-        for (int k = i + 1 + part; k <= cc; k += 4) { cplx a = G[i][k], b = Ri[k][cc]; ar0 += a.x * b.x - a.y * b.y; ai0 += a.x * b.y + a.y * b.x; }
+        for (int k = i + 1 + part; k <= cc; k += 16) { cplx a = G[i][k], b = Ri[k][cc]; ar0 += a.x * b.x - a.y * b.y; ai0 += a.x * b.y + a.y * b.x; }
       }
-      ar0 += __shfl_xor_sync(0xffffffffu, ar0, 8); ai0 += __shfl_xor_sync(0xffffffffu, ai0, 8);
-      ar0 += __shfl_xor_sync(0xffffffffu, ar0, 16); ai0 += __shfl_xor_sync(0xffffffffu, ai0, 16);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) { ar0 += __shfl_xor_sync(0xffffffffu, ar0, o); ai0 += __shfl_xor_sync(0xffffffffu, ai0, o); }
       if (part == 0 && i <= cc) {
         double dinv = rdinv[i];
         Ri[i][cc] = make_double2(((i == cc ? 1.0 : 0.0) - ar0) * dinv, -ai0 * dinv);
@@ -386,11 +394,11 @@ __global__ void __launch_bounds__(256, 1) chol_inv64_kernel(const cplx* __restri
     }
   }
   __syncthreads();
-  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
+  for (int e = tid; e < JP * JP; e += CHOL_THREADS) { int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
   __syncthreads();
-  for (int e = tid; e < JP * JP; e += 256) { int row = e % JP, col = e / JP; Ri[row][col] = pass == 0 ? make_double2(row == col ? 1.0 : 0.0, 0.0) : Rtot[e]; }
+  for (int e = tid; e < JP * JP; e += CHOL_THREADS) { int row = e % JP, col = e / JP; Ri[row][col] = pass == 0 ? make_double2(row == col ? 1.0 : 0.0, 0.0) : Rtot[e]; }
   __syncthreads();
-  for (int e = tid; e < JP * JP; e += 256) {   // Rtot <- R * Rtot
+  for (int e = tid; e < JP * JP; e += CHOL_THREADS) {   // Rtot <- R * Rtot
     int row = e % JP, col = e / JP;
     double xr = 0, xi = 0;
     double yr = 0, yi = 0;
@@ -610,7 +618,7 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)JP * JP * sizeof(cplx), s));
       zgemm_auto(g, s);
-      chol_inv64_kernel<<<1, 256, chol_smem, s>>>(w.Gpart, 1, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
+      chol_inv64_kernel<<<1, CHOL_THREADS, chol_smem, s>>>(w.Gpart, 1, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
                                                   chol_passes == 3 ? shift_factor : 0.0);
       TN_CUDA(cudaGetLastError());
       count_launch(1);

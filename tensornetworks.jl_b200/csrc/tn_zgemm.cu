@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 // round work on neighbouring tiles over the SAME k range (they share operand rows / columns through L2, exactly like
 // the tiles of a full wave -- a free-running unit split loses that reuse and cost 4x the DRAM reads).  Tiles with
 // nseg > 1 are accumulated with red.global.add.f64.
-// Sub-wave problems (fewer tiles than CTA slots; operands fit in L2 anyway) instead use one contiguous run of k-tile
+// Problems of less than two waves of tiles (operands fit in L2 anyway) instead use one contiguous run of k-tile
 // units per CTA (unit_ctas > 0): fewer, longer runs amortise the pipeline ramp and the atomic epilogue better.
 struct SkPlan { int tiles_fast, dp_tiles, rem_tiles, nseg, kt, unit_ctas; };
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
@@ -422,7 +422,7 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
     if (eff < 0.94 && KT >= 16 && T < (1ll << 30)) {
       SkPlan pl;
       pl.tiles_fast = dd.swap_raster ? (int)tn_ : (int)tm;
-      pl.dp_tiles = (int)((T / slots) * slots);
+      pl.dp_tiles = (T < 2 * (long long)slots) ? 0 : (int)((T / slots) * slots);   // under two waves: one unit run per CTA
       pl.rem_tiles = (int)(T - pl.dp_tiles);
       pl.kt = KT;
       // segments per remainder tile: minimise the duration ceil(rem * nseg / slots) / nseg of the last phase
@@ -434,7 +434,7 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
         if (dur < best - 1e-9) { best = dur; pl.nseg = ns; }
       }
       pl.unit_ctas = 0;
-      if (pl.dp_tiles == 0) {   // sub-wave problem: contiguous unit runs, at least 16 k-tiles per CTA
+      if (pl.dp_tiles == 0) {   // small problem: contiguous unit runs, at least 16 k-tiles per CTA
         pl.unit_ctas = (int)std::max<long long>(1, std::min<long long>(slots, (long long)pl.rem_tiles * KT / 16));
         pl.nseg = 2;            // (marks the launch as split)
       }
