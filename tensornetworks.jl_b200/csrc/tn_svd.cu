@@ -121,14 +121,8 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
           // t = sign(dl)|c| / (|dl| + sqrt(dl^2 + |c|^2)), dl = (b-a)/2;  with h = |dl| + sqrt(dl^2+|c|^2):
           // cs = h / sqrt(h^2 + |c|^2),  s = sign(dl) c / sqrt(h^2 + |c|^2)   (one sqrt, one rsqrt, no division:
           // FP64 latency on this part is ~50 cycles per dependent op, so the length of this chain sets the step time)
-          // (h only steers the rotation ANGLE: the rotation stays unitary to FP64 accuracy for any h because cs and s share
-          // the accurate factor q below.  So the first square root is taken in FP32 when the argument is in range -- a
-          // 1e-7 relative angle error costs nothing in a Jacobi iteration and removes ~10 dependent FP64 operations from the
-          // 32-thread critical section of every step.)
           double dl = 0.5 * (b - a);
-          const double r2 = fma(dl, dl, absc2);
-          const double r = (r2 > 1e-30 && r2 < 1e30) ? (double)sqrtf((float)r2) : sqrt(r2);
-          double h = fabs(dl) + r;
+          double h = fabs(dl) + sqrt(fma(dl, dl, absc2));
           double q = rsqrt(fma(h, h, absc2));
           cs = h * q;
           double sg = dl >= 0 ? q : -q;
@@ -300,7 +294,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const cplx* __restrict__ sr
 constexpr int CHOL_THREADS = 1024;
 __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
                                                              cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot, int pass, int last_pass,
-                                                             double shift_factor) {
+                                                             double shift_factor, int* __restrict__ done_flag) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);                                    // G, then R in its upper triangle
   cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1, then old Rtot
@@ -309,6 +303,13 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx*
   __shared__ double rrow[JP];       // 1 / R(j,j) per row (0 = null / failed pivot)
   __shared__ double rdinv[JP];      // reciprocal diagonal of R (divisions cost ~600 cycles of FP64 latency: do each once)
   const int tid = threadIdx.x;
+  // CholeskyQR3 with early termination: the second pass marks the panel as finished when its Gram matrix was already
+  // within 1e-3 of the identity (one Cholesky pass on such a panel leaves O(eps) orthogonality error); the third pass'
+  // Gram / Cholesky / apply launches then return at once.
+  if (done_flag != nullptr) {
+    if (pass == 0) { if (tid == 0) *done_flag = 0; }
+    else if (pass == 2 && *done_flag != 0) return;
+  }
   double fro = 0;
   for (int e = tid; e < JP * JP; e += CHOL_THREADS) {
     int row = e % JP, col = e / JP;
@@ -324,13 +325,26 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx*
   const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
   if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
   __syncthreads();
+  double dev = 0;                                        // max |G - I| over the non-null part (second pass only)
   for (int e = tid; e < JP * JP; e += CHOL_THREADS) {   // symmetrise + shift
     int row = e % JP, col = e / JP;
     if (row < col) {
       cplx a = G[row][col], b = G[col][row];
       cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
       G[row][col] = h; G[col][row] = make_double2(h.x, -h.y);
-    } else if (row == col) { G[row][col].x += shift; G[row][col].y = 0; }
+      dev = fmax(dev, fmax(fabs(h.x), fabs(h.y)));
+    } else if (row == col) {
+      if (!nullcol[row]) dev = fmax(dev, fabs(G[row][col].x - 1.0));
+      G[row][col].x += shift; G[row][col].y = 0;
+    }
+  }
+  if (done_flag != nullptr && pass == 1) {
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    __syncthreads();                                     // red[] was read above
+    if ((tid & 31) == 0) red[tid >> 5] = dev;
+    __syncthreads();
+    dev = 0; for (int i = 0; i < CHOL_THREADS / 32; ++i) dev = fmax(dev, red[i]);
+    if (dev < 1e-3) { last_pass = 1; if (tid == 0) *done_flag = 1; }
   }
   __syncthreads();
   // Right-looking Cholesky G = R^H R, one barrier per column: step j only READS row j (final since step j-1) and
@@ -615,15 +629,20 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
     cplx* P = Q + (long long)pk * JP * ldq;
     for (int it = 0; it < chol_passes; ++it) {
       GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
+      // third pass of CholeskyQR3: skipped on the device when the second pass found the panel already orthonormal to 1e-3
+      const int* skip3 = (chol_passes == 3 && it == 2) ? w.cflag : nullptr;
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
+      g.skip = skip3;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)JP * JP * sizeof(cplx), s));
       zgemm_auto(g, s);
       chol_inv64_kernel<<<1, CHOL_THREADS, chol_smem, s>>>(w.Gpart, 1, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
-                                                  chol_passes == 3 ? shift_factor : 0.0);
+                                                  chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr);
       TN_CUDA(cudaGetLastError());
       count_launch(1);
       // P <- P * Rinv (in place: each CTA owns 128 rows x all 64 columns)
-      zgemm_auto(gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq)), s);
+      GemmDesc ap = gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq));
+      ap.skip = skip3;
+      zgemm_auto(ap, s);
     }
     // R(pk,pk) = Rtot
     TN_CUDA(cudaMemcpy2DAsync(R + (long long)pk * JP + (long long)pk * JP * npad, (size_t)npad * sizeof(cplx), Rtot, (size_t)JP * sizeof(cplx),
@@ -687,7 +706,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
     TN_CUDA(cudaMallocAsync((void**)&w.perm, npad * sizeof(int), s));
     w.s_cap = npad;
   }
-  if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
+  if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.cflag, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
   int blocks;
   SvdProf& pf = prof();
   if (pf.on) { for (double& m : pf.ms) m = 0; pf.used = 0; pf.mark(PH_START, s); }
@@ -794,7 +813,7 @@ void svd_free(SvdWork& w) {
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
-  if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); }
+  if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); cudaFree(w.cflag); }
   for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
   w = SvdWork{};

@@ -16,6 +16,7 @@ struct SvdWork {
   double* sig = nullptr; int* perm = nullptr; size_t s_cap = 0;   // sorted singular values + permutation
   double* sig2 = nullptr;                          // unsorted squared column norms
   unsigned long long* offmax = nullptr;            // convergence measure (double bits)
+  int* cflag = nullptr;                            // CholeskyQR3 early-termination flag of the current panel
   int* kout = nullptr;                             // device-side truncation rank
   std::map<int, int*> tables;                      // round-robin pair tables per block count
   // QR preconditioner (two GEMM-based QR factorisations: A = Q1 R1, R1^H = Q2 R2, Jacobi on X = R2^H)
