@@ -22,6 +22,7 @@ CHI_MAX = int(os.environ.get("CHI_MAX", "512"))
 ORACLE_CHI = int(os.environ.get("ORACLE_CHI", "64"))
 CUTOFF = float(os.environ.get("CUTOFF", "1e-12"))
 CHI_MIN = int(os.environ.get("CHI_MIN", "64"))
+NSWEEPS = int(os.environ.get("NSWEEPS", "2"))      # sweeps per maxdim (the bond dimension at most doubles per sweep)
 ctx = tnb200.Context.default()
 
 
@@ -76,7 +77,7 @@ if "c2" in what:
     direction = False
     chi = CHI_MIN
     while chi <= CHI_MAX:
-        res, direction2 = gpu_sweeps(g, Hs, 2, direction, chi)
+        res, direction2 = gpu_sweeps(g, Hs, NSWEEPS, direction, chi)
         line = dict(config="C2 XXZ N=100 w=5 two-site DMRG", maxdim=chi, cutoff=CUTOFF, gpu=res)
         if chi <= ORACLE_CHI:
             ho = []
