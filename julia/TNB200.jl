@@ -2,7 +2,7 @@
 # build image).  It keeps the reference's API and dispatches the hot path into libtnb200.so.
 module TNB200
 using TensorNetworks
-import TensorNetworks: GMPS, AbstractProjMPS, movecenter!, product, calculate, buildleft!, buildright!, block, applygates!, norm, normalize!
+import TensorNetworks: GMPS, AbstractProjMPS, movecenter!, product, calculate, buildleft!, buildright!, block, applygates!, norm, normalize!, inner
 
 const lib = get(ENV, "TNB200_LIB", "libtnb200.so")
 struct TruncT; cutoff::Cdouble; maxdim::Int64; mindim::Int64; end
@@ -104,6 +104,18 @@ function qjmc_run!(psi::CuGMPS, gates::CuGateList, jumpsites::Vector{Int32}, jum
         obs, jumps, times, steps + 1, nj))
     jumps[1:nj[]], times[1:nj[]], obs[:, 1:nsave]
 end
+# inner(st, psi, oplist, phi) (mps.jl:87-134) with psi, phi on the device: per-term coeff * <psi| O_t |phi>
+function inner(st::Sitetypes, psi::CuGMPS, oplist::OpList, phi::CuGMPS)
+    nops = Int32[length(s) for s in oplist.sites]
+    sites = Int32[x for s in oplist.sites for x in s]
+    mats = ComplexF64[]
+    for ops in oplist.ops, name in ops; append!(mats, vec(ComplexF64.(op(st, name)))); end
+    coeffs = ComplexF64.(oplist.coeffs); out = zeros(ComplexF64, length(nops))
+    check(ccall((:tn_inner_oplist, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{ComplexF64}, Ptr{ComplexF64}, Ptr{ComplexF64}),
+                psi.h, phi.h, length(nops), nops, sites, mats, coeffs, out))
+    out
+end
+
 # Many trajectories from one initial state (the loop a user writes around qjmc_simulation): tn_qjmc_ensemble hands them out to
 # `workers` host threads / CUDA streams inside the library; trajectory ids key the random numbers, so results do not depend on
 # the worker count or on which GPU ran them (shard ids over processes / GPUs as `ids = rank+1:world:ntraj`).
