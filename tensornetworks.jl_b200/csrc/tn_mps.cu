@@ -390,10 +390,10 @@ void heff_stage3(Env* e, int site, int a0, int a1, cplx* out) {
 }
 
 // H_eff * theta for sites (site, site+1):  out(a,s1,s2,a') = coeff * sum L M1 M2 theta R   (projmps.jl:107-134, :144)
-void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4) {
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4, bool prepared) {
   Ctx* c = e->ctx; cudaStream_t s = c->stream;
   HeffDims h = heff_dims(e, site);
-  heff_prepare(e, site);
+  if (!prepared) heff_prepare(e, site);   // W = M1.M2 + intermediates; the Lanczos loop prepares once per bond
   if (ev4) TN_CUDA(cudaEventRecord(ev4[0], s));
   heff_stage12(e, theta, site, 0, h.cb2, ev4 ? &ev4[1] : nullptr);
   if (ev4) TN_CUDA(cudaEventRecord(ev4[2], s));
@@ -515,6 +515,7 @@ double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, lon
   cplx* w = c->scratch[9].get((size_t)n, s);
   cplx* tmpv[3]; for (int j = 0; j < 3; ++j) tmpv[j] = c->scratch[10 + j].get((size_t)n, s);
   double T[3][3] = {{0}};
+  heff_prepare(e, site);    // once per bond: the <= 5 H_eff applications below share W and the intermediates
   cplx* ds = c->dscal;   // device scalars: [0..3] dots, [8] norm^2, [16+..] log of alpha/beta per step
   // v1 = theta0 / ||theta0||
   { const cplx* xs[1] = {theta0}; zdots(n, 1, xs, theta0, ds + 8, c->partials, s); zscale_invnorm(n, theta0, ds + 8, V[0], s); }
@@ -522,7 +523,7 @@ double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, lon
   int logn = 0;   // scalars recorded on device: pairs (alpha_i at ds[16+2i], beta_i^2 at ds[17+2i])
   auto expand = [&](int Kc) {
     // w = H V[Kc-1]; alpha = Re<v,w>; w -= sum_j <v_j,w> v_j (twice); beta^2 = <w,w>
-    env_product_dev(e, V[Kc - 1], site, w);
+    env_product_dev(e, V[Kc - 1], site, w, nullptr, true);
     numops++;
     const cplx* xs[3] = {V[0], V[1], V[2]};
     zdots(n, Kc, xs, w, ds, c->partials, s);

@@ -79,7 +79,7 @@ void env_buildleft(Env* e, int idx);
 void env_buildright(Env* e, int idx);
 void env_movecenter(Env* e, int idx);
 const Tensor& env_block(Env* e, int idx);
-void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4 = nullptr);   // sites (site, site+1)
+void env_product_dev(Env* e, const cplx* theta, int site, cplx* out, cudaEvent_t* ev4 = nullptr, bool prepared = false);   // sites (site, site+1)
 void env_product_host(Env* e, const cplx* theta_host, int site, cplx* out_host);   // pipelined PCIe copies
 cplx env_calculate(Env* e);
 
