@@ -485,6 +485,15 @@ static bool precond_enabled() {
   return g_precond_mode == 1;
 }
 
+// Upper bound on the split-K factors of the SVD's Gram / projection GEMMs.  Splitting trades CTA efficiency (short k
+// loops, atomic epilogues) for latency; a single stream wants the latency, many concurrent streams (QJMC ensembles) are
+// throughput-bound and can lower it (TN_SVD_MAXSPLIT).
+static int max_split() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_MAXSPLIT"); v = e ? std::max(1, atoi(e)) : 32; }
+  return v;
+}
+
 static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
 
 // Optional phase timing (TN_SVD_PROFILE=1): CUDA events at the phase boundaries, summed per factorisation and printed
@@ -520,7 +529,7 @@ enum { PH_START = 0, PH_GRAM = 1, PH_EVD = 2, PH_ROT = 3, PH_QR = 4, PH_FIN = 5,
 static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
   // Gram GEMM grid = np pairs x ksplit: fill the 2 x 148 CTA slots of the 64 x 64 kernel once (no partial second wave)
-  int ksplit = std::max(1, std::min(std::min(16, jrows / 64), (2 * 148) / np));
+  int ksplit = std::max(1, std::min(std::min(std::min(16, max_split()), jrows / 64), (2 * 148) / np));
   int kchunk = ((jrows + ksplit - 1) / ksplit + 7) / 8 * 8;
   ksplit = (jrows + kchunk - 1) / kchunk;
   ensure(w.Gpart, w.G_cap, (size_t)std::max(ksplit, 32) * np * JP * JP, s);
@@ -619,7 +628,7 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
   if (!cfg) { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); cfg = true; }
   TN_CUDA(cudaMemsetAsync(R, 0, (size_t)npad * npad * sizeof(cplx), s));
   ensure(w.Gpart, w.G_cap, (size_t)32 * JP * JP, s);
-  int ksplit = std::max(1, std::min(32, rows / 64));   // one 64 x 64 tile per panel: spread its K range over many SMs
+  int ksplit = std::max(1, std::min(std::min(32, max_split()), rows / 64));   // one 64 x 64 tile per panel: spread its K range over many SMs
   int kchunk = ((rows + ksplit - 1) / ksplit + 7) / 8 * 8;
   ksplit = (rows + kchunk - 1) / kchunk;
   cplx* Rinv = w.small; cplx* Rtot = w.small + JP * JP;
@@ -652,7 +661,7 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       cplx* T = Q + (long long)(pk + 1) * JP * ldq;
       // C = P^H T  (64 x nt), split-K partials -> R(pk, trail)
       // 64 x 128 tiles, one CTA per SM: pick the split that fills one wave of 148 CTAs
-      int csplit = std::max(1, std::min(std::min(16, rows / 64), 148 / ((nt + 127) / 128)));
+      int csplit = std::max(1, std::min(std::min(std::min(16, max_split()), rows / 64), 148 / ((nt + 127) / 128)));
       int cchunk = ((rows + csplit - 1) / csplit + 7) / 8 * 8;
       csplit = (rows + cchunk - 1) / cchunk;
       // split-K contributions go straight into the block row of R (zeroed by the memset above) with red.global.add.f64
