@@ -26,6 +26,7 @@ typedef struct tn_ctx tn_ctx;
 typedef struct tn_mps tn_mps;     /* GMPS of rank 1 (MPS) or 2 (MPO): structures/mps/gmps.jl:8-13 */
 typedef struct tn_env tn_env;     /* ProjMPS: structures/mps/projmps.jl:1-8 */
 typedef struct tn_gates tn_gates; /* GateList: structures/mps/gatelist.jl:8-13 */
+typedef struct tn_envsum tn_envsum; /* ProjMPSSum: structures/mps/projmpssum.jl:1-4 */
 
 /* kwargs of svd(): tensors.jl:170-172 (cutoff=0, maxdim=0 meaning unlimited, mindim=1) */
 typedef struct { double cutoff; int64_t maxdim; int64_t mindim; } tn_trunc_t;
@@ -120,12 +121,40 @@ int32_t tn_env_product_dev(tn_env* e, const void* theta_dev, int32_t direction, 
 int32_t tn_env_product_profile(tn_env* e, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps, double* stage_ms3);
 int32_t tn_env_calculate(tn_env* e, tn_cplx* out);      /* projmps.jl:192-216 */
 
+/* ---- projector branch and sums of projections ----------------------------------------------------------------- */
+/* ProjMPS(V, psi; rank=2, squared=true, coeff, center) as built at algorithms/mps/dmrg.jl:144-145: the penalty
+ * coeff * |V><V| in psi's local basis; product = coeff * phi <phi, A> with phi = conj(project(...)) (projmps.jl:135-143). */
+int32_t tn_env_create_squared(tn_ctx* ctx, tn_mps* V, tn_mps* psi, tn_cplx coeff, int32_t center, tn_env** out);
+/* product(projV, A, direction, nsites) for nsites = 1 or 2 (projmps.jl:103-145): the rank-2 branch of an environment with
+ * an MPO layer, or the squared branch of tn_env_create_squared.  A / out on the host, shape (chi_l, d[, d], chi_r) of the
+ * sites site .. site+nsites-1, site = direction ? center-nsites+1 : center. */
+int32_t tn_env_product_n(tn_env* e, const tn_cplx* A_host, int32_t direction, int32_t nsites, tn_cplx* out_host);
+/* project(projV, A, direction, nsites): projmps.jl:153-185, for ProjMPS(bra, ket) and ProjMPS(bra, mpo, ket).  The
+ * reference never reads A, so it is not an argument.  out_host has the ket-side shape (chi_l, d[, d], chi_r). */
+int32_t tn_env_project(tn_env* e, int32_t direction, int32_t nsites, tn_cplx* out_host);
+/* ProjMPSSum(projVs; center): projmpssum.jl:11-19.  The members stay owned by their tn_env handles, which must outlive
+ * the sum, live in the same context and share the ket MPS. */
+int32_t tn_envsum_create(tn_ctx* ctx, int32_t n, tn_env* const* envs, int32_t center, tn_envsum** out);
+int32_t tn_envsum_free(tn_envsum* s);
+int32_t tn_envsum_movecenter(tn_envsum* s, int32_t idx);                                      /* projmpssum.jl:51-55 */
+int32_t tn_envsum_calculate(tn_envsum* s, tn_cplx* out);                                      /* projmpssum.jl:97-108 */
+int32_t tn_envsum_product(tn_envsum* s, const tn_cplx* A_host, int32_t direction, int32_t nsites, tn_cplx* out_host); /* :63-73 */
+int32_t tn_envsum_project(tn_envsum* s, int32_t direction, int32_t nsites, tn_cplx* out_host);                         /* :81-91 */
+
 /* ---- fused steps (what the drivers call) ------------------------------------------------------ */
 /* One direction of a two-site DMRG sweep, algorithms/mps/dmrg.jl:35-63: for every bond movecenter!(Hs),
  * theta = psi[s]*psi[s+1], eigsolve (Lanczos, KrylovKit schedule), replacesites!(..., normalize=true);
  * then movecenter!(Hs, end).  direction 0 = left-to-right.  Returns the last Ritz value and maxbonddim. */
 int32_t tn_dmrg_sweep(tn_mps* psi, tn_env* env, int32_t direction, tn_lanczos_t lanczos, tn_trunc_t trunc,
                       double* energy_out, int64_t* maxbond_out);
+/* The same half sweep over a ProjMPSSum (several MPOs and / or squared MPS projections: dmrg.jl:128-154, excited states by
+ * penalty) and for nsites = 1 or 2 (dmrg.jl:3; the one-site branch of replacesites! moves the centre untruncated). */
+int32_t tn_dmrg_sweep_sum(tn_mps* psi, tn_envsum* Hs, int32_t direction, int32_t nsites, tn_lanczos_t lanczos, tn_trunc_t trunc,
+                          double* energy_out, int64_t* maxbond_out);
+/* One direction of a vmps sweep, algorithms/mps/vmps.jl:36-62: for every bond movecenter!(Vs), vec = conj(project(Vs, .)),
+ * replacesites!(psi, vec, site1, direction; trunc) without normalisation; then movecenter!(Vs, end).  The cost
+ * norm(psi)^2 - 2|calculate(Vs)| (vmps.jl:16-23) and the convergence logic stay host-side. */
+int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsites, tn_trunc_t trunc, int64_t* maxbond_out);
 /* eigsolve alone on the two sites at the environment centre (host theta in/out); numops = H_eff applications */
 int32_t tn_eigsolve(tn_env* e, const tn_cplx* theta0_host, int32_t direction, tn_lanczos_t lanczos,
                     double* eig_out, tn_cplx* theta_out_host, int32_t* numops_out);

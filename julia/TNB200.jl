@@ -2,7 +2,7 @@
 # build image).  It keeps the reference's API and dispatches the hot path into libtnb200.so.
 module TNB200
 using TensorNetworks
-import TensorNetworks: GMPS, AbstractProjMPS, movecenter!, product, calculate, buildleft!, buildright!, block, applygates!, norm, normalize!, inner
+import TensorNetworks: GMPS, AbstractProjMPS, movecenter!, product, project, calculate, buildleft!, buildright!, block, applygates!, norm, normalize!, inner
 
 const lib = get(ENV, "TNB200_LIB", "libtnb200.so")
 struct TruncT; cutoff::Cdouble; maxdim::Int64; mindim::Int64; end
@@ -56,6 +56,49 @@ function product(p::CuProjMPS, A, direction::Bool=false, nsites::Int=2)   # proj
 end
 function calculate(p::CuProjMPS)
     v = Ref{ComplexF64}(); check(ccall((:tn_env_calculate, lib), Int32, (Ptr{Cvoid}, Ref{ComplexF64}), p.h, v)); v[]
+end
+
+# squared MPS projection ProjMPS(V, psi; rank=2, squared=true, coeff) (dmrg.jl:144-145) and sums of projections (projmpssum.jl)
+function CuProjMPS(V::CuGMPS, psi::CuGMPS, ::Val{:squared}; coeff=1.0, center=1)
+    h = Ref{Ptr{Cvoid}}()
+    check(ccall((:tn_env_create_squared, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, ComplexF64, Int32, Ref{Ptr{Cvoid}}),
+                psi.ctx.h, V.h, psi.h, ComplexF64(coeff), center, h))
+    CuProjMPS(h[], psi, V, center)
+end
+function project(p::CuProjMPS, A, direction::Bool=false, nsites::Int=2)   # projmps.jl:153-185 (A only fixes the shape)
+    out = similar(A)
+    check(ccall((:tn_env_project, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), p.h, direction, nsites, out)); out
+end
+mutable struct CuProjMPSSum <: AbstractProjMPS; h::Ptr{Cvoid}; projs::Vector{CuProjMPS}; center::Int; end
+function CuProjMPSSum(projs::Vector{CuProjMPS}; center=1)
+    h = Ref{Ptr{Cvoid}}(); hs = [p.h for p in projs]
+    check(ccall((:tn_envsum_create, lib), Int32, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}, Int32, Ref{Ptr{Cvoid}}), projs[1].psi.ctx.h, length(hs), hs, center, h))
+    s = CuProjMPSSum(h[], projs, center); finalizer(x -> ccall((:tn_envsum_free, lib), Int32, (Ptr{Cvoid},), x.h), s); s
+end
+movecenter!(p::CuProjMPSSum, idx::Int) = (check(ccall((:tn_envsum_movecenter, lib), Int32, (Ptr{Cvoid}, Int32), p.h, idx)); p.center = idx)
+function product(p::CuProjMPSSum, A, direction::Bool=false, nsites::Int=2)   # projmpssum.jl:63-73
+    out = similar(A)
+    check(ccall((:tn_envsum_product, lib), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int32, Int32, Ptr{ComplexF64}), p.h, A, direction, nsites, out)); out
+end
+function project(p::CuProjMPSSum, A, direction::Bool=false, nsites::Int=2)   # projmpssum.jl:81-91
+    out = similar(A)
+    check(ccall((:tn_envsum_project, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}), p.h, direction, nsites, out)); out
+end
+function calculate(p::CuProjMPSSum)
+    v = Ref{ComplexF64}(); check(ccall((:tn_envsum_calculate, lib), Int32, (Ptr{Cvoid}, Ref{ComplexF64}), p.h, v)); v[]
+end
+# fused sweeps over a sum: dmrg.jl:35-63 for dmrg(psi, H1, H2, V...; coeffs) and nsites = 1 | 2; vmps.jl:36-62
+function dmrg_sweep!(psi::CuGMPS, Hs::CuProjMPSSum, direction::Bool; nsites=2, krylovdim=3, kryloviter=2, cutoff=1e-12, maxdim=1000, mindim=1)
+    e = Ref{Cdouble}(); D = Ref{Int64}()
+    check(ccall((:tn_dmrg_sweep_sum, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, LanczosT, TruncT, Ref{Cdouble}, Ref{Int64}),
+                psi.h, Hs.h, direction, nsites, LanczosT(krylovdim, kryloviter, 1e-14), TruncT(cutoff, maxdim, mindim), e, D))
+    e[], D[]
+end
+function vmps_sweep!(psi::CuGMPS, Vs::CuProjMPSSum, direction::Bool; nsites=2, cutoff=1e-12, maxdim=1000, mindim=1)
+    D = Ref{Int64}()
+    check(ccall((:tn_vmps_sweep, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, TruncT, Ref{Int64}),
+                psi.h, Vs.h, direction, nsites, TruncT(cutoff, maxdim, mindim), D))
+    D[]
 end
 
 # fused sweep: replaces the body of dmrg.jl:35-63

@@ -47,6 +47,7 @@ struct tn_ctx { Ctx c; };
 struct tn_mps { Mps* m; };
 struct tn_env { Env* e; };
 struct tn_gates { Gates* g; };
+struct tn_envsum { EnvSum* s; };
 
 static thread_local std::string g_err;
 
@@ -343,6 +344,104 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
     int nj = qjmc_run(psi->m, gates->g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), uniforms, seed, trajectory,
                       obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap);
     if (njumps_out) *njumps_out = nj;
+  });
+}
+
+// ---- projector sums / squared projectors / project / one-site branch / vmps (tn_projsum.cu) ----------------------
+int32_t tn_env_create_squared(tn_ctx* ctx, tn_mps* V, tn_mps* psi, tn_cplx coeff, int32_t center, tn_env** out) {
+  return guard([&] {
+    TN_CHECK(ctx && V && psi && out, "null pointer");
+    auto* h = new tn_env();
+    h->e = env_create_squared(&ctx->c, V->m, psi->m, cplx{coeff.re, coeff.im}, center);
+    *out = h;
+  });
+}
+static int nsite_site(int center, int N, int direction, int nsites) {   // projmps.jl:109, :155
+  TN_CHECK(nsites == 1 || nsites == 2, "nsites must be 1 or 2");
+  TN_CHECK(center >= 1, "the environment centre is not set");
+  int site = direction ? center - nsites + 1 : center;
+  TN_CHECK(site >= 1 && site + nsites - 1 <= N, "the sites fall outside the chain");
+  return site;
+}
+static long long nsite_size(Mps* ket, int site, int nsites) {
+  long long n = ket->chiL(site) * ket->chiR(site + nsites - 1);
+  for (int i = 0; i < nsites; ++i) n *= ket->d;
+  return n;
+}
+static void envsum_product_host(EnvSum* es, const tn_cplx* A, int direction, int nsites, tn_cplx* out) {
+  Ctx* c = es->ctx; cudaStream_t s = c->stream;
+  Mps* ket = es->projs[0]->ket;
+  int site = nsite_site(es->center, ket->N, direction, nsites);
+  long long n = nsite_size(ket, site, nsites);
+  cplx* din = c->scratch[13].get((size_t)n, s);
+  cplx* dout = c->scratch[14].get((size_t)n, s);
+  TN_CUDA(cudaMemcpyAsync(din, A, (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, s));
+  envsum_prepare(es, site, nsites);
+  envsum_apply(es, din, site, nsites, dout);
+  TN_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+  c->sync();
+}
+static void envsum_project_host(EnvSum* es, int direction, int nsites, tn_cplx* out) {
+  Ctx* c = es->ctx; cudaStream_t s = c->stream;
+  Mps* ket = es->projs[0]->ket;
+  int site = nsite_site(es->center, ket->N, direction, nsites);
+  long long n = nsite_size(ket, site, nsites);
+  cplx* d = c->scratch[14].get((size_t)n, s);
+  envsum_project_phi(es, site, nsites, d);
+  zconj_inplace(n, d, s);                    // project() itself, not its conjugate
+  TN_CUDA(cudaMemcpyAsync(out, d, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+  c->sync();
+}
+int32_t tn_env_product_n(tn_env* eh, const tn_cplx* A, int32_t direction, int32_t nsites, tn_cplx* out) {
+  return guard([&] {
+    TN_CHECK(eh && A && out, "null pointer");
+    EnvSum one{eh->e->ctx, {eh->e}, eh->e->center};
+    envsum_product_host(&one, A, direction, nsites, out);
+  });
+}
+int32_t tn_env_project(tn_env* eh, int32_t direction, int32_t nsites, tn_cplx* out) {
+  return guard([&] {
+    TN_CHECK(eh && out, "null pointer");
+    EnvSum one{eh->e->ctx, {eh->e}, eh->e->center};
+    envsum_project_host(&one, direction, nsites, out);
+  });
+}
+int32_t tn_envsum_create(tn_ctx* ctx, int32_t n, tn_env* const* envs, int32_t center, tn_envsum** out) {
+  return guard([&] {
+    TN_CHECK(ctx && envs && out && n >= 1, "ProjMPSSum: bad arguments");
+    std::vector<Env*> v;
+    for (int i = 0; i < n; ++i) { TN_CHECK(envs[i] != nullptr, "ProjMPSSum: null projection"); v.push_back(envs[i]->e); }
+    auto* h = new tn_envsum();
+    try { h->s = envsum_create(&ctx->c, n, v.data(), center); } catch (...) { delete h; throw; }
+    *out = h;
+  });
+}
+int32_t tn_envsum_free(tn_envsum* s) { return guard([&] { if (s) { envsum_free(s->s); delete s; } }); }
+int32_t tn_envsum_movecenter(tn_envsum* s, int32_t idx) { return guard([&] { envsum_movecenter(s->s, idx); }); }
+int32_t tn_envsum_calculate(tn_envsum* s, tn_cplx* out) { return guard([&] { cplx v = envsum_calculate(s->s); out->re = v.x; out->im = v.y; }); }
+int32_t tn_envsum_product(tn_envsum* s, const tn_cplx* A, int32_t direction, int32_t nsites, tn_cplx* out) {
+  return guard([&] { TN_CHECK(s && A && out, "null pointer"); envsum_product_host(s->s, A, direction, nsites, out); });
+}
+int32_t tn_envsum_project(tn_envsum* s, int32_t direction, int32_t nsites, tn_cplx* out) {
+  return guard([&] { TN_CHECK(s && out, "null pointer"); envsum_project_host(s->s, direction, nsites, out); });
+}
+int32_t tn_dmrg_sweep_sum(tn_mps* psi, tn_envsum* Hs, int32_t direction, int32_t nsites, tn_lanczos_t lz, tn_trunc_t tr,
+                          double* energy, int64_t* maxbond) {
+  return guard([&] {
+    TN_CHECK(psi && Hs, "null pointer");
+    long long mb = 0;
+    dmrg_halfsweep_sum(psi->m, Hs->s, direction != 0, nsites, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, T(tr), energy, &mb);
+    psi->m->ctx->sync();
+    if (maxbond) *maxbond = mb;
+  });
+}
+int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsites, tn_trunc_t tr, int64_t* maxbond) {
+  return guard([&] {
+    TN_CHECK(psi && Vs, "null pointer");
+    long long mb = 0;
+    vmps_halfsweep(psi->m, Vs->s, direction != 0, nsites, T(tr), &mb);
+    psi->m->ctx->sync();
+    if (maxbond) *maxbond = mb;
   });
 }
 

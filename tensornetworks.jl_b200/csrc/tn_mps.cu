@@ -16,9 +16,7 @@
 namespace tn {
 void count_launch(int n);
 
-static const cplx ONE = {1.0, 0.0}, ZERO = {0.0, 0.0};
-void zconj_inplace(long long n, cplx* x, cudaStream_t s);
-
+static const cplx ONE = {1.0, 0.0};
 cplx* Buf::get(size_t n, cudaStream_t s) {
   if (n > cap) {
     if (p) TN_CUDA(cudaFreeAsync(p, s));
@@ -40,17 +38,6 @@ void Ctx::alloc(Tensor& t, const std::vector<long long>& dims) {
   t.dims = dims;
 }
 void Ctx::free(Tensor& t) { if (t.p) cudaFreeAsync(t.p, stream); t.p = nullptr; t.cap = 0; t.dims.clear(); }
-
-static GemmDesc mk(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int conjA, const cplx* B, Idx2 bk, Idx2 bn, int conjB,
-                   cplx* C, Idx2 cm, Idx2 cn, cplx alpha = ONE, cplx beta = ZERO) {
-  GemmDesc g{};
-  g.M = M; g.N = N; g.K = K;
-  g.A = A; g.am = am; g.ak = ak; g.conjA = conjA;
-  g.B = B; g.bk = bk; g.bn = bn; g.conjB = conjB;
-  g.C = C; g.cm = cm; g.cn = cn; g.alpha = alpha; g.beta = beta;
-  g.batch = 1; g.ksplit = 1; g.kchunk = K;
-  return g;
-}
 
 // ================================================================================================
 // MPS container
@@ -95,7 +82,7 @@ void mps_upload_site(Mps* m, int i, const long long* dims, const cplx* host) {
   m->ctx->sync();
 }
 
-static cplx read_scalar(Ctx* c, int slot) {
+cplx read_scalar(Ctx* c, int slot) {
   TN_CUDA(cudaMemcpyAsync(c->hscal + slot, c->dscal + slot, sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
   c->sync();
   return c->hscal[slot];
@@ -234,6 +221,7 @@ void env_free(Env* e) {
   if (!e) return;
   for (auto& t : e->blocks) e->ctx->free(t);
   e->ctx->free(e->edge);
+  e->ctx->free(e->phi);
   delete e;
 }
 const Tensor& env_block(Env* e, int idx) {   // abstractprojmps.jl:43-46
@@ -330,6 +318,12 @@ __global__ void build_w2_kernel(const cplx* __restrict__ M1, const cplx* __restr
     xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x;
   }
   W[e] = make_double2(xr, xi);
+}
+
+void build_w2(const cplx* M1, const cplx* M2, cplx* W, int w, int w1, int w2, int d, cudaStream_t s) {
+  int tot = w * d * d * d * d * w2;
+  build_w2_kernel<<<(tot + 127) / 128, 128, 0, s>>>(M1, M2, W, w, w1, w2, d);
+  count_launch(1);
 }
 
 // H_eff * theta for sites (site, site+1):  out(a,s1,s2,a') = coeff * sum L M1 M2 theta R   (projmps.jl:107-134, :144)
@@ -508,14 +502,18 @@ static void eigh_sym3(int K, const double T[3][3], double* D, double U[3][3]) {
 }
 
 double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, long long n, Lanczos lz, int* numops_out) {
-  Ctx* c = e->ctx; cudaStream_t s = c->stream;
+  heff_prepare(e, site);    // once per bond: the <= 5 H_eff applications below share W and the intermediates
+  return lanczos_core(e->ctx, [&](const cplx* in, cplx* out) { env_product_dev(e, in, site, out, nullptr, true); }, theta0, theta_out, n, lz, numops_out);
+}
+
+double lanczos_core(Ctx* c, const ApplyFn& apply, const cplx* theta0, cplx* theta_out, long long n, Lanczos lz, int* numops_out) {
+  cudaStream_t s = c->stream;
   TN_CHECK(lz.krylovdim >= 1 && lz.krylovdim <= 3, "krylovdim must be 1..3 (the reference uses 3)");
   const int KD = lz.krylovdim;
   cplx* V[3]; for (int j = 0; j < 3; ++j) V[j] = c->scratch[6 + j].get((size_t)n, s);
   cplx* w = c->scratch[9].get((size_t)n, s);
   cplx* tmpv[3]; for (int j = 0; j < 3; ++j) tmpv[j] = c->scratch[10 + j].get((size_t)n, s);
   double T[3][3] = {{0}};
-  heff_prepare(e, site);    // once per bond: the <= 5 H_eff applications below share W and the intermediates
   cplx* ds = c->dscal;   // device scalars: [0..3] dots, [8] norm^2, [16+..] log of alpha/beta per step
   // v1 = theta0 / ||theta0||
   { const cplx* xs[1] = {theta0}; zdots(n, 1, xs, theta0, ds + 8, c->partials, s); zscale_invnorm(n, theta0, ds + 8, V[0], s); }
@@ -523,7 +521,7 @@ double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, lon
   int logn = 0;   // scalars recorded on device: pairs (alpha_i at ds[16+2i], beta_i^2 at ds[17+2i])
   auto expand = [&](int Kc) {
     // w = H V[Kc-1]; alpha = Re<v,w>; w -= sum_j <v_j,w> v_j (twice); beta^2 = <w,w>
-    env_product_dev(e, V[Kc - 1], site, w, nullptr, true);
+    apply(V[Kc - 1], w);
     numops++;
     const cplx* xs[3] = {V[0], V[1], V[2]};
     zdots(n, Kc, xs, w, ds, c->partials, s);

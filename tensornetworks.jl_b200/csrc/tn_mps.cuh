@@ -5,6 +5,7 @@
 #include "tn_common.cuh"
 #include "tn_svd.cuh"
 #include "tn_vec.cuh"
+#include <functional>
 #include <memory>
 
 namespace tn {
@@ -25,7 +26,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   SvdWork svd;
-  Buf scratch[16];
+  Buf scratch[24];           // 0-15: MPS / environment / Lanczos work space (tn_mps.cu); 16-23: projector sums (tn_projsum.cu)
   cplx* dscal = nullptr;     // 64 device scalars
   cplx* hscal = nullptr;     // 64 pinned host scalars
   cplx* partials = nullptr;  // dot-product partial sums
@@ -53,12 +54,30 @@ struct Env {                     // ProjMPS(bra, mpo, ket; rank=2)  or overlap P
   std::vector<Tensor> blocks;    // (chi_bra, w, chi_ket)
   Tensor edge;                   // ones(1,1,1)
   int center; cplx coeff;
+  bool squared = false;          // ProjMPS(V, psi; rank=2, squared=true): product = coeff * phi <phi, A> (projmps.jl:135-143)
+  Tensor phi;                    // conj(project(projV, ...)) of the sites being optimised (tn_projsum.cu)
+};
+
+struct EnvSum {                  // ProjMPSSum (projmpssum.jl:1-4): every member shares the ket MPS
+  Ctx* ctx; std::vector<Env*> projs; int center;
 };
 
 struct Gate { int site, nsites; cplx* dev; };
 struct Gates { Ctx* ctx; int d; std::vector<std::vector<Gate>> rows; };
 
 struct Lanczos { int krylovdim, maxiter; double tol; };
+
+// GEMM descriptor for one (unbatched, unsplit) strided contraction
+inline GemmDesc mk(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int conjA, const cplx* B, Idx2 bk, Idx2 bn, int conjB,
+                   cplx* C, Idx2 cm, Idx2 cn, cplx alpha = cplx{1.0, 0.0}, cplx beta = cplx{0.0, 0.0}) {
+  GemmDesc g{};
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.am = am; g.ak = ak; g.conjA = conjA;
+  g.B = B; g.bk = bk; g.bn = bn; g.conjB = conjB;
+  g.C = C; g.cm = cm; g.cn = cn; g.alpha = alpha; g.beta = beta;
+  g.batch = 1; g.ksplit = 1; g.kchunk = K;
+  return g;
+}
 
 // --- MPS -------------------------------------------------------------------------------------
 Mps* mps_create(Ctx* c, int rank, int d, int N, const long long* dims, const cplx* const* host_sites, int center);
@@ -85,6 +104,12 @@ cplx env_calculate(Env* e);
 
 // --- drivers ------------------------------------------------------------------------------------
 double lanczos_lowest(Env* e, int site, const cplx* theta0, cplx* theta_out, long long n, Lanczos lz, int* numops);
+// the same eigensolver for any linear map out = H(in) on n-element device vectors (launched on c->stream)
+typedef std::function<void(const cplx* in, cplx* out)> ApplyFn;
+double lanczos_core(Ctx* c, const ApplyFn& apply, const cplx* theta0, cplx* theta_out, long long n, Lanczos lz, int* numops);
+cplx read_scalar(Ctx* c, int slot);
+void heff_prepare(Env* e, int site);
+void zconj_inplace(long long n, cplx* x, cudaStream_t s);
 void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, double* energy, long long* maxbond);
 Gates* gates_create(Ctx* c, int d, int nrows, const int* counts, const int* sites, const int* nsites, const cplx* const* host_gates);
 void gates_free(Gates* g);
@@ -92,5 +117,20 @@ void apply_gates(Mps* psi, Gates* g, Trunc tr);
 void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cplx* out_host);
 void inner_oplist(Mps* bra, Mps* ket, int nterms, const int* nops, const int* op_sites, const cplx* ops_host, const cplx* coeffs,
                   cplx* out_host);
+
+// --- projector sums, squared projectors, project(), one-site branch, vmps (tn_projsum.cu) ---------------------------
+Env* env_create_squared(Ctx* c, Mps* V, Mps* psi, cplx coeff, int center);               // ProjMPS(V, psi; rank=2, squared=true)
+void env_project_phi(Env* e, int site, int nsites, cplx* phi);                           // phi = conj(project(...)): projmps.jl:153-185
+void env_product1_dev(Env* e, const cplx* A, int site, cplx* out);                       // product(..., nsites=1), rank-2 branch
+void mps_replacesite1(Mps* m, const cplx* A, int site, bool direction, bool normalize);  // replacesites!, one-site branch: gmps.jl:204-213
+EnvSum* envsum_create(Ctx* c, int n, Env* const* projs, int center);
+void envsum_free(EnvSum* es);
+void envsum_movecenter(EnvSum* es, int idx);
+cplx envsum_calculate(EnvSum* es);
+void envsum_prepare(EnvSum* es, int site, int nsites);
+void envsum_apply(EnvSum* es, const cplx* in, int site, int nsites, cplx* out);          // product(projVs, A, direction, nsites)
+void envsum_project_phi(EnvSum* es, int site, int nsites, cplx* out);                    // conj(project(projVs, ...))
+void dmrg_halfsweep_sum(Mps* psi, EnvSum* es, bool direction, int nsites, Lanczos lz, Trunc tr, double* energy, long long* maxbond);
+void vmps_halfsweep(Mps* psi, EnvSum* es, bool direction, int nsites, Trunc tr, long long* maxbond);
 
 }  // namespace tn

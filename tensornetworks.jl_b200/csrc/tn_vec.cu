@@ -138,6 +138,21 @@ void zaxpy(long long n, cplx alpha, const cplx* x, cplx* y, cudaStream_t s) {
   count_launch(1);
 }
 
+__global__ void __launch_bounds__(256) zaxpy_dev_kernel(long long n, cplx a, const cplx* __restrict__ h, const cplx* __restrict__ x, cplx* __restrict__ y) {
+  const cplx hv = h[0];
+  const double cr = a.x * hv.x - a.y * hv.y, ci = a.x * hv.y + a.y * hv.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    cplx v = x[i], w = y[i];
+    y[i] = make_double2(w.x + cr * v.x - ci * v.y, w.y + cr * v.y + ci * v.x);
+  }
+}
+void zaxpy_dev(long long n, cplx alpha, const cplx* h, const cplx* x, cplx* y, cudaStream_t s) {
+  int blocks = (int)std::min<long long>(148 * 8, (n + 255) / 256);
+  zaxpy_dev_kernel<<<std::max(blocks, 1), 256, 0, s>>>(n, alpha, h, x, y);
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
+
 // ---- gate mix -------------------------------------------------------------------------------
 // Tensor viewed as (l, i1, p1, i2, p2, r) with p1,p2 of extent `inner` (1 for an MPS).  One thread
 // per (l, p1, p2, r) point applies the d^2 x d^2 gate to the d^2 (i1,i2) fibre: reads and writes are

@@ -18,6 +18,8 @@ void zlincomb(long long n, int nx, const cplx* const* x_host_ptrs, const double*
 void zscal(long long n, cplx alpha, cplx* x, cudaStream_t s);
 // y += alpha * x
 void zaxpy(long long n, cplx alpha, const cplx* x, cplx* y, cudaStream_t s);
+// y += alpha * h[0] * x   (h in device memory: a dot product that never visits the host)
+void zaxpy_dev(long long n, cplx alpha, const cplx* h, const cplx* x, cplx* y, cudaStream_t s);
 
 // Two-site gate mix (reference gatelist.jl:149-154):
 //   out(l, o1, [p1], o2, [p2], r) = sum_{i1,i2} G(o1,i1,o2,i2) * in(l, i1, [p1], i2, [p2], r)

@@ -73,6 +73,17 @@ PROTOTYPES = {
     "tn_env_product_dev": [P, P, I32, P, I32],
     "tn_env_calculate": [P, C.POINTER(tn_cplx)],
     "tn_dmrg_sweep": [P, P, I32, tn_lanczos_t, tn_trunc_t, pF64, pI64],
+    "tn_env_create_squared": [P, P, P, tn_cplx, I32, PP],
+    "tn_env_product_n": [P, P, I32, I32, P],
+    "tn_env_project": [P, I32, I32, P],
+    "tn_envsum_create": [P, I32, PP, I32, PP],
+    "tn_envsum_free": [P],
+    "tn_envsum_movecenter": [P, I32],
+    "tn_envsum_calculate": [P, C.POINTER(tn_cplx)],
+    "tn_envsum_product": [P, P, I32, I32, P],
+    "tn_envsum_project": [P, I32, I32, P],
+    "tn_dmrg_sweep_sum": [P, P, I32, I32, tn_lanczos_t, tn_trunc_t, pF64, pI64],
+    "tn_vmps_sweep": [P, P, I32, I32, tn_trunc_t, pI64],
     "tn_eigsolve": [P, P, I32, tn_lanczos_t, pF64, P, pI32],
     "tn_gates_upload": [P, I32, I32, pI32, pI32, pI32, PP, PP],
     "tn_gates_free": [P],

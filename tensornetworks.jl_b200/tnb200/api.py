@@ -180,16 +180,24 @@ class GMPS:
 
 
 class ProjMPS:
-    """ProjMPS(psi, H, psi; rank=2) environment cache: projmps.jl:1-42."""
+    """ProjMPS(bra, [mpo,] ket; rank, squared, coeff, center) environment cache: projmps.jl:1-42.
+    ``squared=True`` (mpo must be None) is the rank-1 projector penalty ProjMPS(V, psi; rank=2, squared=true)
+    that dmrg builds for MPS arguments (dmrg.jl:144-145)."""
 
-    def __init__(self, bra, mpo, ket, coeff=1.0, center=1):
+    def __init__(self, bra, mpo, ket, coeff=1.0, center=1, squared=False):
         self.ctx = ket.ctx
         self.lib = ket.lib
         self.bra, self.mpo, self.ket = bra, mpo, ket
+        self.squared = bool(squared)
         h = C.c_void_p()
         co = complex(coeff)
-        check(self.lib.tn_env_create(self.ctx.h, bra.h, mpo.h if mpo is not None else None, ket.h,
-                                     tn_cplx(co.real, co.imag), int(center), C.byref(h)))
+        if self.squared:
+            if mpo is not None:
+                raise _lib.TNError("a squared projection has no MPO layer")
+            check(self.lib.tn_env_create_squared(self.ctx.h, bra.h, ket.h, tn_cplx(co.real, co.imag), int(center), C.byref(h)))
+        else:
+            check(self.lib.tn_env_create(self.ctx.h, bra.h, mpo.h if mpo is not None else None, ket.h,
+                                         tn_cplx(co.real, co.imag), int(center), C.byref(h)))
         self.h = h
 
     def __del__(self):
@@ -234,14 +242,28 @@ class ProjMPS:
     def product(self, A, direction=False, nsites=2, out=None):
         """H_eff * A for the two sites at the centre: projmps.jl:103-145 (rank-2 branch).
         ``out`` may be a caller-owned (e.g. pinned) complex128 Fortran-ordered buffer."""
-        if nsites != 2:
-            raise _lib.TNError("only the two-site product is on the hot path")
+        if nsites not in (1, 2):
+            raise _lib.TNError("nsites must be 1 or 2")
         A = _f(A)
         if out is None:
             out = np.zeros(A.shape, dtype=np.complex128, order='F')
         elif not (out.dtype == np.complex128 and out.flags.f_contiguous and out.size == A.size):
             raise _lib.TNError("out must be a complex128 Fortran-contiguous array of A's size")
-        check(self.lib.tn_env_product(self.h, _ptr(A), int(bool(direction)), _ptr(out)))
+        if nsites == 2 and not self.squared:
+            check(self.lib.tn_env_product(self.h, _ptr(A), int(bool(direction)), _ptr(out)))
+        else:   # one-site rank-2 branch / squared branch (projmps.jl:135-143)
+            check(self.lib.tn_env_product_n(self.h, _ptr(A), int(bool(direction)), int(nsites), _ptr(out)))
+        return out
+
+    def _local_shape(self, direction, nsites):
+        site = self.center - nsites + 1 if direction else self.center
+        dims = self.ket.dims()
+        return (int(dims[site - 1][0]),) + (self.ket.dim,) * nsites + (int(dims[site + nsites - 2][-1]),)
+
+    def project(self, A=None, direction=False, nsites=2):
+        """project(projV, A, direction, nsites): projmps.jl:153-185 (A is unused, as in the reference)."""
+        out = np.zeros(self._local_shape(direction, nsites), dtype=np.complex128, order='F')
+        check(self.lib.tn_env_project(self.h, int(bool(direction)), int(nsites), _ptr(out)))
         return out
 
     def calculate(self):
@@ -256,6 +278,57 @@ class ProjMPS:
         e, n = C.c_double(), C.c_int32()
         check(self.lib.tn_eigsolve(self.h, _ptr(A0), int(bool(direction)), tn_lanczos_t(krylovdim, maxiter, tol), C.byref(e), _ptr(out), C.byref(n)))
         return e.value, out, n.value
+
+
+class ProjMPSSum:
+    """ProjMPSSum(projVs; center): projmpssum.jl:1-108.  Members must share the ket MPS."""
+
+    def __init__(self, projs, center=1):
+        self.projs = list(projs)
+        if not self.projs:
+            raise _lib.TNError("ProjMPSSum needs at least one projection")
+        self.ctx = self.projs[0].ctx
+        self.lib = self.projs[0].lib
+        self.ket = self.projs[0].ket
+        arr = (C.c_void_p * len(self.projs))(*[p.h.value for p in self.projs])
+        h = C.c_void_p()
+        check(self.lib.tn_envsum_create(self.ctx.h, len(self.projs), arr, int(center), C.byref(h)))
+        self.h = h
+        self.center = int(center)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.tn_envsum_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def __len__(self):
+        return len(self.ket)
+
+    def movecenter(self, idx):
+        check(self.lib.tn_envsum_movecenter(self.h, int(idx)))
+        self.center = int(idx)
+
+    def calculate(self):
+        v = tn_cplx()
+        check(self.lib.tn_envsum_calculate(self.h, C.byref(v)))
+        return complex(v.re, v.im)
+
+    def product(self, A, direction=False, nsites=2):
+        A = _f(A)
+        out = np.zeros(A.shape, dtype=np.complex128, order='F')
+        check(self.lib.tn_envsum_product(self.h, _ptr(A), int(bool(direction)), int(nsites), _ptr(out)))
+        return out
+
+    def project(self, A=None, direction=False, nsites=2):
+        site = self.center - nsites + 1 if direction else self.center
+        dims = self.ket.dims()
+        shape = (int(dims[site - 1][0]),) + (self.ket.dim,) * nsites + (int(dims[site + nsites - 2][-1]),)
+        out = np.zeros(shape, dtype=np.complex128, order='F')
+        check(self.lib.tn_envsum_project(self.h, int(bool(direction)), int(nsites), _ptr(out)))
+        return out
 
 
 class GateList:
@@ -334,19 +407,33 @@ def contract_strided(M, N, K, A, am, ak, conjA, B, bk, bn, conjB, c_elems, cm, c
 # ---------------------------------------------------------------------------------------------
 # drivers
 # ---------------------------------------------------------------------------------------------
-def dmrg(psi, H, nsites=2, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=1000, tol=1e-10, tolgrad=1e-5,
-         numconverges=4, verbose=False, cutoff=1e-12, maxdim=1000, mindim=1, coeff=1.0, history=None):
-    """dmrg(psi, H; kwargs...): algorithms/mps/dmrg.jl:1-154 for one MPO.  The sweep body
-    (:35-63) runs on the device (tn_dmrg_sweep); the convergence logic (:66-89) is host-side."""
+def dmrg(psi, *Hs, coeffs=None, coeff=None, nsites=2, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=1000, tol=1e-10,
+         tolgrad=1e-5, numconverges=4, verbose=False, cutoff=1e-12, maxdim=1000, mindim=1, history=None):
+    """dmrg(psi, Hs::GMPS...; kwargs...): algorithms/mps/dmrg.jl:1-154.  Every rank-2 argument is an MPO term
+    ProjMPS(psi, H, psi; rank=2, coeff), every rank-1 argument a penalty ProjMPS(V, psi; rank=2, squared=true, coeff)
+    (:136-147).  The sweep body (:35-63) runs on the device (tn_dmrg_sweep for one MPO with nsites=2, tn_dmrg_sweep_sum
+    otherwise); the convergence logic (:66-89) is host-side."""
     if psi.rank != 1:
         raise _lib.TNError("Psi must be a GMPS of rank 1 (vector).")
-    if nsites != 2:
-        raise _lib.TNError("only nsites=2 is on the hot path")
-    if len(H) != len(psi) or H.dim != psi.dim or H.rank != 2:
-        raise _lib.TNError("GMPS must share the same properties.")
+    if nsites not in (1, 2):
+        raise _lib.TNError("nsites must be 1 or 2")
+    if len(Hs) == 0:
+        raise _lib.TNError("You must provide atleast one MPS/MPO for the Hamiltonian.")
+    if coeffs is None:
+        coeffs = [1.0 if coeff is None else coeff] * len(Hs)
+    if len(coeffs) != len(Hs):
+        raise _lib.TNError("coeffs must have one entry per Hamiltonian term")
+    for H in Hs:
+        if len(H) != len(psi) or H.dim != psi.dim:
+            raise _lib.TNError("GMPS must share the same properties.")
+        if H.rank not in (1, 2):
+            raise _lib.TNError("Hamiltonian must be composed of MPOs (rank 2) or MPSs (rank 1).")
     lib = psi.lib
     psi.movecenter(1)
-    Hs = ProjMPS(psi, H, psi, coeff=coeff, center=1)
+    projs = [ProjMPS(psi, H, psi, coeff=c, center=1) if H.rank == 2 else ProjMPS(H, None, psi, coeff=c, center=1, squared=True)
+             for H, c in zip(Hs, coeffs)]
+    single = len(projs) == 1 and nsites == 2 and not projs[0].squared
+    Hs = projs[0] if single else ProjMPSSum(projs, center=1)
     cost = Hs.calculate()
     lastcost = cost
     D = psi.maxbonddim()
@@ -359,7 +446,10 @@ def dmrg(psi, H, nsites=2, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=100
     tr = Trunc(cutoff, maxdim, mindim)
     while not converged:
         e, mb = C.c_double(), C.c_int64()
-        check(lib.tn_dmrg_sweep(psi.h, Hs.h, int(direction), lz, tr, C.byref(e), C.byref(mb)))
+        if single:
+            check(lib.tn_dmrg_sweep(psi.h, Hs.h, int(direction), lz, tr, C.byref(e), C.byref(mb)))
+        else:
+            check(lib.tn_dmrg_sweep_sum(psi.h, Hs.h, int(direction), int(nsites), lz, tr, C.byref(e), C.byref(mb)))
         cost = e.value
         direction = not direction
         sweeps += 1
@@ -385,6 +475,61 @@ def dmrg(psi, H, nsites=2, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=100
         if verbose:
             print("Sweep=%d, energy=%.12f, maxbonddim=%d" % (sweeps, np.real(cost), D))
     return psi, cost
+
+
+def vmps(*psis, minsweeps=2, maxsweeps=200, tol=1e-10, numconverges=3, verbose=False, nsites=2, cutoff=1e-12, maxdim=1000,
+         mindim=1, history=None):
+    """vmps(psis::GMPS...; kwargs...): algorithms/mps/vmps.jl:1-105.  psi0 = copy of psis[0] with its centre at site 1,
+    Vs = ProjMPSSum([ProjMPS(psi_k, psi0)]); the sweep body (:36-62) runs on the device (tn_vmps_sweep), the cost
+    norm(psi)^2 - 2|calculate(Vs)| and the convergence counters (:64-83) host-side."""
+    first = psis[0]
+    psi = GMPS(first.rank, first.dim, first.tensors, first.center, first.ctx)
+    if psi.rank != 1:
+        raise _lib.TNError("vmps: rank-1 MPS only")
+    psi.movecenter(1)
+    Vs = ProjMPSSum([ProjMPS(p, None, psi, center=1) for p in psis], center=1)
+    return vmps_sweeps(psi, Vs, minsweeps=minsweeps, maxsweeps=maxsweeps, tol=tol, numconverges=numconverges, verbose=verbose,
+                       nsites=nsites, cutoff=cutoff, maxdim=maxdim, mindim=mindim, history=history)
+
+
+def vmps_sweeps(psi, Vs, minsweeps=2, maxsweeps=200, tol=1e-10, numconverges=3, verbose=False, nsites=2, cutoff=1e-12,
+                maxdim=1000, mindim=1, history=None):
+    """vmps(psi, Vs::AbstractProjMPS; kwargs...): vmps.jl:1-92 for a ProjMPSSum of ProjMPS(psi_k, [H,] psi)."""
+    lib = psi.lib
+    tr = Trunc(cutoff, maxdim, mindim)
+
+    def calculatecost():                      # vmps.jl:16-23
+        return psi.norm() ** 2 - 2 * abs(Vs.calculate())
+
+    def diff(x, y):
+        return abs(x - y) if abs(x) < 1e-10 else abs((x - y) / x)
+    lastcost = calculatecost()
+    lastD = psi.maxbonddim()
+    direction = False
+    converged = False
+    convergedsweeps = sweeps = 0
+    while not converged:
+        mb = C.c_int64()
+        check(lib.tn_vmps_sweep(psi.h, Vs.h, int(direction), int(nsites), tr, C.byref(mb)))
+        Vs.center = 1 if direction else len(psi)
+        direction = not direction
+        sweeps += 1
+        D = mb.value
+        cost = calculatecost()
+        if sweeps >= minsweeps:
+            if diff(cost, lastcost) < tol and lastD == D:
+                convergedsweeps += 1          # never reset: vmps.jl:75 compares instead of assigning
+            if convergedsweeps >= numconverges:
+                converged = True
+            if sweeps >= maxsweeps and maxsweeps != 0:
+                converged = True
+        lastcost = cost
+        lastD = D
+        if history is not None:
+            history.append((sweeps, complex(cost), D))
+        if verbose:
+            print("Sweep=%d, energy=%.12f, maxbonddim=%d" % (sweeps, np.real(cost), D))
+    return psi
 
 
 def applygates(psi, gates, cutoff=0.0, maxdim=0, mindim=1):

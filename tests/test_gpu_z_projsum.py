@@ -1,0 +1,149 @@
+"""GPU parity for the projector branch (SURVEY 8(a) A4/A5 fan-out over ProjMPSSum, 8(f) rank 3): project (with and
+without an MPO layer, one and two sites), the squared rank-1 penalty, products of sums, the one-site rank-2 product,
+excited-state / multi-MPO / one-site DMRG and vmps, all through the C ABI against the oracle.
+Tolerances: contractions 1e-13 relative Frobenius, energies 1e-10 relative, overlaps / costs 1e-8.
+(The file sorts after the other GPU suites on purpose: it was written in a session without GPU time left.)"""
+import numpy as np
+import pytest
+
+import oracle
+from gpu_util import crandn, random_complex_mps, random_mpo, relerr
+from models import tfim, dense_hamiltonian, mps_to_dense
+
+pytestmark = pytest.mark.gpu
+
+
+def _dense(g):
+    ts = g.tensors
+    v = ts[0]
+    for t in ts[1:]:
+        v = np.tensordot(v, t, axes=([v.ndim - 1], [0]))
+    return v.reshape(-1)
+
+
+@pytest.mark.parametrize("N,chiv,chip,w", [(6, 5, 6, 3), (7, 12, 9, 4)])
+def test_project_and_one_site_product(N, chiv, chip, w):
+    import tnb200
+    rng = np.random.default_rng(N + chiv)
+    V = random_complex_mps(rng, N, 2, chiv, center=1)
+    psi = random_complex_mps(rng, N, 2, chip, center=3)
+    H = random_mpo(rng, N, 2, w)
+    gV, gpsi, gH = tnb200.GMPS.from_host(V), tnb200.GMPS.from_host(psi), tnb200.GMPS.from_host(H)
+    for c in (2, 3, N - 1):
+        P = oracle.ProjMPS([V, psi], rank=1, center=c)
+        Q = oracle.ProjMPS([V, H, psi], rank=1, center=c)
+        E = oracle.ProjMPS([psi, H, psi], rank=2, center=c, coeff=0.7 - 0.2j)
+        G = tnb200.ProjMPS(gV, None, gpsi, center=c)
+        GQ = tnb200.ProjMPS(gV, gH, gpsi, center=c)
+        GE = tnb200.ProjMPS(gpsi, gH, gpsi, coeff=0.7 - 0.2j, center=c)
+        for direction in (False, True):
+            assert relerr(G.project(None, direction, 2), P.project(None, direction, 2)) < 1e-13
+            assert relerr(GQ.project(None, direction, 2), Q.project(None, direction, 2)) < 1e-13
+        assert relerr(G.project(None, False, 1), P.project(None, False, 1)) < 1e-13
+        assert relerr(GQ.project(None, False, 1), Q.project(None, False, 1)) < 1e-13
+        A = crandn(rng, *psi[c].shape)
+        assert relerr(GE.product(A, False, 1), E.product(A, False, 1)) < 1e-13
+
+
+def test_squared_projector_and_sum_product():
+    import tnb200
+    rng = np.random.default_rng(21)
+    N = 7
+    V = random_complex_mps(rng, N, 2, 6, center=1)
+    V2 = random_complex_mps(rng, N, 2, 3, center=1)
+    psi = random_complex_mps(rng, N, 2, 8, center=4)
+    Ha, Hb = random_mpo(rng, N, 2, 3), random_mpo(rng, N, 2, 5)
+    gV, gV2, gpsi = tnb200.GMPS.from_host(V), tnb200.GMPS.from_host(V2), tnb200.GMPS.from_host(psi)
+    gHa, gHb = tnb200.GMPS.from_host(Ha), tnb200.GMPS.from_host(Hb)
+    c = 4
+    S = oracle.ProjMPS([V, psi], rank=2, squared=True, coeff=2.5, center=c)
+    GS = tnb200.ProjMPS(gV, None, gpsi, coeff=2.5, center=c, squared=True)
+    for nsites, direction in ((2, False), (2, True), (1, False)):
+        site = c - nsites + 1 if direction else c
+        shape = (psi[site].shape[0],) + (2,) * nsites + (psi[site + nsites - 1].shape[2],)
+        A = crandn(rng, *shape)
+        assert relerr(GS.product(A, direction, nsites), S.product(A, direction, nsites)) < 1e-12
+    assert abs(GS.calculate() - S.calculate()) < 1e-12
+    # sum of two MPO terms and two penalties
+    osum = oracle.ProjMPSSum([oracle.ProjMPS([psi, Ha, psi], rank=2, center=c, coeff=0.3),
+                              oracle.ProjMPS([psi, Hb, psi], rank=2, center=c, coeff=-1.1),
+                              S, oracle.ProjMPS([V2, psi], rank=2, squared=True, coeff=0.4, center=c)], center=c)
+    gsum = tnb200.ProjMPSSum([tnb200.ProjMPS(gpsi, gHa, gpsi, coeff=0.3, center=c), tnb200.ProjMPS(gpsi, gHb, gpsi, coeff=-1.1, center=c),
+                              GS, tnb200.ProjMPS(gV2, None, gpsi, coeff=0.4, center=c, squared=True)], center=c)
+    for nsites in (2, 1):
+        shape = (psi[c].shape[0],) + (2,) * nsites + (psi[c + nsites - 1].shape[2],)
+        A = crandn(rng, *shape)
+        assert relerr(gsum.product(A, False, nsites), osum.product(A, False, nsites)) < 1e-12
+    assert abs(gsum.calculate() - osum.calculate()) < 1e-11 * abs(osum.calculate())
+    gsum.movecenter(2)
+    osum.movecenter(2)
+    A = crandn(rng, psi[2].shape[0], 2, 2, psi[3].shape[2])
+    assert relerr(gsum.product(A, False, 2), osum.product(A, False, 2)) < 1e-12
+
+
+def test_excited_state_dmrg_matches_oracle_and_ed():
+    import tnb200
+    sh = oracle.spinhalf()
+    N = 8
+    H = tfim(N)
+    ev = np.linalg.eigvalsh(dense_hamiltonian(sh, H).toarray())
+    M = oracle.MPO(sh, H)
+    p0 = oracle.randomMPS(2, N, 4, np.random.default_rng(1))
+    p1 = oracle.randomMPS(2, N, 4, np.random.default_rng(2))
+    gM = tnb200.GMPS.from_host(M)
+    g0, E0 = tnb200.dmrg(tnb200.GMPS.from_host(p0), gM, maxdim=32, cutoff=1e-14, maxsweeps=20)
+    assert abs(E0 - ev[0]) < 1e-10 * abs(ev[0])
+    ho, hg = [], []
+    o0, _ = oracle.dmrg(p0.copy(), M, maxdim=32, cutoff=1e-14, maxsweeps=20)
+    oracle.dmrg(p1.copy(), M, o0, coeffs=[1.0, 20.0], maxdim=32, cutoff=1e-14, maxsweeps=30, history=ho)
+    g1, E1 = tnb200.dmrg(tnb200.GMPS.from_host(p1), gM, g0, coeffs=[1.0, 20.0], maxdim=32, cutoff=1e-14, maxsweeps=30, history=hg)
+    assert abs(E1 - ev[1]) < 1e-9 * abs(ev[1])
+    assert abs(E1 - ho[-1][1]) < 1e-10 * abs(ho[-1][1])
+    assert abs(np.vdot(_dense(g0), _dense(g1))) < 1e-7
+
+
+def test_two_mpo_terms_and_one_site_dmrg():
+    import tnb200
+    sh = oracle.spinhalf()
+    N = 8
+    Ha, Hb = oracle.OpList(N), oracle.OpList(N)
+    for i in range(1, N + 1):
+        Ha.add("x", i, 1.0)
+        Ha.add("z", i, 0.05)
+    for i in range(1, N):
+        Hb.add(["z", "z"], [i, i + 1], 1.2)
+    E_ref = np.linalg.eigvalsh(dense_hamiltonian(sh, tfim(N)).toarray())[0]
+    Ma, Mb = oracle.MPO(sh, Ha), oracle.MPO(sh, Hb)
+    p = oracle.randomMPS(2, N, 4, np.random.default_rng(7))
+    g, E = tnb200.dmrg(tnb200.GMPS.from_host(p), tnb200.GMPS.from_host(Ma), tnb200.GMPS.from_host(Mb), maxdim=32, cutoff=1e-14, maxsweeps=20)
+    assert abs(E - E_ref) < 1e-10 * abs(E_ref)
+    # one-site DMRG keeps the bond dimension: same sweeps as the oracle from the same chi = 8 start
+    q = oracle.randomMPS(2, N, 8, np.random.default_rng(8))
+    ho, hg = [], []
+    oracle.dmrg(q.copy(), oracle.MPO(sh, tfim(N)), nsites=1, maxsweeps=6, history=ho)
+    tnb200.dmrg(tnb200.GMPS.from_host(q), tnb200.GMPS.from_host(oracle.MPO(sh, tfim(N))), nsites=1, maxsweeps=6, history=hg)
+    assert len(ho) == len(hg)
+    for a, b in zip(ho, hg):
+        assert a[2] == b[2] and abs(a[1] - b[1]) < 1e-7 * abs(a[1])
+    assert abs(ho[-1][1] - hg[-1][1]) < 1e-10 * abs(ho[-1][1])
+
+
+def test_vmps_matches_oracle():
+    import tnb200
+    rng = np.random.default_rng(12)
+    N = 8
+    a = random_complex_mps(rng, N, 2, 6, center=1)
+    b = random_complex_mps(rng, N, 2, 6, center=1)
+    target = mps_to_dense(a) + mps_to_dense(b)
+    for nsites, maxdim in ((2, 16), (2, 4), (1, 16)):
+        ho, hg = [], []
+        po = oracle.vmps(a, b, nsites=nsites, maxdim=maxdim, cutoff=0.0 if maxdim == 4 else 1e-14, maxsweeps=6, history=ho)
+        pg = tnb200.vmps(tnb200.GMPS.from_host(a), tnb200.GMPS.from_host(b), nsites=nsites, maxdim=maxdim,
+                         cutoff=0.0 if maxdim == 4 else 1e-14, maxsweeps=6, history=hg)
+        assert len(ho) == len(hg)
+        assert abs(hg[-1][1] - ho[-1][1]) < 1e-8 * abs(ho[-1][1])
+        assert hg[-1][2] == ho[-1][2]
+        vo, vg = mps_to_dense(po), _dense(pg)
+        assert abs(abs(np.vdot(vo, vg)) - np.linalg.norm(vo) * np.linalg.norm(vg)) < 1e-8 * np.linalg.norm(vo) ** 2
+        if maxdim == 16 and nsites == 2:
+            assert np.linalg.norm(vg - target) < 1e-9 * np.linalg.norm(target)
