@@ -159,6 +159,24 @@ int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsi
 int32_t tn_eigsolve(tn_env* e, const tn_cplx* theta0_host, int32_t direction, tn_lanczos_t lanczos,
                     double* eig_out, tn_cplx* theta_out_host, int32_t* numops_out);
 
+/* ---- device-pointer entry points: for a caller that orchestrates the bond loop itself and only hands the dense pieces to the
+ * library -- the multi-GPU MPO-bond-sharded DMRG sweep, whose H_eff application contains collectives, or a Julia
+ * caller that keeps KrylovKit-style control with its own linear map. ------------------------------------------------------------ */
+/* device address of psi[site]; valid until that site is next modified (replacesites, movecenter, gates, upload) */
+int32_t tn_mps_site_ptr(tn_mps* m, int32_t site, void** dev_out);
+/* tn_mps_replacesites with the two-site tensor already in device memory */
+int32_t tn_mps_replacesites_dev(tn_mps* m, const void* theta_dev, int32_t site, int32_t direction, int32_t normalize, tn_trunc_t trunc);
+/* psi[site] = x (abstractmps.jl setindex!) from a device buffer */
+int32_t tn_mps_upload_site_dev(tn_mps* m, int32_t site, const int64_t* dims, const void* data_dev);
+/* device-to-device copy ordered on the context's stream (completed on return) */
+int32_t tn_memcpy_dev(tn_ctx* ctx, void* dst_dev, const void* src_dev, int64_t nbytes);
+/* KrylovKit eigsolve(f, x0, 1, :SR; krylovdim, maxiter, tol, ishermitian=true) (dmrg.jl:51-53) for a caller-supplied Hermitian
+ * linear map on n-element complex128 device vectors.  apply(user, in_dev, out_dev) is entered with in_dev complete; all its writes
+ * to out_dev must be complete (or enqueued on the context's stream) when it returns 0.  Non-zero aborts with TN_ERR_INVALID. */
+typedef int32_t (*tn_apply_fn)(void* user, const void* in_dev, void* out_dev);
+int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* theta_out_dev, tn_lanczos_t lanczos,
+                       tn_apply_fn apply, void* user, double* eig_out, int32_t* numops_out);
+
 /* GateList upload: nrows rows; counts[r] gates in row r; per gate (flattened in row order) the first
  * site, the number of sites (1 or 2) and a host pointer to the gate tensor (out1,in1[,out2,in2]),
  * column-major, as produced by trotterize(): gatelist.jl:75-121. */

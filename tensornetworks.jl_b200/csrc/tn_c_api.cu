@@ -445,6 +445,56 @@ int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsi
   });
 }
 
+// ---- device-pointer entry points for callers that orchestrate the sweep themselves (multi-GPU sharded DMRG) -------
+int32_t tn_mps_site_ptr(tn_mps* m, int32_t site, void** dev_out) {
+  return guard([&] {
+    TN_CHECK(m && dev_out, "null pointer");
+    TN_CHECK(site >= 1 && site <= m->m->N, "site index out of range");
+    m->m->ctx->sync();
+    *dev_out = (void*)m->m->sites[site - 1].p;
+  });
+}
+int32_t tn_mps_replacesites_dev(tn_mps* m, const void* theta_dev, int32_t site, int32_t direction, int32_t normalize, tn_trunc_t tr) {
+  return guard([&] {
+    TN_CHECK(m && theta_dev, "null pointer");
+    mps_replacesites2(m->m, (const cplx*)theta_dev, site, direction != 0, normalize != 0, T(tr));
+    m->m->ctx->sync();
+  });
+}
+int32_t tn_mps_upload_site_dev(tn_mps* m, int32_t site, const int64_t* dims, const void* data_dev) {
+  return guard([&] {
+    Mps* p = m->m; Ctx* c = p->ctx;
+    TN_CHECK(site >= 1 && site <= p->N, "site index out of range");
+    std::vector<long long> dd(dims, dims + p->rank + 2);
+    c->alloc(p->sites[site - 1], dd);
+    TN_CUDA(cudaMemcpyAsync(p->sites[site - 1].p, data_dev, (size_t)p->sites[site - 1].size() * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+    c->sync();
+  });
+}
+int32_t tn_memcpy_dev(tn_ctx* ctx, void* dst_dev, const void* src_dev, int64_t nbytes) {
+  return guard([&] {
+    TN_CHECK(ctx && dst_dev && src_dev && nbytes >= 0, "memcpy: bad arguments");
+    TN_CUDA(cudaMemcpyAsync(dst_dev, src_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->c.stream));
+    ctx->c.sync();
+  });
+}
+int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* theta_out_dev, tn_lanczos_t lz, tn_apply_fn apply, void* user,
+                       double* eig, int32_t* numops) {
+  return guard([&] {
+    TN_CHECK(ctx && theta0_dev && theta_out_dev && apply && eig && n >= 1, "eigsolve: bad arguments");
+    Ctx* c = &ctx->c;
+    int ops = 0;
+    double v = lanczos_core(c, [&](const cplx* in, cplx* out) {
+      c->sync();                                   // `in` is complete before the caller's map reads it
+      int32_t st = apply(user, (const void*)in, (void*)out);
+      if (st != 0) throw tn::Error(TN_ERR_INVALID, "eigsolve: the caller's linear map returned status " + std::to_string(st));
+    }, (const cplx*)theta0_dev, (cplx*)theta_out_dev, n, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, &ops);
+    c->sync();
+    *eig = v;
+    if (numops) *numops = ops;
+  });
+}
+
 int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites, const tn_cplx* ops_host,
                         const tn_cplx* coeffs, tn_cplx* out) {
   return guard([&] {

@@ -31,6 +31,8 @@ PP = C.POINTER(C.c_void_p)
 I32, I64, F64, U64 = C.c_int32, C.c_int64, C.c_double, C.c_uint64
 pI32, pI64, pF64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_double)
 
+APPLY_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p)     # tn_apply_fn
+
 # name -> argtypes ; all return int32 status except the two noted
 PROTOTYPES = {
     "tn_ctx_create": [I32, PP],
@@ -85,6 +87,11 @@ PROTOTYPES = {
     "tn_dmrg_sweep_sum": [P, P, I32, I32, tn_lanczos_t, tn_trunc_t, pF64, pI64],
     "tn_vmps_sweep": [P, P, I32, I32, tn_trunc_t, pI64],
     "tn_eigsolve": [P, P, I32, tn_lanczos_t, pF64, P, pI32],
+    "tn_mps_site_ptr": [P, I32, PP],
+    "tn_mps_replacesites_dev": [P, P, I32, I32, I32, tn_trunc_t],
+    "tn_mps_upload_site_dev": [P, I32, pI64, P],
+    "tn_memcpy_dev": [P, P, P, I64],
+    "tn_eigsolve_fn": [P, I64, P, P, tn_lanczos_t, APPLY_FN, P, pF64, pI32],
     "tn_gates_upload": [P, I32, I32, pI32, pI32, pI32, PP, PP],
     "tn_gates_free": [P],
     "tn_apply_gates": [P, P, tn_trunc_t],

@@ -142,3 +142,416 @@ def run_ensemble(run_one, ntraj, rank=0, world=1, dist=None, workers=1):
             merged.update(g)
         results = merged
     return results
+
+
+# ---------------------------------------------------------------------------------------------
+# MPO-bond-sharded environments and DMRG sweep (SURVEY 8(e), row "DMRG matvec at large chi (A5) + environments (A4)")
+#
+# Rank g owns the slice w in chunk(g) of EVERY environment block (chi_bra, w, chi_ket), so a block set that does not
+# fit one GPU (C5: ~390 GB) is spread over the box; the site tensors, Theta, the Lanczos vectors and the truncated SVD
+# are replicated.  chunk(g) = [g*c, min((g+1)*c, w)) with c = ceil(w / G): the equal chunks reduce_scatter needs (the
+# largest chunk -- the critical path -- is the same as for a balanced split).
+#   buildleft  (projmps.jl:50-66):  X1_g = L_g . A  ->  X2p = X1_g . M[w in g]  (partial sums for ALL w')
+#                                    -> reduce_scatter over w' -> L'_g = conj(A) . X2_g
+#   buildright (projmps.jl:74-95):  mirror image with a reduce_scatter over the left MPO bond
+#   product    (projmps.jl:107-134): as ShardedHeff above, blocks taken from the store, all_reduce of the result
+# The bond loop of dmrg.jl:35-63 runs in this process; the dense pieces go through a ``backend``:
+#   GpuBackend -- C ABI (tn_contract_strided_dev, tn_eigsolve_fn, tn_mps_replacesites_dev, ...) + torch.distributed/NCCL.
+# The CPU tests drive the same code with a NumPy stand-in backend over gloo (tests/test_sharded_cpu.py).
+# ---------------------------------------------------------------------------------------------
+def chunk_range(n, rank, world):
+    """Equal-chunk partition of range(n): chunk size ceil(n / world); trailing ranks may be empty."""
+    c = (n + world - 1) // world
+    return min(rank * c, n), min((rank + 1) * c, n)
+
+
+def _i1(stride):
+    return (BIG, int(stride), 0)
+
+
+def _i2(n0, s0, s1):
+    return (int(n0), int(s0), int(s1))
+
+
+class ShardedProjMPS:
+    """ProjMPS(psi, H, psi; rank=2) with every block sharded over the MPO bond (abstractprojmps.jl:33-81 protocol).
+
+    ``psi`` is the backend's MPS handle (replicated), ``mpo_host`` the list of MPO site tensors (w_l, d, d, w_r) as NumPy
+    arrays (tiny, host-side), ``be`` the backend.  Blocks are flat column-major buffers (chi_bra, w_g, chi_ket)."""
+
+    def __init__(self, psi, mpo_host, be, rank=0, world=1, dist=None, center=1, coeff=1.0):
+        self.psi, self.be, self.rank, self.world, self.dist = psi, be, rank, world, dist
+        self.mpo = [np.asarray(m, dtype=np.complex128) for m in mpo_host]
+        self.N = len(self.mpo)
+        self.d = self.mpo[0].shape[1]
+        self.coeff = complex(coeff)
+        self.blocks = [None] * self.N          # per site: (buffer, (chi_bra, w_g, chi_ket)) or None
+        self.center = 0
+        self._mslice = {}
+        self.movecenter(center)
+
+    # ---- helpers -------------------------------------------------------------------------------------------------
+    def _wrange(self, w):
+        return chunk_range(w, self.rank, self.world)
+
+    def _wchunk(self, w):
+        return (w + self.world - 1) // self.world
+
+    def _edge(self):
+        """ones(1,1,1) (abstractprojmps.jl:33-35): rank 0 owns the single MPO-bond value."""
+        wg = 1 if self.rank == 0 else 0
+        buf = self.be.new(max(wg, 1))
+        if wg:
+            self.be.fill_ones(buf, 1)
+        return buf, (1, wg, 1)
+
+    def block(self, idx):
+        if idx < 1 or idx > self.N:
+            return self._edge()
+        b = self.blocks[idx - 1]
+        if b is None:
+            raise _lib.TNError("environment block has not been built")
+        return b
+
+    def _mpo_dev(self, key, arr):
+        """flat device copy of a (sliced) MPO tensor, cached"""
+        if key not in self._mslice:
+            self._mslice[key] = self.be.from_host(np.reshape(arr, -1, order='F'))
+        return self._mslice[key]
+
+    def _reduce_scatter(self, full, chunk_elems):
+        """sum over ranks of ``full`` (world equal chunks, slowest index = the sharded MPO bond); returns this rank's chunk"""
+        if self.world == 1:
+            return full
+        out = self.be.new(chunk_elems)
+        self.be.sync()
+        self.be.reduce_scatter(out, full, self.dist)
+        return out
+
+    # ---- block updates -------------------------------------------------------------------------------------------
+    def buildleft(self, idx):
+        be, d = self.be, self.d
+        Lb, (ca, wg, cb) = self.block(idx - 1)
+        A, adims = be.site(self.psi, idx)
+        ca_, _, cb2 = adims
+        ca2 = cb2                                             # bra == ket
+        M = self.mpo[idx - 1]
+        w, w2 = M.shape[0], M.shape[3]
+        lo, hi = self._wrange(w)
+        assert hi - lo == wg and ca_ == ca == cb, "buildleft: block / site dimension mismatch"
+        c2 = self._wchunk(w2)
+        w2pad = c2 * self.world
+        X2p = be.new(ca * d * cb2 * w2pad)                    # (a, s, b', w'_pad), zero-initialised
+        if wg > 0:
+            # X1[(a,wg),(s',b')] = L_g[(a,wg),b] A[b,(s',b')]
+            X1 = be.new(ca * wg * d * cb2)
+            be.contract(ca * wg, d * cb2, cb, Lb, _i1(1), _i1(ca * wg), 0, A, _i1(1), _i1(cb), 0, X1, _i1(1), _i1(ca * wg))
+            # X2p(a,s,b',w') = sum_{(wg,s')} X1(a,(wg,s'),b') M_g(wg,s,s',w'); rows m = (a,b'), n = (s,w')
+            Mg = self._mpo_dev(("L", idx, lo, hi), M[lo:hi])
+            be.contract(ca * cb2, d * w2, wg * d, X1, _i2(ca, 1, ca * wg * d), _i1(ca), 0,
+                        Mg, _i2(wg, 1, wg * d), _i2(d, wg, wg * d * d), 0,
+                        X2p, _i2(ca, 1, ca * d), _i2(d, ca, ca * d * cb2))
+        X2g = self._reduce_scatter(X2p, ca * d * cb2 * c2)    # (a, s, b', c2); first w2g columns valid
+        lo2, hi2 = self._wrange(w2)
+        w2g = hi2 - lo2
+        out = be.new(max(ca2 * w2g * cb2, 1))
+        if w2g > 0:
+            # L'_g(a',w'g,b') = sum_{(a,s)} conj(A[(a,s),a']) X2g[(a,s),(b',w'g)]
+            be.contract(ca2, cb2 * w2g, ca * d, A, _i1(ca * d), _i1(1), 1, X2g, _i1(1), _i1(ca * d), 0,
+                        out, _i1(1), _i2(cb2, ca2 * w2g, ca2))
+        be.sync()
+        self.blocks[idx - 1] = (out, (ca2, w2g, cb2))
+
+    def buildright(self, idx):
+        be, d = self.be, self.d
+        Rb, (ca, wg, cb) = self.block(idx + 1)
+        A, adims = be.site(self.psi, idx)
+        cbl, _, cb_ = adims
+        cal = cbl
+        M = self.mpo[idx - 1]
+        wl, w = M.shape[0], M.shape[3]
+        lo, hi = self._wrange(w)
+        assert hi - lo == wg and cb_ == cb == ca, "buildright: block / site dimension mismatch"
+        cl = self._wchunk(wl)
+        wlpad = cl * self.world
+        Y2p = be.new(cbl * ca * d * wlpad)                    # (b_l, a, s, w_l_pad)
+        if wg > 0:
+            # Y1(b_l,s',wg,a) = sum_b A[(b_l,s'),b] R_g[(a,wg),b]; n = (a,wg) written transposed
+            Y1 = be.new(cbl * d * wg * ca)
+            be.contract(cbl * d, ca * wg, cb, A, _i1(1), _i1(cbl * d), 0, Rb, _i1(ca * wg), _i1(1), 0,
+                        Y1, _i1(1), _i2(ca, cbl * d * wg, cbl * d))
+            # Y2p(b_l,a,s,w_l) = sum_{(s',wg)} Y1(b_l,(s',wg),a) M_g(w_l,s,s',wg); rows m = (b_l,a), n = (s,w_l)
+            Mg = self._mpo_dev(("R", idx, lo, hi), M[:, :, :, lo:hi])
+            be.contract(cbl * ca, d * wl, d * wg, Y1, _i2(cbl, 1, cbl * d * wg), _i1(cbl), 0,
+                        Mg, _i1(wl * d), _i2(d, wl, 1), 0, Y2p, _i1(1), _i1(cbl * ca))
+        Y2g = self._reduce_scatter(Y2p, cbl * ca * d * cl)    # (b_l, a, s, cl)
+        lol, hil = self._wrange(wl)
+        wlg = hil - lol
+        out = be.new(max(cal * wlg * cbl, 1))
+        if wlg > 0:
+            # R'_g(a_l,wlg,b_l) = sum_{(a,s)} conj(A)(a_l,s,a) Y2g(b_l,(a,s),wlg); k = (a,s) with a fastest
+            be.contract(cal, cbl * wlg, ca * d, A, _i1(1), _i2(ca, cal * d, cal), 1,
+                        Y2g, _i1(cbl), _i2(cbl, 1, cbl * ca * d), 0, out, _i1(1), _i2(cbl, cal * wlg, cal))
+        be.sync()
+        self.blocks[idx - 1] = (out, (cal, wlg, cbl))
+
+    def movecenter(self, idx):                                # abstractprojmps.jl:60-81
+        N = self.N
+        if idx < 1 or idx > N:
+            raise _lib.TNError("The index is out of range.")
+        if self.center == 0:
+            for i in range(1, idx):
+                self.buildleft(i)
+            for i in range(1, N - idx + 1):
+                self.buildright(N + 1 - i)
+        elif idx > self.center:
+            for i in range(1, idx - self.center + 1):
+                self.buildleft(self.center - 1 + i)
+        elif idx < self.center:
+            for i in range(1, self.center - idx + 1):
+                self.buildright(self.center + 1 - i)
+        self.center = idx
+
+    # ---- H_eff application -----------------------------------------------------------------------------------------
+    def prepare(self, site):
+        """per bond: W_g = M1[w in g] . M2 and the work buffers of the two-site product for sites (site, site+1)"""
+        be, d = self.be, self.d
+        d2 = d * d
+        Lb, (ca, wg, cb) = self.block(site - 1)
+        Rb, (ca2, w2g, cb2) = self.block(site + 2)
+        M1, M2 = self.mpo[site - 1], self.mpo[site]
+        w, w2 = M1.shape[0], M2.shape[3]
+        lo, hi = self._wrange(w)
+        c2 = self._wchunk(w2)
+        p = dict(site=site, ca=ca, wg=wg, cb=cb, ca2=ca2, w2g=w2g, cb2=cb2, w2=w2, c2=c2, L=Lb, R=Rb)
+        if wg > 0:
+            p["W"] = be.from_host(np.reshape(dense_w(M1[lo:hi], M2), -1, order='F'))
+            p["T1"] = be.new(ca * wg * d2 * cb2)
+        p["T2p"] = be.new(ca * d2 * cb2 * c2 * self.world)
+        p["out"] = be.new(ca * d2 * ca2)
+        self._prep = p
+
+    def product(self, theta, out):
+        """out = coeff * H_eff . theta for the prepared bond; theta / out are backend buffers (chi, d, d, chi), flat."""
+        be, d2, p = self.be, self.d * self.d, self._prep
+        ca, wg, cb, ca2, w2g, cb2, w2, c2 = (p[k] for k in ("ca", "wg", "cb", "ca2", "w2g", "cb2", "w2", "c2"))
+        if wg > 0:
+            # T1[(a,wg),(s1',s2',b')] = L_g[(a,wg),b] theta[b,(s1',s2',b')]
+            be.contract(ca * wg, d2 * cb2, cb, p["L"], _i1(1), _i1(ca * wg), 0, theta, _i1(1), _i1(cb), 0, p["T1"], _i1(1), _i1(ca * wg))
+            # T2p(a,s1,s2,b',w2) = sum_{(wg,s1',s2')} T1(a,(wg,s1',s2'),b') W_g[(wg,s1',s2'),(s1,s2,w2)]
+            be.contract(ca * cb2, d2 * w2, wg * d2, p["T1"], _i2(ca, 1, ca * wg * d2), _i1(ca), 0, p["W"], _i1(1), _i1(wg * d2), 0,
+                        p["T2p"], _i2(ca, 1, ca * d2), _i2(d2, ca, ca * d2 * cb2))
+        T2g = self._reduce_scatter(p["T2p"], ca * d2 * cb2 * c2)
+        res = p["out"]
+        if w2g > 0:
+            # out_p[(a,s1,s2),a'] = coeff * sum_{(b',w2g)} T2g[(a,s1,s2),(b',w2g)] R_g(a',w2g,b')
+            be.contract(ca * d2, ca2, cb2 * w2g, T2g, _i1(1), _i1(ca * d2), 0, p["R"], _i2(cb2, ca2 * w2g, ca2), _i1(1), 0,
+                        res, _i1(1), _i1(ca * d2), alpha=self.coeff)
+        else:
+            be.zero(res)
+        be.sync()
+        if self.world > 1:
+            be.all_reduce(res, self.dist)
+        be.copy(out, res, ca * d2 * ca2)
+
+    def calculate(self):
+        """<psi|H|psi> at the centre (projmps.jl:192-216): left block extended over the centre site, closed with the right block."""
+        site = self.center
+        saved = self.blocks[site - 1]
+        self.blocks[site - 1] = None
+        self.buildleft(site)
+        tmp, tdims = self.blocks[site - 1]
+        self.blocks[site - 1] = saved
+        Rb, rdims = self.block(site + 1)
+        assert tdims == rdims
+        n = tdims[0] * tdims[1] * tdims[2]
+        v = self.be.dotu(tmp, Rb, n) if n > 0 else 0.0
+        if self.world > 1:
+            v = self.be.all_reduce_scalar(v, self.dist)
+        return self.coeff * v
+
+
+def sharded_dmrg(psi, mpo_host, be, rank=0, world=1, dist=None, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=1000, tol=1e-10,
+                 tolgrad=1e-5, numconverges=4, verbose=False, cutoff=1e-12, maxdim=1000, mindim=1, coeff=1.0, history=None):
+    """dmrg(psi, H; nsites=2, kwargs...) (algorithms/mps/dmrg.jl:1-154) with the environments and the H_eff application
+    sharded over the MPO bond on ``world`` ranks.  Every rank runs this function with the same arguments and ends with the
+    same psi: after each bond the two new site tensors of rank 0 are broadcast, so rounding differences between the
+    replicated SVDs cannot make the replicas drift apart."""
+    N = be.length(psi)
+    be.movecenter(psi, 1)
+    Hs = ShardedProjMPS(psi, mpo_host, be, rank, world, dist, center=1, coeff=coeff)
+    cost = Hs.calculate()
+    lastcost = cost
+    lastD = D = be.maxbonddim(psi)
+    grad = 0.0
+    direction = False
+    converged = False
+    convergedsweeps = convergedgrad = sweeps = 0
+    d = Hs.d
+    while not converged:
+        for j in range(1, N):
+            site = N + 1 - j if direction else j
+            site1 = site - 1 if direction else site
+            Hs.movecenter(site)
+            A, (cl, _, cm) = be.site(psi, site1)
+            B, (_, _, cr) = be.site(psi, site1 + 1)
+            n = cl * d * d * cr
+            th0, th1 = be.new(n), be.new(n)
+            be.contract(cl * d, d * cr, cm, A, _i1(1), _i1(cl * d), 0, B, _i1(1), _i1(cm), 0, th0, _i1(1), _i1(cl * d))
+            Hs.prepare(site1)
+            cost = be.eigsolve(Hs.product, th0, th1, n, krylovdim, kryloviter, 1e-14)
+            be.replacesites(psi, th1, site1, direction, True, cutoff, maxdim, mindim)
+            if world > 1:
+                be.broadcast_site(psi, site1, dist)
+                be.broadcast_site(psi, site1 + 1, dist)
+        Hs.movecenter(1 if direction else N)
+        direction = not direction
+        sweeps += 1
+        D = be.maxbonddim(psi)
+
+        def diff(x, y):
+            return abs(x - y) if abs(x) < 1e-10 else abs((x - y) / x)
+        if sweeps >= minsweeps:
+            dd = diff(cost, lastcost)
+            convergedsweeps = convergedsweeps + 1 if (dd < tol and lastD == D) else 0
+            with np.errstate(divide='ignore', invalid='ignore'):
+                g = abs(np.float64(dd - grad) / np.float64(dd + grad))
+            convergedgrad = convergedgrad + 1 if (g < tolgrad and lastD == D) else 0
+            if max(convergedsweeps, convergedgrad) >= numconverges:
+                converged = True
+            if sweeps >= maxsweeps and maxsweeps != 0:
+                converged = True
+        grad = abs(diff(cost, lastcost))
+        lastcost = cost
+        lastD = D
+        if history is not None:
+            history.append((sweeps, float(np.real(cost)), D))
+        if verbose and rank == 0:
+            print("Sweep=%d, energy=%.12f, maxbonddim=%d" % (sweeps, np.real(cost), D))
+    return psi, cost
+
+
+class _Raw:
+    """library-owned device memory seen through the backend's buffer protocol (data_ptr only)"""
+
+    def __init__(self, ptr):
+        self.ptr = int(ptr)
+
+    def data_ptr(self):
+        return self.ptr
+
+
+class GpuBackend:
+    """Dense pieces of the sharded sweep on one GPU: contractions, Lanczos, truncated SVD through the C ABI; buffers are flat
+    torch complex128 CUDA tensors (or library memory wrapped in _Raw); collectives through torch.distributed (NCCL)."""
+
+    def __init__(self, ctx, device):
+        import torch
+        self.torch, self.ctx, self.lib, self.device = torch, ctx, ctx.lib, device
+
+    # buffers.  torch fills / copies run on torch's stream, the library on its own non-blocking stream: every torch-side
+    # write is completed (device synchronize) before the buffer is handed to the library.
+    def new(self, n):
+        b = self.torch.zeros(max(int(n), 1), dtype=self.torch.complex128, device=self.device)
+        self.torch.cuda.synchronize()
+        return b
+
+    def from_host(self, flat):
+        b = self.torch.from_numpy(np.ascontiguousarray(flat, dtype=np.complex128)).to(self.device)
+        self.torch.cuda.synchronize()
+        return b
+
+    def fill_ones(self, buf, n):
+        buf[:n] = 1.0
+        self.torch.cuda.synchronize()
+
+    def zero(self, buf):
+        buf.zero_()
+        self.torch.cuda.synchronize()
+
+    def copy(self, dst, src, n):
+        self.torch.cuda.synchronize()
+        check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(dst.data_ptr()), C.c_void_p(src.data_ptr()), int(n) * 16))
+
+    def sync(self):
+        self.ctx.sync()
+        self.torch.cuda.synchronize()
+
+    def dotu(self, a, b, n):
+        self.sync()
+        return complex(self.torch.sum(a[:n] * b[:n]).item())
+
+    # dense kernels
+    def contract(self, M, N, K, A, am, ak, conjA, B, bk, bn, conjB, Cc, cm, cn, alpha=1.0, beta=0.0):
+        al = complex(alpha)
+        check(self.lib.tn_contract_strided_dev(self.ctx.h, M, N, K, C.c_void_p(A.data_ptr()), tn_idx2_t(*am), tn_idx2_t(*ak), int(conjA),
+                                               C.c_void_p(B.data_ptr()), tn_idx2_t(*bk), tn_idx2_t(*bn), int(conjB),
+                                               C.c_void_p(Cc.data_ptr()), tn_idx2_t(*cm), tn_idx2_t(*cn), tn_cplx(al.real, al.imag),
+                                               tn_cplx(float(beta), 0.0)))
+
+    def eigsolve(self, apply, th0, th1, n, krylovdim, maxiter, tol):
+        from ._lib import tn_lanczos_t, APPLY_FN
+        err = []
+
+        def cb(_user, pin, pout):
+            try:
+                apply(_Raw(pin), _Raw(pout))
+                return 0
+            except Exception as e:          # never unwind through the C frames
+                err.append(e)
+                return 1
+        e, nops = C.c_double(), C.c_int32()
+        self.sync()
+        st = self.lib.tn_eigsolve_fn(self.ctx.h, int(n), C.c_void_p(th0.data_ptr()), C.c_void_p(th1.data_ptr()),
+                                     tn_lanczos_t(krylovdim, maxiter, tol), APPLY_FN(cb), None, C.byref(e), C.byref(nops))
+        if err:
+            raise err[0]
+        check(st)
+        return e.value
+
+    # MPS handle (tnb200.GMPS)
+    def length(self, psi):
+        return len(psi)
+
+    def movecenter(self, psi, idx):
+        psi.movecenter(idx)
+
+    def maxbonddim(self, psi):
+        return psi.maxbonddim()
+
+    def site(self, psi, i):
+        p = C.c_void_p()
+        check(self.lib.tn_mps_site_ptr(psi.h, int(i), C.byref(p)))
+        return _Raw(p.value), tuple(int(x) for x in psi.dims()[i - 1])
+
+    def replacesites(self, psi, theta, site, direction, normalize, cutoff, maxdim, mindim):
+        from ._lib import tn_trunc_t
+        self.sync()
+        check(self.lib.tn_mps_replacesites_dev(psi.h, C.c_void_p(theta.data_ptr()), int(site), int(bool(direction)), int(bool(normalize)),
+                                               tn_trunc_t(float(cutoff), int(maxdim), int(mindim))))
+
+    # collectives
+    def reduce_scatter(self, out, full, dist):
+        t = self.torch
+        dist.reduce_scatter_tensor(t.view_as_real(out), t.view_as_real(full), op=dist.ReduceOp.SUM)
+        t.cuda.synchronize()
+
+    def all_reduce(self, buf, dist):
+        t = self.torch
+        dist.all_reduce(t.view_as_real(buf), op=dist.ReduceOp.SUM)
+        t.cuda.synchronize()
+
+    def all_reduce_scalar(self, v, dist):
+        t = self.torch
+        x = t.tensor([complex(v).real, complex(v).imag], dtype=t.float64, device=self.device)
+        dist.all_reduce(x, op=dist.ReduceOp.SUM)
+        return complex(x[0].item(), x[1].item())
+
+    def broadcast_site(self, psi, i, dist):
+        raw, dims = self.site(psi, i)
+        n = int(np.prod(dims))
+        buf = self.new(n)
+        check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(buf.data_ptr()), C.c_void_p(raw.data_ptr()), n * 16))
+        dist.broadcast(self.torch.view_as_real(buf), src=0)
+        self.torch.cuda.synchronize()
+        check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(raw.data_ptr()), C.c_void_p(buf.data_ptr()), n * 16))

@@ -147,3 +147,56 @@ def test_vmps_matches_oracle():
         assert abs(abs(np.vdot(vo, vg)) - np.linalg.norm(vo) * np.linalg.norm(vg)) < 1e-8 * np.linalg.norm(vo) ** 2
         if maxdim == 16 and nsites == 2:
             assert np.linalg.norm(vg - target) < 1e-9 * np.linalg.norm(target)
+
+
+def test_eigsolve_with_caller_map_matches_fused_eigsolve():
+    """tn_eigsolve_fn (caller-supplied linear map on device vectors) with the map = tn_env_product_dev reproduces tn_eigsolve."""
+    import ctypes as C
+    import torch
+    import tnb200
+    from tnb200 import _lib
+    sh = oracle.spinhalf()
+    H = oracle.MPO(sh, tfim(8))
+    psi = random_complex_mps(np.random.default_rng(3), 8, 2, 8, center=4)
+    gpsi, gH = tnb200.GMPS.from_host(psi), tnb200.GMPS.from_host(H)
+    G = tnb200.ProjMPS(gpsi, gH, gpsi, center=4)
+    A0 = np.tensordot(psi[4], psi[5], axes=([2], [0]))
+    e_ref, v_ref, nops_ref = G.eigsolve(A0, False)
+    ctx = tnb200.Context.default()
+    lib = ctx.lib
+    th0 = torch.from_numpy(np.reshape(A0, -1, order='F').copy()).cuda()
+    th1 = torch.zeros_like(th0)
+    torch.cuda.synchronize()
+    calls = []
+
+    def cb(_u, pin, pout):
+        calls.append(1)
+        return lib.tn_env_product_dev(G.h, C.c_void_p(pin), 0, C.c_void_p(pout), 1)
+    e, nops = C.c_double(), C.c_int32()
+    _lib.check(lib.tn_eigsolve_fn(ctx.h, th0.numel(), C.c_void_p(th0.data_ptr()), C.c_void_p(th1.data_ptr()),
+                                  _lib.tn_lanczos_t(3, 2, 1e-14), _lib.APPLY_FN(cb), None, C.byref(e), C.byref(nops)))
+    assert nops.value == nops_ref == len(calls)
+    assert abs(e.value - e_ref) < 1e-12 * abs(e_ref)
+    v = th1.cpu().numpy().reshape(A0.shape, order='F')
+    assert abs(abs(np.vdot(v, v_ref)) - 1.0) < 1e-10
+
+
+def test_sharded_dmrg_world1_matches_unsharded():
+    """The sharded sweep's GPU backend (tn_contract_strided_dev, tn_eigsolve_fn, tn_mps_site_ptr, tn_mps_replacesites_dev) at
+    world size 1 against the fused single-GPU sweep and the oracle."""
+    import tnb200
+    from tnb200.sharded import GpuBackend, sharded_dmrg
+    from models import xxz
+    sh = oracle.spinhalf()
+    N = 10
+    M = oracle.MPO(sh, xxz(N, 1.0))
+    p0 = oracle.randomMPS(2, N, 4, np.random.default_rng(1))
+    ho, hg, hs = [], [], []
+    oracle.dmrg(p0.copy(), M, maxdim=24, maxsweeps=4, history=ho)
+    tnb200.dmrg(tnb200.GMPS.from_host(p0), tnb200.GMPS.from_host(M), maxdim=24, maxsweeps=4, history=hg)
+    ctx = tnb200.Context.default()
+    sharded_dmrg(tnb200.GMPS.from_host(p0), [M[i] for i in range(1, N + 1)], GpuBackend(ctx, "cuda"), maxdim=24, maxsweeps=4, history=hs)
+    assert len(ho) == len(hs) == len(hg)
+    for a, b, c in zip(ho, hs, hg):
+        assert a[2] == b[2] == c[2]
+        assert abs(a[1] - b[1]) < 1e-10 * abs(a[1]) and abs(c[1] - b[1]) < 1e-10 * abs(a[1])
