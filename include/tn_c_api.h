@@ -70,6 +70,10 @@ int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta_host, int32_t site, 
 int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op_host /* d x d */);   /* mps.jl:141-152 */
 /* singular values across bond (site, site+1) -- the SVD inside entropy(): gmps.jl:184-189 */
 int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out);
+/* Bond compression of an assembled MPO (or any GMPS): the two truncated-SVD sweeps at the end of MPO(st, H), mpo.jl:443-457
+ * (and addMPOs, mpo.jl:296-311) -- right-going O[i] = U S, O[i+1] = V^H O[i+1]; left-going O[i] = S V^H, O[i-1] = O[i-1] U.
+ * The reference's default there is cutoff = 1e-15.  Leaves the centre unset. */
+int32_t tn_mpo_compress(tn_mps* m, tn_trunc_t trunc);
 /* <psi| O_k |psi> for single-site operators: mps.jl:87-134 (one-site terms), qjmc.jl:170-220 */
 int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_cplx* ops_host, tn_cplx* out);
 

@@ -108,7 +108,8 @@ void mps_normalize(Mps* m) {   // gmps.jl:46-51
 }
 
 // gauge move to the right (gmps.jl:75-82): psi[i] = U, psi[i+1] = (S V^H) psi[i+1]
-static void moveright(Mps* m, int i, Trunc tr) {
+// (s_stays: the MPO compression sweep of mpo.jl:443-449 keeps S on the site instead: O[i] = U S, O[i+1] = V^H O[i+1])
+static void moveright(Mps* m, int i, Trunc tr, bool s_stays = false) {
   if (!(0 < i && i < m->N)) return;
   Ctx* c = m->ctx; cudaStream_t s = c->stream;
   Tensor& A = m->sites[i - 1]; Tensor& Bn = m->sites[i];
@@ -116,9 +117,9 @@ static void moveright(Mps* m, int i, Trunc tr) {
   int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s); c->svds++;
   Tensor U; std::vector<long long> du = A.dims; du.back() = k;
   c->alloc(U, du);
-  svd_gather_U(c->svd, U.p, rows, false, s);
+  svd_gather_U(c->svd, U.p, rows, s_stays, s);
   cplx* SV = c->scratch[0].get((size_t)k * cols, s);
-  svd_gather_Vh(c->svd, SV, k, true, s);
+  svd_gather_Vh(c->svd, SV, k, !s_stays, s);
   long long tail = Bn.size() / Bn.dims.front();
   Tensor Nn; std::vector<long long> dn = Bn.dims; dn.front() = k;
   c->alloc(Nn, dn);
@@ -127,7 +128,8 @@ static void moveright(Mps* m, int i, Trunc tr) {
   m->sites[i - 1] = U; m->sites[i] = Nn;
 }
 // gauge move to the left (gmps.jl:60-67): psi[i] = V^H reshaped, psi[i-1] = psi[i-1] (U S)
-static void moveleft(Mps* m, int i, Trunc tr) {
+// (s_stays: mpo.jl:451-457 keeps S on the site: O[i] = S V^H, O[i-1] = O[i-1] U)
+static void moveleft(Mps* m, int i, Trunc tr, bool s_stays = false) {
   if (!(1 < i && i <= m->N)) return;
   Ctx* c = m->ctx; cudaStream_t s = c->stream;
   Tensor& A = m->sites[i - 1]; Tensor& Pv = m->sites[i - 2];
@@ -135,9 +137,9 @@ static void moveleft(Mps* m, int i, Trunc tr) {
   int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s); c->svds++;
   Tensor V; std::vector<long long> dv = A.dims; dv.front() = k;
   c->alloc(V, dv);
-  svd_gather_Vh(c->svd, V.p, k, false, s);
+  svd_gather_Vh(c->svd, V.p, k, s_stays, s);
   cplx* US = c->scratch[0].get((size_t)rows * k, s);
-  svd_gather_U(c->svd, US, rows, true, s);
+  svd_gather_U(c->svd, US, rows, !s_stays, s);
   long long head = Pv.size() / Pv.dims.back();
   Tensor Nn; std::vector<long long> dn = Pv.dims; dn.back() = k;
   c->alloc(Nn, dn);
@@ -157,6 +159,14 @@ void mps_movecenter(Mps* m, int idx, Trunc tr) {   // gmps.jl:90-112
     for (int i = 1; i <= m->center - idx; ++i) moveleft(m, m->center + 1 - i, tr);
   }
   m->center = idx;
+}
+
+// Bond compression of a freshly assembled MPO, mpo.jl:443-457 (also addMPOs, mpo.jl:296-311): a right-going then a left-going
+// sweep of truncated SVDs in which the singular values stay on the site that was factorised.
+void mpo_compress(Mps* m, Trunc tr) {
+  for (int i = 1; i <= m->N - 1; ++i) moveright(m, i, tr, true);
+  for (int i = m->N; i >= 2; --i) moveleft(m, i, tr, true);
+  m->center = 0;
 }
 
 // Split a two-site tensor theta (chi_l, p, p, chi_r), p = d^rank, back into two sites (gmps.jl:215-266).

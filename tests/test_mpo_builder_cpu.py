@@ -1,0 +1,67 @@
+"""Host half of the product's MPO(st, H) (tnb200/mpo.py): the finite-state-machine assembly reproduces the dense Hamiltonian
+for on-site, nearest-neighbour and long-range (cylinder) operator lists; and the reference's compression sweeps
+(mpo.jl:443-457, emulated here with the oracle's svd) bring it to the same bond dimensions as the oracle's MPO(st, H)."""
+import numpy as np
+import pytest
+
+import oracle
+from models import tfim, xxz, j1j2_cylinder, dense_hamiltonian
+
+
+def _terms(sh, H):
+    return [([sh.op(o) for o in ops], sites, c) for ops, sites, c in zip(H.ops, H.sites, H.coeffs)]
+
+
+def _dense(Ts):
+    t = Ts[0]
+    for x in Ts[1:]:
+        t = np.tensordot(t, x, axes=([t.ndim - 1], [0]))
+    t = t[0, ..., 0]
+    N = len(Ts)
+    return np.transpose(t, list(range(0, 2 * N, 2)) + list(range(1, 2 * N, 2))).reshape(2 ** N, 2 ** N)
+
+
+@pytest.mark.parametrize("name,H", [("tfim", tfim(6)), ("tfim2", tfim(2)), ("xxz", xxz(6, 0.5)), ("j1j2", j1j2_cylinder(2, 3)),
+                                    ("j1j2_3x3", j1j2_cylinder(3, 3))])
+def test_fsm_assembly_matches_dense(name, H):
+    from tnb200.mpo import fsm_tensors
+    sh = oracle.spinhalf()
+    Ts = fsm_tensors(len(H), 2, _terms(sh, H))
+    assert Ts[0].shape[0] == 1 and Ts[-1].shape[3] == 1
+    assert np.allclose(_dense(Ts), dense_hamiltonian(sh, H).toarray(), atol=1e-12)
+
+
+def test_unsorted_sites_and_complex_coefficients():
+    from tnb200.mpo import fsm_tensors
+    sh = oracle.spinhalf()
+    X, Y, Z = sh.op("x"), sh.op("y"), sh.op("z")
+    terms = [([Z, X], [4, 1], 0.3 - 0.2j), ([Y], [2], 1.5), ([X, Y, Z], [2, 3, 5], -0.7j)]
+    Ts = fsm_tensors(5, 2, terms)
+    I = np.eye(2)
+
+    def kron(*ms):
+        out = np.eye(1)
+        for m in ms:
+            out = np.kron(out, m)
+        return out
+    want = (0.3 - 0.2j) * kron(X, I, I, Z, I) + 1.5 * kron(I, Y, I, I, I) - 0.7j * kron(I, X, Y, I, Z)
+    assert np.allclose(_dense(Ts), want, atol=1e-13)
+
+
+def test_compression_sweeps_reach_the_oracle_bond_dimensions():
+    from tnb200.mpo import fsm_tensors
+    sh = oracle.spinhalf()
+    H = j1j2_cylinder(4, 3)
+    O = [t.copy() for t in fsm_tensors(len(H), 2, _terms(sh, H))]
+    N = len(O)
+    for i in range(N - 1):                      # mpo.jl:443-449
+        U, S, V = oracle.svd(O[i], 4, cutoff=1e-15)
+        O[i] = np.tensordot(U, S, axes=([3], [0]))
+        O[i + 1] = np.tensordot(V, O[i + 1], axes=([1], [0]))
+    for i in range(N - 1, 0, -1):               # mpo.jl:451-457
+        U, S, V = oracle.svd(O[i], 1, cutoff=1e-15)
+        O[i] = np.tensordot(S, U, axes=([1], [0]))
+        O[i - 1] = np.tensordot(O[i - 1], V, axes=([3], [1]))
+    ref = oracle.MPO(sh, H)
+    assert [t.shape[3] for t in O] == [ref[i].shape[3] for i in range(1, N + 1)]
+    assert np.allclose(_dense(O), dense_hamiltonian(sh, H).toarray(), atol=1e-10)
