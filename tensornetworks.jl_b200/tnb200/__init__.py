@@ -8,4 +8,4 @@ calls; only scalars, observables and explicitly downloaded tensors cross PCIe.""
 from ._lib import TNError, load, LIB_PATH  # noqa: F401
 from .api import (Context, GMPS, ProjMPS, ProjMPSSum, GateList, svd, contract_strided, dmrg, vmps, vmps_sweeps, tebd,  # noqa: F401
                   applygates, qjmc_simulation, qjmc_ensemble, inner, Trunc)
-from . import models  # noqa: F401
+from . import models, mpo, evolve, sharded  # noqa: F401

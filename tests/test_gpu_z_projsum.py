@@ -226,3 +226,32 @@ def test_mpo_builder_with_device_compression(name):
     p0 = oracle.randomMPS(2, N, 4, np.random.default_rng(1234))
     _, E = tnb200.dmrg(tnb200.GMPS.from_host(p0), g, maxdim=64, cutoff=1e-14, maxsweeps=30)
     assert abs((E - KAT[key]) / KAT[key]) < 1e-10
+
+
+def test_tebd_front_end_matches_oracle():
+    """tnb200.evolve.tebd (tebd.jl:3-100: trotterize on the host, gates / norm / energy on the device) against oracle.tebd."""
+    import tnb200
+    from tnb200.evolve import tebd
+    sh = oracle.spinhalf()
+    N = 8
+    H = -1 * tfim(N, 1.0, 0.0, 1.0)
+    terms = [([sh.op(o) for o in ops], sites, c) for ops, sites, c in zip(H.ops, H.sites, H.coeffs)]
+    p0 = oracle.randomMPS(2, N, 4, np.random.default_rng(5))
+
+    class Obs:
+        def __init__(self):
+            self.rec = []
+
+        def measure(self, time, psi, norm, energy):
+            self.rec.append((time, norm, energy, psi.maxbonddim()))
+
+        def checkdone(self):
+            return False
+    oo, og = Obs(), Obs()
+    _, Eo = oracle.tebd(sh, p0.copy(), H, 0.02, 0.4, 0.1, observers=[oo], cutoff=1e-12, maxdim=16)
+    _, Eg = tebd(tnb200.GMPS.from_host(p0), terms, 0.02, 0.4, 0.1, observers=[og], cutoff=1e-12, maxdim=16)
+    assert len(oo.rec) == len(og.rec) == 5
+    for a, b in zip(oo.rec, og.rec):
+        assert a[0] == b[0] and abs(a[3] - b[3]) <= 1      # a singular value at the 1e-12 cutoff edge may fall either side
+        assert abs(a[1] - b[1]) < 1e-9 * max(1.0, abs(a[1])) and abs(a[2] - b[2]) < 1e-9 * abs(a[2])
+    assert abs(Eo - Eg) < 1e-9 * abs(Eo)

@@ -65,3 +65,27 @@ def test_compression_sweeps_reach_the_oracle_bond_dimensions():
     ref = oracle.MPO(sh, H)
     assert [t.shape[3] for t in O] == [ref[i].shape[3] for i in range(1, N + 1)]
     assert np.allclose(_dense(O), dense_hamiltonian(sh, H).toarray(), atol=1e-10)
+
+
+def test_product_trotterize_equals_oracle_trotterize():
+    """tnb200.evolve.trotterize (host half of the tebd front-end) against the oracle's gatelist.jl:75-121 restatement."""
+    from tnb200.evolve import trotterize
+    sh = oracle.spinhalf()
+    site_dep = oracle.OpList(6)
+    for i in range(1, 7):
+        site_dep.add("x", i, 0.3 * i)
+    for i in range(1, 6):
+        site_dep.add(["z", "z"], [i, i + 1], 1.0 + 0.1 * i)
+        site_dep.add(["x", "y"], [i, i + 1], 0.2j)
+    onsite_only = oracle.OpList(5)
+    for i in range(1, 6):
+        onsite_only.add("x", i, 0.3 * i)
+    for H in (-1 * tfim(7), -1 * xxz(6, 0.5), site_dep, onsite_only):
+        for evol in ("imag", "real"):
+            for order in (1, 2):
+                gl = oracle.trotterize(sh, H, 0.01, order=order, evol=evol)
+                rs, rg = trotterize(len(H), 2, _terms(sh, H), 0.01, order=order, evol=evol)
+                assert rs == gl.sites
+                for ra, rb in zip(rg, gl.gates):
+                    for a, b in zip(ra, rb):
+                        assert a.shape == b.shape and np.abs(a - b).max() < 1e-14
