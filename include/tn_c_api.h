@@ -190,16 +190,18 @@ int32_t tn_gates_free(tn_gates* g);
 /* applygates!(psi, gates; cutoff, maxdim, mindim): gatelist.jl:191-227 (MPS rank 1 or MPO rank 2) */
 int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc);
 
-/* One QJMC trajectory, algorithms/mps/qjmc.jl:59-164 (classical=true branch): per step applygates!,
- * normalize!, emission rates (single-site jump operators jump_ops[k] d x d at jump_sites[k], rates scaled by
- * jump_coeffs[k]^2), jump test and jump update.  uniforms: 3 per step (host) or NULL for the built-in
- * counter-based generator keyed by (seed, trajectory, step).  Observables: <obs_op> on every site is
+/* One QJMC trajectory, algorithms/mps/qjmc.jl:59-164: per step applygates!, normalize!, emission rates (single-site jump
+ * operators jump_ops[k] d x d at jump_sites[k], rates scaled by jump_coeffs[k]^2), jump test and jump update.
+ * classical != 0 (the reference's default, :88-112): jump when u1 > exp(-sum(rates) dt), channel from u2.
+ * classical == 0 (:65-87): jump when u0 > norm(psi)^2 after the non-unitary gates, channel from u1.
+ * uniforms: 3 per step, indexed [3*step + slot] (host) or NULL for the built-in
+ * counter-based generator keyed by (seed, trajectory, step, slot).  Observables: <obs_op> on every site is
  * written to obs_out[(step/save_every - 1) * N + i] every save_every steps (obs_op may be NULL).
  * jumps_out / jumptimes_out: up to jump_cap records (1-based channel index, time). */
 int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
                     const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t trunc, const double* uniforms,
                     uint64_t seed, uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out,
-                    int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out);
+                    int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out, int32_t classical);
 
 /* inner(st, psi, oplist, phi): mps.jl:87-134.  out[t] = coeffs[t] * <psi| O_t |phi> for nterms operator strings
  * O_t = product of nops[t] single-site operators; op_sites (1-based, strictly ascending inside a term) and ops_host
@@ -223,7 +225,7 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
                          const tn_cplx* const* gate_ptrs, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
                          const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t trunc, uint64_t seed,
                          const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* njumps_out,
-                         int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap);
+                         int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t classical);
 
 #ifdef __cplusplus
 }

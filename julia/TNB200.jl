@@ -136,15 +136,15 @@ movecenter!(psi::CuGMPS, idx::Int; cutoff=0.0, maxdim=0, mindim=1) =
 # library's counter-based generator keyed by (seed, trajectory, step).
 function qjmc_run!(psi::CuGMPS, gates::CuGateList, jumpsites::Vector{Int32}, jumpops::Array{ComplexF64,3}, coeffs::Vector{Float64},
                    steps::Int, dt::Float64; cutoff=1e-12, maxdim=0, mindim=1, uniforms=nothing, seed=0, trajectory=0,
-                   obsop=nothing, save_every=1)
+                   obsop=nothing, save_every=1, classical=true)
     nsave = obsop === nothing ? 0 : steps ÷ save_every
     obs = zeros(ComplexF64, psi.N, max(nsave, 1)); jumps = zeros(Int32, steps + 1); times = zeros(Float64, steps + 1); nj = Ref{Int32}()
     check(ccall((:tn_qjmc_run, lib), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{ComplexF64}, Ptr{Float64}, Int32, Float64, TruncT, Ptr{Float64}, UInt64, UInt64,
-         Ptr{ComplexF64}, Int32, Ptr{ComplexF64}, Ptr{Int32}, Ptr{Float64}, Int32, Ref{Int32}),
+         Ptr{ComplexF64}, Int32, Ptr{ComplexF64}, Ptr{Int32}, Ptr{Float64}, Int32, Ref{Int32}, Int32),
         psi.h, gates.h, length(jumpsites), jumpsites, jumpops, coeffs, steps, dt, TruncT(cutoff, maxdim, mindim),
         uniforms === nothing ? C_NULL : pointer(uniforms), seed, trajectory, obsop === nothing ? C_NULL : pointer(obsop), save_every,
-        obs, jumps, times, steps + 1, nj))
+        obs, jumps, times, steps + 1, nj, classical))
     jumps[1:nj[]], times[1:nj[]], obs[:, 1:nsave]
 end
 # inner(st, psi, oplist, phi) (mps.jl:87-134) with psi, phi on the device: per-term coeff * <psi| O_t |phi>

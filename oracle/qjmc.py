@@ -51,10 +51,8 @@ def qjmc_emission_rates(st, psi, jumpops):
 
 def qjmc_simulation(st, psi, H, jumpops, tmax, dt, observers=(), uniforms=None, save=0, cutoff=1e-12,
                     mindim=1, maxdim=0, classical=True, verbose=False, **kw):
-    """qjmc.jl:28-167, classical branch (:88-112; the default).  ``uniforms`` is a
-    callable returning the next U(0,1) sample."""
-    if not classical:
-        raise NotImplementedError("only the default classical=true branch is on the hot path")
+    """qjmc.jl:28-167: the default classical branch (:88-112) and the norm-based branch (classical=false, :65-87).
+    ``uniforms`` is a callable returning the next U(0,1) sample."""
     if uniforms is None:
         g = np.random.default_rng(0)
         uniforms = g.random
@@ -68,7 +66,27 @@ def qjmc_simulation(st, psi, H, jumpops, tmax, dt, observers=(), uniforms=None, 
         ob.measure(time, psi, jumps, jumptimes)
     for i in range(1, steps + 1):
         applygates(psi, gates, mindim=mindim, maxdim=maxdim, cutoff=cutoff)
-        uniforms()                      # qjmc.jl:64 (unused in classical mode)
+        r0 = uniforms()                 # qjmc.jl:64 (unused in classical mode)
+        if not classical:               # qjmc.jl:65-87: jump when the decayed norm^2 falls below r
+            prob = np.real(psi.norm() ** 2)
+            psi.normalize()
+            if r0 > prob:
+                rates = qjmc_emission_rates(st, psi, jumpops)
+                r = uniforms()
+                cs = np.cumsum(rates) / np.sum(rates)
+                idx = int(np.nonzero(r < cs)[0][0])
+                psi.movecenter(1)
+                applyop(st, psi, jumpops.ops[idx], jumpops.sites[idx])
+                psi.movecenter(len(psi))
+                psi.movecenter(1, cutoff=cutoff, maxdim=maxdim, mindim=mindim)
+                psi.normalize()
+                jumps.append(idx + 1)
+                jumptimes.append(time + dt)
+            time += dt
+            if i % savesteps == 0:
+                for ob in observers:
+                    ob.measure(time, psi, jumps, jumptimes)
+            continue
         psi.normalize()
         rates = qjmc_emission_rates(st, psi, jumpops)
         er = np.sum(rates)

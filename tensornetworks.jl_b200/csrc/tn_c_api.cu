@@ -9,7 +9,7 @@
 namespace tn {
 int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,
              int steps, double dt, Trunc tr, const double* uniforms, uint64_t seed, uint64_t traj,
-             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap);
+             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap, bool classical);
 }
 
 using namespace tn;
@@ -340,10 +340,11 @@ int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t tr) {
 int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
                     const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, const double* uniforms, uint64_t seed,
                     uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* jumps_out,
-                    double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out) {
+                    double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out, int32_t classical) {
   return guard([&] {
     int nj = qjmc_run(psi->m, gates->g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), uniforms, seed, trajectory,
-                      obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap);
+                      obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap,
+                      classical != 0);
     if (njumps_out) *njumps_out = nj;
   });
 }
@@ -511,7 +512,7 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
                          const tn_cplx* const* gate_ptrs, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
                          const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, uint64_t seed, const tn_cplx* obs_op,
                          int32_t save_every, tn_cplx* obs_out, int32_t* njumps_out, int32_t* jumps_out, double* jumptimes_out,
-                         int32_t jump_cap) {
+                         int32_t jump_cap, int32_t classical) {
   return guard([&] {
     TN_CHECK(ntraj >= 0 && nworkers >= 1 && dims && site_ptrs && counts && gate_sites && gate_nsites && gate_ptrs, "qjmc_ensemble: bad arguments");
     TN_CHECK(!obs_op || (obs_out && save_every > 0), "qjmc_ensemble: obs_out / save_every missing");
@@ -536,7 +537,7 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
                             traj_ids ? traj_ids[i] : (uint64_t)i, obs_op ? C(obs_op) : nullptr, save_every,
                             obs_op ? C(obs_out) + (size_t)i * nsaves * N : nullptr,
                             jumps_out ? jumps_out + (size_t)i * jump_cap : nullptr,
-                            jumptimes_out ? jumptimes_out + (size_t)i * jump_cap : nullptr, jump_cap);
+                            jumptimes_out ? jumptimes_out + (size_t)i * jump_cap : nullptr, jump_cap, classical != 0);
           if (njumps_out) njumps_out[i] = nj;
           mps_free(psi); psi = nullptr;
         }

@@ -1,5 +1,7 @@
 // One quantum-jump Monte Carlo trajectory on the device: reference algorithms/mps/qjmc.jl:59-164
-// (classical = true branch, :88-112) with the emission rates of :170-220.
+// (classical = true branch :88-112, and the norm-based branch classical = false :65-87) with the emission rates of :170-220.
+// Uniforms are indexed (step, slot): classical mode draws slot 0 (unused, :64), slot 1 (jump test), slot 2 (channel);
+// the norm-based mode draws slot 0 (jump test against the decayed norm^2) and slot 1 (channel).
 #include "tn_mps.cuh"
 #include <cmath>
 
@@ -16,7 +18,7 @@ static double counter_uniform(uint64_t seed, uint64_t traj, uint64_t step, uint6
 
 int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,
              int steps, double dt, Trunc tr, const double* uniforms, uint64_t seed, uint64_t traj,
-             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap) {
+             const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap, bool classical) {
   Ctx* c = psi->ctx;
   int d = psi->d, N = psi->N;
   TN_CHECK(psi->rank == 1, "qjmc: psi must be an MPS");
@@ -43,20 +45,34 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
   int njumps = 0;
   double time = 0;
   auto draw = [&](int step, int slot) { return uniforms ? uniforms[(size_t)3 * step + slot] : counter_uniform(seed, traj, step, slot); };
-  for (int i = 1; i <= steps; ++i) {
-    apply_gates(psi, gates, tr);                                   // qjmc.jl:61
-    (void)draw(i - 1, 0);                                          // qjmc.jl:64 (drawn, unused in classical mode)
-    mps_normalize(psi);                                            // qjmc.jl:90
-    expect_local(psi, njump, jump_sites, esc.data(), ex.data());   // qjmc.jl:93
+  auto emission_rates = [&]() {                                    // qjmc.jl:170-220 on the normalised state
+    expect_local(psi, njump, jump_sites, esc.data(), ex.data());
     double er = 0;
     for (int k = 0; k < njump; ++k) {
       double c2 = jump_coeffs[k] * jump_coeffs[k];
       rates[k] = std::hypot(c2 * ex[k].x, c2 * ex[k].y);
       er += rates[k];
     }
-    double prob = std::exp(-er * dt);
-    if (draw(i - 1, 1) > prob) {                                   // qjmc.jl:97
-      double r = draw(i - 1, 2), cum = 0;
+    return er;
+  };
+  for (int i = 1; i <= steps; ++i) {
+    apply_gates(psi, gates, tr);                                   // qjmc.jl:61
+    const double r0 = draw(i - 1, 0);                              // qjmc.jl:64 (drawn, unused in classical mode)
+    bool jump;
+    double er = 0;
+    if (classical) {
+      mps_normalize(psi);                                          // qjmc.jl:90
+      er = emission_rates();                                       // qjmc.jl:93
+      jump = draw(i - 1, 1) > std::exp(-er * dt);                  // qjmc.jl:95-97
+    } else {
+      cplx nrm = mps_norm(psi);                                    // qjmc.jl:67: prob = real(norm(psi)^2)
+      const double prob = nrm.x * nrm.x - nrm.y * nrm.y;
+      mps_normalize(psi);                                          // qjmc.jl:68
+      jump = r0 > prob;                                            // qjmc.jl:69
+      if (jump) er = emission_rates();                             // qjmc.jl:71
+    }
+    if (jump) {
+      double r = draw(i - 1, classical ? 2 : 1), cum = 0;          // qjmc.jl:74 / :99
       int idx = njump - 1;
       for (int k = 0; k < njump; ++k) { cum += rates[k]; if (r < cum / er) { idx = k; break; } }
       mps_movecenter(psi, 1, Trunc{0.0, 0, 1});                    // qjmc.jl:103-107

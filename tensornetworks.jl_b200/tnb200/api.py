@@ -555,8 +555,8 @@ def tebd(psi, gates, nsteps, energy_fn=None, nsave=1, cutoff=1e-12, maxdim=0, mi
 
 
 def qjmc_simulation(psi, gates, jump_sites, jump_ops, jump_coeffs, steps, dt, uniforms=None, seed=0, trajectory=0,
-                    obs_op=None, save_every=1, cutoff=1e-12, maxdim=0, mindim=1):
-    """qjmc_simulation loop, algorithms/mps/qjmc.jl:59-164 (classical=true), one trajectory.
+                    obs_op=None, save_every=1, cutoff=1e-12, maxdim=0, mindim=1, classical=True):
+    """qjmc_simulation loop, algorithms/mps/qjmc.jl:59-164 (classical=true :88-112 or the norm-based branch :65-87), one trajectory.
     Returns (jumps, jumptimes, observable array [nsaves, N])."""
     lib = psi.lib
     nj = len(jump_sites)
@@ -578,13 +578,13 @@ def qjmc_simulation(psi, gates, jump_sites, jump_ops, jump_coeffs, steps, dt, un
                           int(steps), float(dt), Trunc(cutoff, maxdim, mindim),
                           None if un is None else un.ctypes.data_as(C.POINTER(C.c_double)), int(seed), int(trajectory),
                           None if oo is None else _ptr(oo), int(save_every), _ptr(obs), jumps.ctypes.data_as(C.POINTER(C.c_int32)),
-                          times.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(njumps)))
+                          times.ctypes.data_as(C.POINTER(C.c_double)), cap, C.byref(njumps), int(bool(classical))))
     n = min(njumps.value, cap)
     return list(jumps[:n]), list(times[:n]), obs[:nsaves]
 
 
 def qjmc_ensemble(tensors, center, gate_sites, gate_tensors, jump_sites, jump_ops, jump_coeffs, steps, dt, traj_ids, workers=8,
-                  device=0, seed=0, obs_op=None, save_every=1, cutoff=1e-12, maxdim=0, mindim=1):
+                  device=0, seed=0, obs_op=None, save_every=1, cutoff=1e-12, maxdim=0, mindim=1, classical=True):
     """Many independent ``qjmc_simulation`` trajectories (the loop a user writes around algorithms/mps/qjmc.jl:28) from one
     initial MPS, distributed over ``workers`` host threads / CUDA streams inside the library (tn_qjmc_ensemble).
     Returns (njumps [T], jumps [T, steps+1], jumptimes [T, steps+1], observable [T, nsaves, N])."""
@@ -616,7 +616,7 @@ def qjmc_ensemble(tensors, center, gate_sites, gate_tensors, jump_sites, jump_op
                                gs.ctypes.data_as(i32p), gn.ctypes.data_as(i32p), gptr, len(js), js.ctypes.data_as(i32p), _ptr(jo),
                                jc.ctypes.data_as(f64p), int(steps), float(dt), Trunc(cutoff, maxdim, mindim), int(seed),
                                None if oo is None else _ptr(oo), int(save_every), _ptr(obs), njumps.ctypes.data_as(i32p),
-                               jumps.ctypes.data_as(i32p), times.ctypes.data_as(f64p), cap))
+                               jumps.ctypes.data_as(i32p), times.ctypes.data_as(f64p), cap, int(bool(classical))))
     return njumps, jumps, times, obs[:, :nsaves]
 
 

@@ -255,3 +255,50 @@ def test_tebd_front_end_matches_oracle():
         assert a[0] == b[0] and abs(a[3] - b[3]) <= 1      # a singular value at the 1e-12 cutoff edge may fall either side
         assert abs(a[1] - b[1]) < 1e-9 * max(1.0, abs(a[1])) and abs(a[2] - b[2]) < 1e-9 * abs(a[2])
     assert abs(Eo - Eg) < 1e-9 * abs(Eo)
+
+
+def test_qjmc_norm_based_branch_matches_oracle():
+    """tn_qjmc_run with classical = 0 (qjmc.jl:65-87) against the oracle with the same per-step uniforms."""
+    import tnb200
+    sh = oracle.spinhalf()
+    N, dt, steps = 7, 0.02, 80
+    H = tfim(N, 1.0, 2.0, 1.0)
+    J = oracle.OpList(N)
+    for i in range(1, N + 1):
+        J.add("s-", i, np.sqrt(0.9))
+    u = np.random.default_rng(12).random(3 * steps)
+
+    class Feeder:                                     # the oracle draws sequentially; the C ABI indexes 3 per step
+        def __init__(self):
+            self.step, self.slot = 0, 0
+
+        def __call__(self):
+            v = u[3 * self.step + self.slot]
+            self.slot += 1
+            return v
+    f = Feeder()
+    psi = oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)])
+    psi.movecenter(1)
+    zs = oracle.OpList(N)
+    for i in range(1, N + 1):
+        zs.add("z", i)
+
+    class Obs:
+        def __init__(self):
+            self.m = []
+
+        def measure(self, time, p, jumps, jt):
+            self.m.append(np.real(oracle.inner(sh, p, zs, p)))
+            f.step, f.slot = len(self.m) - 1, 0
+    ob = Obs()
+    kw = dict(cutoff=1e-10, maxdim=16)
+    jumps, times = oracle.qjmc_simulation(sh, psi, H, J, steps * dt, dt, [ob], uniforms=f, classical=False, **kw)
+    _, gl = oracle.qjmc_gates(sh, H, J, dt)
+    g = tnb200.GMPS.from_host(oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)]))
+    g.movecenter(1)
+    gg = tnb200.GateList.from_host(2, gl)
+    gj, gt, obs = tnb200.qjmc_simulation(g, gg, list(range(1, N + 1)), [sh.op("s-")] * N, [np.sqrt(0.9)] * N, steps, dt,
+                                         uniforms=u, obs_op=sh.op("z"), save_every=1, classical=False, **kw)
+    assert gj == jumps and len(jumps) > 0
+    assert np.allclose(gt, times)
+    assert np.max(np.abs(np.real(obs) - np.array(ob.m[1:]))) < 1e-8

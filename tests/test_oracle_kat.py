@@ -125,3 +125,52 @@ def test_qjmc_matches_dense_state_trajectory():
     assert jumps == dj and len(jumps) > 0
     got = np.real(np.array(ob.measurements[1:]))
     assert np.allclose(got, np.array(dz), atol=1e-8)
+
+
+def test_qjmc_norm_based_branch_matches_dense_state_trajectory():
+    """classical=false (qjmc.jl:65-87): the jump fires when u0 exceeds the norm^2 left after the non-unitary gates; the
+    channel comes from the next uniform.  Dense replay with the same gates and uniforms."""
+    sh = oracle.spinhalf()
+    N, dt, steps = 5, 0.05, 60
+    H = tfim(N, 1.0, 0.3, 0.7)
+    J = oracle.OpList(N)
+    for i in range(1, N + 1):
+        J.add("s-", i, np.sqrt(0.8))
+    u = np.random.default_rng(4).random(2 * steps + 8)
+    it = iter(u)
+    psi = oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)])
+    psi.movecenter(1)
+    zs = oracle.OpList(N)
+    for i in range(1, N + 1):
+        zs.add("z", i)
+    ob = oracle.qjmc.QJMCOperators(zs, sh)
+    jumps, times = oracle.qjmc_simulation(sh, psi, H, J, steps * dt, dt, [ob], uniforms=lambda: next(it), cutoff=0, maxdim=0,
+                                          classical=False)
+    _, gates = oracle.qjmc_gates(sh, H, J, dt)
+    it = iter(u)
+    v = mps_to_dense(oracle.productMPS(sh, ["up" if i % 2 else "dn" for i in range(1, N + 1)])).reshape((2,) * N)
+
+    def apply(v, g, site):
+        n = g.ndim // 2
+        gm = np.transpose(g, [2 * k for k in range(n)] + [2 * k + 1 for k in range(n)])
+        v = np.tensordot(gm, v, axes=(list(range(n, 2 * n)), list(range(site - 1, site - 1 + n))))
+        return np.moveaxis(v, list(range(n)), list(range(site - 1, site - 1 + n)))
+    sm = sh.op("s-")
+    dj, dz = [], []
+    for step in range(steps):
+        for rs, rg in zip(gates.sites, gates.gates):
+            for s, g in zip(rs, rg):
+                v = apply(v, g, s)
+        r0 = next(it)
+        prob = np.linalg.norm(v) ** 2
+        v = v / np.linalg.norm(v)
+        if r0 > prob:
+            rates = np.array([0.8 * np.linalg.norm(apply(v, sm, s)) ** 2 for s in range(1, N + 1)])
+            r = next(it)
+            k = int(np.nonzero(r < np.cumsum(rates) / rates.sum())[0][0])
+            v = apply(v, sm, k + 1)
+            v = v / np.linalg.norm(v)
+            dj.append(k + 1)
+        dz.append([np.real(np.vdot(v, apply(v, sh.op("z"), s))) for s in range(1, N + 1)])
+    assert jumps == dj and len(jumps) > 0
+    assert np.allclose(np.real(np.array(ob.measurements[1:])), np.array(dz), atol=1e-8)
