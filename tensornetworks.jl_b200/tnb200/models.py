@@ -100,3 +100,26 @@ def random_canonical_mps(N, d, chi, seed=0, dtype=np.complex128):
     t0 = tensors[0]
     tensors[0] = t0 / np.linalg.norm(t0)
     return tensors
+
+
+def j1j2_cylinder_terms(Lx, Ly, J1=1.0, J2=0.5):
+    """Operator list [(ops, sites, coeff)] of H = J1 sum_<ij> sigma_i.sigma_j + J2 sum_<<ij>> sigma_i.sigma_j on an Lx x Ly
+    cylinder (periodic in y, open in x), site = x*Ly + y + 1 -- the MPS ordering of BASELINE.json's config 5.
+    Feed to tnb200.mpo.MPO (w = 20 after compression for Ly = 6)."""
+    def idx(x, y):
+        return x * Ly + (y % Ly) + 1
+    bonds = set()
+    for x in range(Lx):
+        for y in range(Ly):
+            i = idx(x, y)
+            for dx, dy, J in ((0, 1, J1), (1, 0, J1), (1, 1, J2), (1, -1, J2)):
+                if x + dx >= Lx:
+                    continue
+                j = idx(x + dx, y + dy)
+                if i != j:
+                    bonds.add((min(i, j), max(i, j), J))
+    terms = []
+    for i, j, J in sorted(bonds):
+        for o in (X, Y, Z):
+            terms.append(([o, o], [i, j], J))
+    return terms

@@ -89,3 +89,12 @@ def test_product_trotterize_equals_oracle_trotterize():
                 for ra, rb in zip(rg, gl.gates):
                     for a, b in zip(ra, rb):
                         assert a.shape == b.shape and np.abs(a - b).max() < 1e-14
+
+
+def test_product_cylinder_terms_equal_the_oracle_oplist():
+    from tnb200 import models as pm
+    from tnb200.mpo import fsm_tensors
+    sh = oracle.spinhalf()
+    for Lx, Ly in ((3, 3), (2, 4)):
+        Ts = fsm_tensors(Lx * Ly, 2, pm.j1j2_cylinder_terms(Lx, Ly))
+        assert np.allclose(_dense(Ts), dense_hamiltonian(sh, j1j2_cylinder(Lx, Ly)).toarray(), atol=1e-12)

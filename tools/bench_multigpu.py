@@ -1,6 +1,7 @@
 """Multi-GPU measurements for the sharded paths; launch with torchrun, one rank per GPU:
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
       tools/bench_multigpu.py --what heff --chi 2048 --w 20
+  ... --what dmrg --lx 12 --ly 6 --chi 1024 --sweeps 2      (MPO-bond-sharded environments + DMRG sweep, J1-J2 cylinder)
   ... --what qjmc --sites 32 --chi 64 --traj 64 --steps 5 --workers 4
 Prints one JSON line on rank 0.  Times on the device (CUDA events), max over ranks."""
 import argparse, json, os, sys, time
@@ -24,6 +25,9 @@ def main():
     ap.add_argument("--traj", type=int, default=32)
     ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--lx", type=int, default=6)
+    ap.add_argument("--ly", type=int, default=4)
+    ap.add_argument("--sweeps", type=int, default=2)
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -74,6 +78,42 @@ def main():
             print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "ms_per_matvec": sec * 1e3,
                               "tflops_total": flops / sec / 1e12, "checksum": chk, "rel_err_vs_einsum": err,
                               "collectives": "NCCL reduce_scatter(T2 over w2) + all_reduce(out)" if world > 1 else "none"}), flush=True)
+    elif a.what == "dmrg":
+        # Sharded DMRG sweeps on the J1-J2 cylinder (C5 shapes when --lx 12 --ly 6 --chi 4096): every rank holds its w-slice
+        # of every environment block; energies must agree with the single-GPU fused sweep (--check, small sizes only).
+        from tnb200.sharded import GpuBackend, sharded_dmrg
+        from tnb200.mpo import MPO
+        Nn = a.lx * a.ly
+        gH = MPO(Nn, d, tnb200.models.j1j2_cylinder_terms(a.lx, a.ly), ctx=ctx)
+        mpo_host = gH.tensors
+        wmax = max(t.shape[3] for t in mpo_host)
+        tens = tnb200.models.random_canonical_mps(Nn, d, a.chi, seed=1)
+        psi = tnb200.GMPS(1, d, tens, 1, ctx=ctx)
+        be = GpuBackend(ctx, "cuda")
+        hist = []
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        # cutoff = 0 keeps the bond dimension at chi, so the shapes are data-independent
+        sharded_dmrg(psi, mpo_host, be, rank, world, dist if world > 1 else None, cutoff=0.0, maxdim=a.chi, minsweeps=a.sweeps,
+                     maxsweeps=a.sweeps, history=hist)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ref = None
+        if a.check and rank == 0:
+            h2 = []
+            tnb200.dmrg(tnb200.GMPS(1, d, tens, 1, ctx=ctx), gH, cutoff=0.0, maxdim=a.chi, minsweeps=a.sweeps, maxsweeps=a.sweeps, history=h2)
+            ref = [h[1] for h in h2]
+        if rank == 0:
+            print(json.dumps({"what": "dmrg_mpo_bond_sharded", "n_gpus": world, "lattice": [a.lx, a.ly], "sites": Nn, "chi": a.chi, "w_max": wmax,
+                              "sweeps": a.sweeps, "s_per_sweep": float(t.item()) / a.sweeps, "energies": [h[1] for h in hist],
+                              "maxbond": [h[2] for h in hist], "single_gpu_energies": ref,
+                              "collectives": "NCCL reduce_scatter (block updates, T2) + all_reduce (H_eff result) + broadcast (new sites)" if world > 1 else "none",
+                              "mem_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
     else:
         Nn, chi = a.sites, a.chi
         X, Z, I2, SM = tnb200.models.X, tnb200.models.Z, tnb200.models.I2, tnb200.models.SM

@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round (everything the last session of round 1 built without GPU time left):
+#   gpurun --timeout 900 -- 'bash tools/run_next_round_first.sh'            (1 GPU)
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools/run_next_round_first.sh 2' (sharded sweep at 2 GPUs)
+# Writes gpurun_out/next_*.log / .jsonl.
+N=${1:-1}
+mkdir -p gpurun_out
+if [ "$N" = "1" ]; then
+  timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/next_gpu_tests.log 2>&1; tail -5 gpurun_out/next_gpu_tests.log
+  timeout 120 python tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check > gpurun_out/next_sharded_dmrg_1.jsonl 2> gpurun_out/next_sharded_dmrg_1.err
+  cat gpurun_out/next_sharded_dmrg_1.jsonl; tail -3 gpurun_out/next_sharded_dmrg_1.err
+  timeout 200 python bench.py > gpurun_out/next_bench.json 2> gpurun_out/next_bench.err; cat gpurun_out/next_bench.json
+else
+  RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519"
+  timeout 300 $RUN tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check > gpurun_out/next_sharded_dmrg_$N.jsonl 2> gpurun_out/next_sharded_dmrg_$N.err
+  timeout 500 $RUN tools/bench_multigpu.py --what dmrg --lx 12 --ly 6 --chi 1024 --sweeps 1 >> gpurun_out/next_sharded_dmrg_$N.jsonl 2>> gpurun_out/next_sharded_dmrg_$N.err
+  cat gpurun_out/next_sharded_dmrg_$N.jsonl; tail -5 gpurun_out/next_sharded_dmrg_$N.err
+fi
