@@ -83,6 +83,13 @@ int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_
 int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t trunc,
                      tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
 
+/* B truncated SVDs of same-shape matrices in one batched factorisation (the gate / gauge-move SVDs of B QJMC trajectories that
+ * advance in lockstep: every kernel launch of the single-problem pipeline covers all B problems).  mats: B consecutive m x n
+ * column-major matrices on the host.  Problem b writes U at U + b*m*kmax (m x k_b), S at S + b*kmax, Vh at Vh + b*kmax*n
+ * (k_b x n, leading dimension k_b), kmax = min(m, n), and its rank to k_out[b].  Same truncation rule as tn_svd_trunc. */
+int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_t m, int64_t n, tn_trunc_t trunc,
+                             tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
+
 /* tuning switch (process-wide): 1 = QR-preconditioned Jacobi (default), 0 = plain Jacobi */
 int32_t tn_svd_set_precond(int32_t mode);
 

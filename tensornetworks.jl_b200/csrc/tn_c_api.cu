@@ -36,6 +36,7 @@ static void ctx_release(Ctx& c) {
   cudaSetDevice(c.device);
   if (c.stream) cudaStreamSynchronize(c.stream);
   svd_free(c.svd);
+  svd_batched_free(c.svdb);
   for (auto& b : c.scratch) b.release();
   cudaFree(c.dscal); cudaFreeHost(c.hscal); cudaFree(c.partials);
   if (c.copy_stream) { cudaStreamDestroy(c.copy_stream); for (auto& ev : c.copy_ev) cudaEventDestroy(ev); }
@@ -179,6 +180,33 @@ int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_t
     c->sync();
     *k_out = k;
     if (sweeps_out) *sweeps_out = c->svd.sweeps;
+  });
+}
+
+int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_t m, int64_t n, tn_trunc_t tr, tn_cplx* U, double* S,
+                             tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out) {
+  return guard([&] {
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    TN_CHECK(B >= 1 && m >= 1 && n >= 1 && mats && U && S && Vh && k_out, "batched svd: bad arguments");
+    const size_t mn = (size_t)(m * n), kmax = (size_t)std::min(m, n);
+    cplx* dM = c->scratch[0].get((size_t)B * mn, s);
+    TN_CUDA(cudaMemcpyAsync(dM, mats, (size_t)B * mn * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    std::vector<const cplx*> ptrs(B);
+    for (int b = 0; b < B; ++b) ptrs[b] = dM + (size_t)b * mn;
+    svd_batched_factor(c->svdb, B, ptrs.data(), (int)m, (int)n, m, T(tr), s); c->svds += B;
+    cplx* dU = c->scratch[1].get((size_t)m * kmax, s);
+    cplx* dV = c->scratch[2].get(kmax * (size_t)n, s);
+    for (int b = 0; b < B; ++b) {
+      const int k = c->svdb.k[b];
+      svd_batched_gather_U(c->svdb, b, dU, m, false, s);
+      svd_batched_gather_Vh(c->svdb, b, dV, k, false, s);
+      TN_CUDA(cudaMemcpyAsync(U + (size_t)b * m * kmax, dU, (size_t)m * k * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+      TN_CUDA(cudaMemcpyAsync(Vh + (size_t)b * kmax * n, dV, (size_t)k * n * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+      TN_CUDA(cudaMemcpyAsync(S + (size_t)b * kmax, c->svdb.sig + (size_t)b * c->svdb.npad, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
+      c->sync();                      // dU / dV are reused by the next problem
+      k_out[b] = k;
+    }
+    if (sweeps_out) *sweeps_out = c->svdb.sweeps;
   });
 }
 

@@ -26,6 +26,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   SvdWork svd;
+  SvdBatch svdb;             // batched factorisations (same-shape problems of lockstep trajectories)
   Buf scratch[24];           // 0-15: MPS / environment / Lanczos work space (tn_mps.cu); 16-23: projector sums (tn_projsum.cu)
   cplx* dscal = nullptr;     // 64 device scalars
   cplx* hscal = nullptr;     // 64 pinned host scalars

@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(1024) sort_trunc_kernel(const double* __restri
   extern __shared__ __align__(16) unsigned char sm_raw[];
   double* key = reinterpret_cast<double*>(sm_raw);
   int* val = reinterpret_cast<int*>(key + npow2);
+  // one CTA per problem of a batched factorisation (grid = 1 otherwise): problem b owns entries [b * ncols, (b + 1) * ncols)
+  sig2 += (long long)blockIdx.x * ncols; sig += (long long)blockIdx.x * ncols; perm += (long long)blockIdx.x * ncols; kout += blockIdx.x;
   for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
     key[i] = i < ncols ? sig2[i] : -1.0;
     val[i] = i;
@@ -303,6 +305,9 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx*
   __shared__ double rrow[JP];       // 1 / R(j,j) per row (0 = null / failed pivot)
   __shared__ double rdinv[JP];      // reciprocal diagonal of R (divisions cost ~600 cycles of FP64 latency: do each once)
   const int tid = threadIdx.x;
+  // batched factorisations (svd_batched_factor) launch one CTA per problem: CTA b works on the b-th 64 x 64 slot of every buffer
+  Gpart += (long long)blockIdx.x * JP * JP; Rinv_out += (long long)blockIdx.x * JP * JP; Rtot += (long long)blockIdx.x * JP * JP;
+  if (done_flag != nullptr) done_flag += blockIdx.x;
   // CholeskyQR3 with early termination: the second pass marks the panel as finished when its Gram matrix was already
   // within 1e-3 of the identity (one Cholesky pass on such a panel leaves O(eps) orthogonality error); the third pass'
   // Gram / Cholesky / apply launches then return at once.
@@ -826,6 +831,270 @@ void svd_free(SvdWork& w) {
   for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
   w = SvdWork{};
+}
+
+// ================================================================================================
+// Batched factorisation: B matrices of the same shape (the gate / gauge-move SVDs of B QJMC trajectories that advance in
+// lockstep; SURVEY 2b K5 "batched variant").  The problems are stacked side by side -- Z = [Z_0 | Z_1 | ...], Q1, Q2, R alike --
+// so every launch of the single-problem pipeline becomes ONE launch over B problems: the GEMMs get a batch dimension (problem
+// stride), the Jacobi pair table lists the column-block pairs of all problems (B * np CTAs per EVD launch instead of np: at
+// n = 512 one problem occupies 8 of 148 SMs), the Cholesky / sort kernels run one CTA per problem.  All problems sweep until the
+// slowest has converged (pairs that are already diagonal are skipped by the rotation GEMM).  The per-problem factors are read
+// through the ordinary gathers on a view of the stacked workspace.
+// ================================================================================================
+static const int* pair_table_b(SvdBatch& w, int B, int nb, cudaStream_t s) {
+  auto key = std::make_pair(B, nb);
+  auto it = w.tables.find(key);
+  if (it != w.tables.end()) return it->second;
+  const int steps = nb - 1, np = nb / 2;
+  std::vector<int> h((size_t)steps * B * np * 2);
+  for (int st = 0; st < steps; ++st)
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < np; ++k) {
+        int a, c;
+        if (nb == 2) { a = 0; c = 1; }
+        else if (k == 0) { a = nb - 1; c = st; }
+        else { a = (st + k) % (nb - 1); c = (st - k + (nb - 1)) % (nb - 1); }
+        const size_t e = (((size_t)st * B + b) * np + k) * 2;
+        h[e + 0] = b * nb + std::min(a, c);
+        h[e + 1] = b * nb + std::max(a, c);
+      }
+  int* d = nullptr;
+  TN_CUDA(cudaMalloc((void**)&d, h.size() * sizeof(int)));
+  TN_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  w.tables[key] = d;
+  return d;
+}
+
+static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
+  const int B = w.B, nb = w.npad / JB, np = nb / 2, steps = nb - 1, npg = B * np;
+  // Gram GEMM grid = B * np pairs x ksplit: about one wave of the 2 x 148 CTA slots
+  int ksplit = std::max(1, std::min(std::min(std::min(16, max_split()), jrows / 64), (2 * 148) / npg));
+  int kchunk = ((jrows + ksplit - 1) / ksplit + 7) / 8 * 8;
+  ksplit = (jrows + kchunk - 1) / kchunk;
+  ensure(w.Gpart, w.G_cap, (size_t)npg * JP * JP, s);
+  ensure(w.J, w.J_cap, (size_t)npg * JP * JP, s);
+  ensure(w.skip, w.skip_cap, (size_t)npg, s);
+  const int* tab = pair_table_b(w, B, nb, s);
+  const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
+  TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem));
+  const double tol = 3.0 * std::sqrt((double)jrows) * 2.220446049250313e-16;
+  const long long colblk = (long long)JB * w.ldz;
+  const int inner_sweeps = (np == 1) ? 12 : 1;
+  const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
+  w.sweeps = 0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
+    for (int st = 0; st < steps; ++st) {
+      Idx2 cols{JB, (long long)w.ldz, colblk, tab + (size_t)st * npg * 2, 2};
+      GemmDesc g{};
+      g.M = JP; g.N = JP; g.K = jrows;
+      g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
+      g.B = w.Z; g.bk = idx1(1); g.bn = cols; g.conjB = 0;
+      g.C = w.Gpart; g.cm = idx1(1); g.cn = idx1(JP);
+      g.alpha = make_double2(1, 0); g.beta = make_double2(0, 0);
+      g.batch = npg; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
+      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
+      if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)npg * JP * JP * sizeof(cplx), s));
+      zgemm_auto(g, s);
+      jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, s>>>(w.Gpart, 1, 0, w.J, tol, w.offmax, inner_sweeps, nact, w.skip);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      GemmDesc a{};
+      a.M = jrows + w.npad; a.N = JP; a.K = JP;
+      a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
+      a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
+      a.C = w.Z; a.cm = idx1(1); a.cn = cols;
+      a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
+      a.batch = npg; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
+      a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
+      a.skip = w.skip;
+      zgemm_auto(a, s);
+    }
+    unsigned long long bits = 0;
+    TN_CUDA(cudaMemcpyAsync(&bits, w.offmax, 8, cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaStreamSynchronize(s));
+    double off; std::memcpy(&off, &bits, 8);
+    w.sweeps = sweep + 1;
+    if (off <= tol) break;
+  }
+}
+
+// Right-looking block Gram-Schmidt pass (bgs_pass) over B stacked problems: Q = [Q_0 | Q_1 | ...] (rows x B*npad, ld = ldq),
+// R = [R_0 | R_1 | ...] (npad x B*npad, ld = npad).
+static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, int chol_passes, cudaStream_t s) {
+  const int B = w.B;
+  const long long qs = (long long)npad * ldq, rs = (long long)npad * npad, gs = (long long)JP * JP;
+  const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
+  TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
+  TN_CUDA(cudaMemsetAsync(R, 0, (size_t)B * rs * sizeof(cplx), s));
+  ensure(w.Gpart, w.G_cap, (size_t)B * gs, s);
+  // B tiles of 64 x 64 per panel: split their K range until about one wave of CTAs is in flight
+  int ksplit = std::max(1, std::min(std::min(std::min(32, max_split()), rows / 64), (2 * 148) / B));
+  int kchunk = ((rows + ksplit - 1) / ksplit + 7) / 8 * 8;
+  ksplit = (rows + kchunk - 1) / kchunk;
+  cplx* Rinv = w.small; cplx* Rtot = w.small + (size_t)B * gs;
+  const double shift_factor = 11.0 * ((double)rows * JP + (double)JP * (JP + 1)) * 2.220446049250313e-16;
+  const int npanels = npad / JP;
+  for (int pk = 0; pk < npanels; ++pk) {
+    cplx* P = Q + (long long)pk * JP * ldq;
+    for (int it = 0; it < chol_passes; ++it) {
+      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
+      const int* skip3 = (chol_passes == 3 && it == 2) ? w.cflag : nullptr;     // per problem: third CholeskyQR pass not needed
+      g.batch = B; g.bsA = qs; g.bsB = qs; g.bsC = gs;
+      g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
+      g.skip = skip3;
+      if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)B * gs * sizeof(cplx), s));
+      zgemm_auto(g, s);
+      chol_inv64_kernel<<<B, CHOL_THREADS, chol_smem, s>>>(w.Gpart, 1, gs, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
+                                                          chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      GemmDesc ap = gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq));
+      ap.batch = B; ap.bsA = qs; ap.bsB = gs; ap.bsC = qs;
+      ap.skip = skip3;
+      zgemm_auto(ap, s);
+    }
+    for (int b = 0; b < B; ++b)     // R_b(pk,pk) = Rtot_b
+      TN_CUDA(cudaMemcpy2DAsync(R + b * rs + (long long)pk * JP + (long long)pk * JP * npad, (size_t)npad * sizeof(cplx), Rtot + b * gs,
+                                (size_t)JP * sizeof(cplx), (size_t)JP * sizeof(cplx), JP, cudaMemcpyDeviceToDevice, s));
+    const int nt = npad - (pk + 1) * JP;
+    if (nt > 0) {
+      cplx* T = Q + (long long)(pk + 1) * JP * ldq;
+      int csplit = std::max(1, std::min(std::min(std::min(16, max_split()), rows / 64), 148 / (B * ((nt + 127) / 128))));
+      int cchunk = ((rows + csplit - 1) / csplit + 7) / 8 * 8;
+      csplit = (rows + cchunk - 1) / cchunk;
+      cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
+      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
+      c.batch = B; c.bsA = qs; c.bsB = qs; c.bsC = rs;
+      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
+      zgemm_auto(c, s);
+      GemmDesc u = gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0);
+      u.batch = B; u.bsA = qs; u.bsB = rs; u.bsC = qs;
+      zgemm_auto(u, s);
+    }
+  }
+}
+
+static void bgs_qr_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, cudaStream_t s) {
+  const size_t rs = (size_t)npad * npad;
+  ensure(w.Ra, w.Ra_cap, w.B * rs, s);
+  ensure(w.Rb, w.Rb_cap, w.B * rs, s);
+  ensure(w.Rc, w.Rc_cap, w.B * rs, s);
+  bgs_pass_b(w, Q, ldq, rows, npad, w.Rc, 3, s);
+  bgs_pass_b(w, Q, ldq, rows, npad, w.Rb, 1, s);
+  GemmDesc g = gd(npad, npad, npad, w.Rb, idx1(1), idx1(npad), 0, w.Rc, idx1(1), idx1(npad), 0, w.Ra, idx1(1), idx1(npad));   // R = R'' R'
+  g.batch = w.B; g.bsA = (long long)rs; g.bsB = (long long)rs; g.bsC = (long long)rs;
+  zgemm_auto(g, s);
+}
+
+void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+  TN_CHECK(B >= 1 && B <= 1024 && m >= 1 && n >= 1, "batched svd: bad batch / shape");
+  w.B = B; w.m = m; w.n = n;
+  w.transposed = m < n;
+  w.rows = w.transposed ? n : m;
+  w.ncols = w.transposed ? m : n;
+  w.npad = ((w.ncols + JP - 1) / JP) * JP;
+  const int npad = w.npad, rows = w.rows;
+  TN_CHECK(npad <= 8192 && (long long)B * (npad / JB) < (1 << 24), "batched svd: problem too large");
+  w.precond = precond_enabled() && npad > JP;
+  const size_t tot = (size_t)B * npad;
+  if (w.s_cap < tot) {
+    if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
+    TN_CUDA(cudaMallocAsync((void**)&w.sig, tot * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.sig2, tot * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.perm, tot * sizeof(int), s));
+    w.s_cap = tot;
+  }
+  if (!w.offmax) TN_CUDA(cudaMalloc((void**)&w.offmax, 8));
+  ensure(w.kout, w.kout_cap, (size_t)B, s);
+  ensure(w.cflag, w.cflag_cap, (size_t)B, s);
+  ensure(w.small, w.small_cap, (size_t)2 * B * JP * JP, s);
+  int blocks;
+  if (!w.precond) {
+    w.jrows = rows;
+    w.ldz = pad_ld(rows + npad);
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * tot, s);
+    launch_1d((long long)w.ldz * npad, blocks);
+    for (int b = 0; b < B; ++b)
+      svd_init_kernel<<<blocks, 256, 0, s>>>(Ms[b], ld, m, n, w.transposed ? 1 : 0, w.Z + (size_t)b * npad * w.ldz, rows, w.ncols, npad, w.ldz);
+    TN_CUDA(cudaGetLastError());
+    count_launch(B);
+    jacobi_sweeps_b(w, rows, s);
+  } else {
+    ensure(w.Q1, w.Q1_cap, (size_t)rows * tot, s);
+    launch_1d((long long)rows * npad, blocks);
+    for (int b = 0; b < B; ++b)
+      svd_init_kernel<<<blocks, 256, 0, s>>>(Ms[b], ld, m, n, w.transposed ? 1 : 0, w.Q1 + (size_t)b * npad * rows, rows, w.ncols, npad, rows);
+    count_launch(B);
+    bgs_qr_b(w, w.Q1, rows, rows, npad, s);                       // Ra_b = R1 of problem b
+    ensure(w.Q2, w.Q2_cap, (size_t)npad * tot, s);
+    launch_1d((long long)npad * npad, blocks);
+    for (int b = 0; b < B; ++b)
+      conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra + (size_t)b * npad * npad, npad, npad, npad, w.Q2 + (size_t)b * npad * npad, npad);
+    count_launch(B);
+    bgs_qr_b(w, w.Q2, npad, npad, npad, s);                       // Ra_b = R2
+    w.jrows = npad;
+    w.ldz = pad_ld(2 * npad);
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * tot, s);
+    for (int b = 0; b < B; ++b) {
+      cplx* Zb = w.Z + (size_t)b * npad * w.ldz;
+      conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra + (size_t)b * npad * npad, npad, npad, npad, Zb, w.ldz);   // W <- R2^H
+      set_identity_kernel<<<blocks, 256, 0, s>>>(Zb + npad, w.ldz, npad);
+    }
+    TN_CUDA(cudaGetLastError());
+    count_launch(2 * B);
+    jacobi_sweeps_b(w, npad, s);
+  }
+  colnorm2_kernel<<<(unsigned)tot, 128, 0, s>>>(w.Z, w.jrows, w.ldz, w.sig2);
+  int npow2 = 64; while (npow2 < npad) npow2 <<= 1;
+  TN_CUDA(cudaFuncSetAttribute(sort_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+  sort_trunc_kernel<<<B, 1024, npow2 * 12, s>>>(w.sig2, npad, npow2, w.sig, w.perm, w.ncols, tr.cutoff, tr.maxdim, tr.mindim, w.kout);
+  TN_CUDA(cudaGetLastError());
+  count_launch(2);
+  w.k.assign(B, 0);
+  TN_CUDA(cudaMemcpyAsync(w.k.data(), w.kout, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+}
+
+// single-problem view of problem b: the ordinary gathers work on it unchanged
+static SvdWork batch_view(SvdBatch& w, int b) {
+  TN_CHECK(b >= 0 && b < w.B, "batched svd: problem index out of range");
+  SvdWork v;
+  const size_t npad = (size_t)w.npad;
+  v.Z = w.Z + (size_t)b * npad * w.ldz;
+  v.sig = w.sig + b * npad; v.perm = w.perm + b * npad;
+  v.Q1 = w.Q1 ? w.Q1 + (size_t)b * npad * w.rows : nullptr;
+  v.Q2 = w.Q2 ? w.Q2 + (size_t)b * npad * npad : nullptr;
+  v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
+  v.precond = w.precond; v.jrows = w.jrows;
+  v.m = w.m; v.n = w.n; v.rows = w.rows; v.ncols = w.ncols; v.ncols_pad = w.npad; v.ldz = w.ldz; v.nsv = w.ncols; v.k = w.k[b];
+  v.transposed = w.transposed;
+  return v;
+}
+void svd_batched_gather_U(SvdBatch& w, int b, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
+  SvdWork v = batch_view(w, b);
+  svd_gather_U(v, U, ldu, times_S, s);
+  w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
+}
+void svd_batched_gather_Vh(SvdBatch& w, int b, cplx* Vh, long long ldv, bool times_S, cudaStream_t s) {
+  SvdWork v = batch_view(w, b);
+  svd_gather_Vh(v, Vh, ldv, times_S, s);
+  w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
+}
+void svd_batched_copy_S(SvdBatch& w, int b, double* S, cudaStream_t s) {
+  TN_CUDA(cudaMemcpyAsync(S, w.sig + (size_t)b * w.npad, (size_t)w.k[b] * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+void svd_batched_free(SvdBatch& w) {
+  for (cplx* p : {w.Z, w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Gpart, w.J, w.small, w.Tg}) if (p) cudaFree(p);
+  if (w.skip) cudaFree(w.skip);
+  if (w.cflag) cudaFree(w.cflag);
+  if (w.kout) cudaFree(w.kout);
+  if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
+  if (w.offmax) cudaFree(w.offmax);
+  for (auto& kv : w.tables) cudaFree(kv.second);
+  w = SvdBatch{};
 }
 
 }  // namespace tn

@@ -44,6 +44,36 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
 // first k singular values (device -> device copy)
 void svd_copy_S(SvdWork& w, double* S, cudaStream_t s);
 void svd_free(SvdWork& w);
+
+// Workspace of a batched factorisation: B same-shape problems stacked side by side (tn_svd.cu, "Batched factorisation").
+struct SvdBatch {
+  int B = 0, m = 0, n = 0, rows = 0, ncols = 0, npad = 0, ldz = 0, jrows = 0, sweeps = 0;
+  bool transposed = false, precond = false;
+  cplx* Z = nullptr; size_t Z_cap = 0;
+  cplx* Q1 = nullptr; size_t Q1_cap = 0;
+  cplx* Q2 = nullptr; size_t Q2_cap = 0;
+  cplx* Ra = nullptr; size_t Ra_cap = 0;
+  cplx* Rb = nullptr; size_t Rb_cap = 0;
+  cplx* Rc = nullptr; size_t Rc_cap = 0;
+  cplx* Gpart = nullptr; size_t G_cap = 0;
+  cplx* J = nullptr; size_t J_cap = 0;
+  cplx* small = nullptr; size_t small_cap = 0;      // per problem: Rinv, Rtot (64 x 64 each)
+  cplx* Tg = nullptr; size_t Tg_cap = 0;
+  int* skip = nullptr; size_t skip_cap = 0;
+  int* cflag = nullptr; size_t cflag_cap = 0;
+  int* kout = nullptr; size_t kout_cap = 0;
+  double* sig = nullptr; double* sig2 = nullptr; int* perm = nullptr; size_t s_cap = 0;
+  unsigned long long* offmax = nullptr;
+  std::map<std::pair<int, int>, int*> tables;        // (B, column blocks) -> round-robin pair table of all problems
+  std::vector<int> k;                                // truncation rank of every problem (host)
+};
+// Factorises B matrices Ms[b] (device pointers, each m x n column-major with leading dimension ld) and applies the
+// reference's truncation rule to each; the ranks are left in w.k.
+void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s);
+void svd_batched_gather_U(SvdBatch& w, int b, cplx* U, long long ldu, bool times_S, cudaStream_t s);
+void svd_batched_gather_Vh(SvdBatch& w, int b, cplx* Vh, long long ldv, bool times_S, cudaStream_t s);
+void svd_batched_copy_S(SvdBatch& w, int b, double* S, cudaStream_t s);
+void svd_batched_free(SvdBatch& w);
 void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn

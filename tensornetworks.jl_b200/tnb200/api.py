@@ -390,6 +390,28 @@ def svd(x, idx, cutoff=0.0, maxdim=0, mindim=1, ctx=None, return_sweeps=False):
     return out + (sw.value,) if return_sweeps else out
 
 
+def svd_batched(mats, cutoff=0.0, maxdim=0, mindim=1, ctx=None):
+    """Truncated SVDs (tensors.jl:168-227 on matrices, idx = last) of a stack ``mats[b]`` (B, m, n) of same-shape matrices in one
+    batched factorisation (tn_svd_trunc_batched).  Returns a list of (U (m x k_b), S (k_b,), Vh (k_b x n))."""
+    ctx = ctx or Context.default()
+    mats = np.asarray(mats, dtype=np.complex128)
+    B, m, n = mats.shape
+    flat = np.ascontiguousarray(np.stack([np.reshape(x, -1, order='F') for x in mats]))
+    kmax = min(m, n)
+    U = np.zeros((B, m * kmax), dtype=np.complex128)
+    Vh = np.zeros((B, kmax * n), dtype=np.complex128)
+    S = np.zeros((B, kmax))
+    k = np.zeros(B, dtype=np.int64)
+    sw = C.c_int32()
+    check(ctx.lib.tn_svd_trunc_batched(ctx.h, B, _ptr(flat), m, n, Trunc(cutoff, maxdim, mindim), _ptr(U), S.ctypes.data_as(C.POINTER(C.c_double)),
+                                       _ptr(Vh), k.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(sw)))
+    out = []
+    for b in range(B):
+        kb = int(k[b])
+        out.append((np.reshape(U[b, :m * kb], (m, kb), order='F'), S[b, :kb].copy(), np.reshape(Vh[b, :kb * n], (kb, n), order='F')))
+    return out
+
+
 def contract_strided(M, N, K, A, am, ak, conjA, B, bk, bn, conjB, c_elems, cm, cn, alpha=1.0, ctx=None):
     """Debug/parity entry to the strided contraction kernel (tensors.jl:9-18 in GEMM form).
     A, B are flat complex128 buffers; index descriptors are (n0, s0, s1) triples."""

@@ -302,3 +302,32 @@ def test_qjmc_norm_based_branch_matches_oracle():
     assert gj == jumps and len(jumps) > 0
     assert np.allclose(gt, times)
     assert np.max(np.abs(np.real(obs) - np.array(ob.m[1:]))) < 1e-8
+
+
+@pytest.mark.parametrize("B,m,n,kw", [(5, 48, 48, dict()), (4, 96, 64, dict(cutoff=1e-10)), (3, 200, 130, dict(maxdim=70)),
+                                      (6, 130, 260, dict(cutoff=1e-12, maxdim=100)), (8, 256, 256, dict(maxdim=128))])
+def test_batched_svd_matches_lapack_and_single(B, m, n, kw):
+    """tn_svd_trunc_batched: B same-shape problems in one batched factorisation (stacked workspace, one launch per pipeline
+    stage) against LAPACK singular values, the reference's truncation rule and reconstruction of the truncated matrix."""
+    import tnb200
+    rng = np.random.default_rng(B * 1000 + m + n)
+    mats = []
+    for b in range(B):
+        x = crandn(rng, m, n)
+        if b % 2 == 1:                                   # graded spectrum: the truncation rule has something to cut
+            u, s, vh = np.linalg.svd(x, full_matrices=False)
+            x = (u * (s[0] * np.exp(-np.arange(len(s)) * (24.0 / len(s))))) @ vh
+        mats.append(x)
+    res = tnb200.svd_batched(np.stack(mats), **kw)
+    assert len(res) == B
+    for x, (U, S, Vh) in zip(mats, res):
+        _, So, _ = oracle.svd(x, 2, **kw)
+        so = np.real(np.diag(So))
+        assert S.shape == so.shape, (S.shape, so.shape)
+        assert np.max(np.abs(S - so)) < 1e-12 * so[0]
+        k = len(S)
+        assert np.linalg.norm(U.conj().T @ U - np.eye(k)) < 1e-11 * np.sqrt(k)
+        assert np.linalg.norm(Vh @ Vh.conj().T - np.eye(k)) < 1e-11 * np.sqrt(k)
+        u, s, vh = np.linalg.svd(x, full_matrices=False)
+        want = (u[:, :k] * s[:k]) @ vh[:k]
+        assert np.linalg.norm((U * S) @ Vh - want) < 1e-11 * s[0] * np.sqrt(k)
