@@ -550,11 +550,18 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     const int nw = std::min<int>(nworkers, std::max(1, ntraj));
     std::atomic<int> next{0};
     std::mutex err_mu; std::string err; int err_code = 0;
+    // TN_QJMC_BATCH=1: the workers' truncated SVDs are collected into batching rounds (tn_svd.cuh: SvdBatcher) -- every round
+    // factorises the pending SVD of every active trajectory, grouped by shape, in one batched pipeline instead of nw
+    // concurrent single-problem pipelines.  Off by default until it has been timed on the GPU.
+    const char* benv = getenv("TN_QJMC_BATCH");
+    SvdBatcher* batcher = (benv && benv[0] == '1' && nw > 1) ? svd_batcher_create(nw) : nullptr;
     auto worker = [&]() {
       Ctx c;
       Gates* g = nullptr; Mps* psi = nullptr;
+      bool attached = false;
       try {
         ctx_init(c, device);
+        if (batcher) { svd_batcher_attach(batcher); attached = true; }
         g = gates_create(&c, d, nrows, counts, gate_sites, gate_nsites, reinterpret_cast<const cplx* const*>(gate_ptrs));
         for (;;) {
           { std::lock_guard<std::mutex> lk(err_mu); if (err_code) break; }
@@ -574,6 +581,10 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
       } catch (const std::exception& e) {
         std::lock_guard<std::mutex> lk(err_mu); if (!err_code) { err_code = TN_ERR_INTERNAL; err = e.what(); }
       }
+      if (batcher) {                       // leave the rounds (also when ctx_init failed: this worker was counted as active)
+        if (!attached) svd_batcher_attach(batcher);
+        svd_batcher_detach(c.stream);
+      }
       if (psi) mps_free(psi);
       if (g) gates_free(g);
       ctx_release(c);
@@ -581,6 +592,11 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     std::vector<std::thread> pool;
     for (int k = 0; k < nw; ++k) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
+    if (batcher) {
+      long long probs = 0; const long long rounds = svd_batcher_rounds(batcher, &probs);
+      if (getenv("TN_QJMC_BATCH_STATS")) fprintf(stderr, "{\"qjmc_batching\": {\"workers\": %d, \"rounds\": %lld, \"svds\": %lld}}\n", nw, rounds, probs);
+      svd_batcher_destroy(batcher);
+    }
     if (err_code) throw tn::Error(err_code, "qjmc_ensemble: " + err);
   });
 }

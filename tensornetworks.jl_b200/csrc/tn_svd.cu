@@ -12,6 +12,9 @@
 //   until every pair's Gram matrix is diagonal to sqrt(m)*eps.  Then sigma_j = ||W(:,j)||, U = W/sigma,
 //   sorted on device; the truncation rank is computed on device with the reference's exact rule.
 #include "tn_svd.cuh"
+#include <condition_variable>
+#include <mutex>
+#include <tuple>
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -702,8 +705,13 @@ static int pad_ld(int rows) {
   return (rows % 64 == 0) ? rows + pad : rows;
 }
 
+static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s);
+static thread_local SvdBatcher* tl_batcher = nullptr;
+
 int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
   TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
+  w.use_view = false;
+  if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s);
   w.m = m; w.n = n;
   w.transposed = m < n;
   w.rows = w.transposed ? n : m;
@@ -801,6 +809,12 @@ static void precond_right(SvdWork& w, int scale_mode, cplx* out, long long ldo, 
 }
 
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
+  if (w.use_view) {      // factors of a batching round: gather from this thread's slot, with this thread's scratch
+    SvdWork& v = *w.bview; v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
+    svd_gather_U(v, U, ldu, times_S, s);
+    w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
+    return;
+  }
   if (w.precond) {
     if (!w.transposed) precond_left(w, times_S ? 0 : 2, U, ldu, false, s);       // Q1 (W[/sigma])
     else precond_right(w, times_S ? 1 : 0, U, ldu, false, s);                    // Q2 (V[*sigma])
@@ -810,6 +824,12 @@ void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t
   else gather(w.Z + w.rows, w.ldz, w.m, w.k, w.perm, w.sig, times_S ? 1 : 0, 0, U, ldu, s);                // V' (* sigma)
 }
 void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream_t s) {
+  if (w.use_view) {
+    SvdWork& v = *w.bview; v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
+    svd_gather_Vh(v, Vh, ldv, times_S, s);
+    w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
+    return;
+  }
   if (w.precond) {
     if (!w.transposed) precond_right(w, times_S ? 1 : 0, Vh, ldv, true, s);      // (Q2 V[*sigma])^H
     else precond_left(w, times_S ? 0 : 2, Vh, ldv, true, s);                     // (Q1 W[/sigma])^H
@@ -819,7 +839,8 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
   else gather(w.Z, w.ldz, w.n, w.k, w.perm, w.sig, times_S ? 0 : 2, 1, Vh, ldv, s);                        // conj(W'/sigma)^T
 }
 void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
-  TN_CUDA(cudaMemcpyAsync(S, w.sig, (size_t)w.k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  const double* sig = w.use_view ? w.bview->sig : w.sig;
+  TN_CUDA(cudaMemcpyAsync(S, sig, (size_t)w.k * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
@@ -830,6 +851,7 @@ void svd_free(SvdWork& w) {
   if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); cudaFree(w.cflag); }
   for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
+  delete w.bview;
   w = SvdWork{};
 }
 
@@ -1095,6 +1117,89 @@ void svd_batched_free(SvdBatch& w) {
   if (w.offmax) cudaFree(w.offmax);
   for (auto& kv : w.tables) cudaFree(kv.second);
   w = SvdBatch{};
+}
+
+// ================================================================================================
+// Batching rounds across worker threads (see tn_svd.cuh)
+// ================================================================================================
+struct BatchReq { SvdWork* w; const cplx* M; int m, n; long long ld; Trunc tr; int k; };
+struct SvdBatcher {
+  std::mutex mu;
+  std::condition_variable cv;
+  int nactive = 0, nwaiting = 0;
+  unsigned long long round = 0;
+  long long problems = 0;
+  std::vector<BatchReq*> pending;
+  typedef std::tuple<int, int, long long, double, long long, long long> Key;   // m, n, ld, cutoff, maxdim, mindim
+  std::map<Key, SvdBatch> work;                                               // one stacked workspace per shape group
+  int err_code = 0; std::string err;
+};
+
+SvdBatcher* svd_batcher_create(int nworkers) { auto* b = new SvdBatcher(); b->nactive = nworkers; return b; }
+void svd_batcher_destroy(SvdBatcher* b) {
+  if (!b) return;
+  for (auto& kv : b->work) svd_batched_free(kv.second);
+  delete b;
+}
+void svd_batcher_attach(SvdBatcher* b) { tl_batcher = b; }
+long long svd_batcher_rounds(SvdBatcher* b, long long* problems) { if (problems) *problems = b->problems; return (long long)b->round; }
+
+// Called with bt.mu held by the thread that completes the round; factorises every parked request on stream s.
+static void batcher_run_round(SvdBatcher& bt, cudaStream_t s) {
+  try {
+    // data-dependent bond dimensions produce many shapes over a long run: drop the cached workspaces now and then (safe here:
+    // every worker synchronised its stream before parking, so nobody still reads the previous round's factors)
+    if (bt.work.size() > 48) { for (auto& kv : bt.work) svd_batched_free(kv.second); bt.work.clear(); }
+    std::map<SvdBatcher::Key, std::vector<BatchReq*>> groups;
+    for (BatchReq* r : bt.pending) groups[SvdBatcher::Key(r->m, r->n, r->ld, r->tr.cutoff, r->tr.maxdim, r->tr.mindim)].push_back(r);
+    for (auto& kv : groups) {
+      std::vector<BatchReq*>& g = kv.second;
+      SvdBatch& wb = bt.work[kv.first];
+      std::vector<const cplx*> ptrs;
+      for (BatchReq* r : g) ptrs.push_back(r->M);
+      svd_batched_factor(wb, (int)g.size(), ptrs.data(), g[0]->m, g[0]->n, g[0]->ld, g[0]->tr, s);   // ends with a stream synchronise
+      for (size_t b = 0; b < g.size(); ++b) {
+        SvdWork& w = *g[b]->w;
+        if (!w.bview) w.bview = new SvdWork();
+        *w.bview = batch_view(wb, (int)b);
+        w.use_view = true;
+        w.k = wb.k[b]; w.m = wb.m; w.n = wb.n; w.sweeps = wb.sweeps;
+        g[b]->k = wb.k[b];
+      }
+      bt.problems += (long long)g.size();
+    }
+  } catch (const tn::Error& e) { bt.err_code = e.code; bt.err = e.what(); }
+  catch (const std::exception& e) { bt.err_code = -3; bt.err = e.what(); }
+  bt.pending.clear();
+  bt.nwaiting = 0;
+  bt.round++;
+  bt.cv.notify_all();
+}
+
+static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+  SvdBatcher& bt = *tl_batcher;
+  // the input matrix is complete, and every gather this thread enqueued from the previous round's workspace has finished,
+  // before the workspace can be overwritten by the next round
+  TN_CUDA(cudaStreamSynchronize(s));
+  BatchReq rq{&w, M, m, n, ld, tr, 0};
+  std::unique_lock<std::mutex> lk(bt.mu);
+  if (bt.err_code) throw tn::Error(bt.err_code, bt.err);
+  bt.pending.push_back(&rq);
+  bt.nwaiting++;
+  const unsigned long long my = bt.round;
+  if (bt.nwaiting >= bt.nactive) batcher_run_round(bt, s);
+  else bt.cv.wait(lk, [&] { return bt.round != my; });
+  if (bt.err_code) throw tn::Error(bt.err_code, bt.err);
+  return rq.k;
+}
+
+void svd_batcher_detach(cudaStream_t s) {
+  SvdBatcher* b = tl_batcher;
+  if (!b) return;
+  tl_batcher = nullptr;
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->nactive--;
+  if (b->nactive > 0 && b->nwaiting >= b->nactive && !b->pending.empty()) batcher_run_round(*b, s);
 }
 
 }  // namespace tn

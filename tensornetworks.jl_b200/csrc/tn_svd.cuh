@@ -2,6 +2,7 @@
 #pragma once
 #include "tn_common.cuh"
 #include <map>
+#include <vector>
 
 namespace tn {
 
@@ -32,6 +33,10 @@ struct SvdWork {
   int m = 0, n = 0, rows = 0, ncols = 0, ncols_pad = 0, ldz = 0, nsv = 0, k = 0, sweeps = 0;
   bool transposed = false;
   double last_off = 0;
+  // set by svd_factor when the calling thread takes part in a batching round (SvdBatcher): the factors live in a slot of a
+  // shared batched workspace and the gathers read them through this single-problem view
+  bool use_view = false;
+  SvdWork* bview = nullptr;
 };
 
 // Factorises the m x n column-major matrix M (leading dimension ld) and applies the reference's
@@ -74,6 +79,16 @@ void svd_batched_gather_U(SvdBatch& w, int b, cplx* U, long long ldu, bool times
 void svd_batched_gather_Vh(SvdBatch& w, int b, cplx* Vh, long long ldv, bool times_S, cudaStream_t s);
 void svd_batched_copy_S(SvdBatch& w, int b, double* S, cudaStream_t s);
 void svd_batched_free(SvdBatch& w);
+
+// Batching rounds across host threads (QJMC ensembles): every worker thread runs the ordinary single-trajectory code; when it
+// reaches svd_factor it parks its request, and once every active worker is parked the last one to arrive factorises all
+// requests -- grouped by shape -- with svd_batched_factor and wakes the others, which then gather their own factors.
+struct SvdBatcher;
+SvdBatcher* svd_batcher_create(int nworkers);      // all nworkers count as active from the start
+void svd_batcher_destroy(SvdBatcher* b);
+void svd_batcher_attach(SvdBatcher* b);            // the calling thread's svd_factor calls join the rounds from now on
+void svd_batcher_detach(cudaStream_t s);           // the calling thread leaves (may complete a round on stream s)
+long long svd_batcher_rounds(SvdBatcher* b, long long* problems);
 void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn

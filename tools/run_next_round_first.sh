@@ -6,9 +6,13 @@
 N=${1:-1}
 mkdir -p gpurun_out
 if [ "$N" = "1" ]; then
-  timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/next_gpu_tests.log 2>&1; tail -5 gpurun_out/next_gpu_tests.log
+  TN_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests -q -m gpu > gpurun_out/next_gpu_tests.log 2>&1; tail -5 gpurun_out/next_gpu_tests.log
   timeout 120 python tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check > gpurun_out/next_sharded_dmrg_1.jsonl 2> gpurun_out/next_sharded_dmrg_1.err
   cat gpurun_out/next_sharded_dmrg_1.jsonl; tail -3 gpurun_out/next_sharded_dmrg_1.err
+  # QJMC C4 shapes: plain multi-stream ensemble vs batching rounds
+  timeout 300 python tools/bench_qjmc.py --sites 64 --chi 256 --traj 32 --steps 2 --workers 16 > gpurun_out/next_qjmc_plain.jsonl 2> gpurun_out/next_qjmc_plain.err
+  TN_QJMC_BATCH=1 TN_QJMC_BATCH_STATS=1 timeout 300 python tools/bench_qjmc.py --sites 64 --chi 256 --traj 32 --steps 2 --workers 32 > gpurun_out/next_qjmc_batched.jsonl 2> gpurun_out/next_qjmc_batched.err
+  cat gpurun_out/next_qjmc_plain.jsonl gpurun_out/next_qjmc_batched.jsonl; tail -2 gpurun_out/next_qjmc_batched.err
   timeout 200 python bench.py > gpurun_out/next_bench.json 2> gpurun_out/next_bench.err; cat gpurun_out/next_bench.json
 else
   RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519"
