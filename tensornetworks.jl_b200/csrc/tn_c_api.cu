@@ -595,6 +595,7 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     if (batcher) {
       long long probs = 0; const long long rounds = svd_batcher_rounds(batcher, &probs);
       if (getenv("TN_QJMC_BATCH_STATS")) fprintf(stderr, "{\"qjmc_batching\": {\"workers\": %d, \"rounds\": %lld, \"svds\": %lld}}\n", nw, rounds, probs);
+      cudaSetDevice(device);
       svd_batcher_destroy(batcher);
     }
     if (err_code) throw tn::Error(err_code, "qjmc_ensemble: " + err);
