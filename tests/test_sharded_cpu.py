@@ -54,6 +54,10 @@ def _worker(rank, world, port, q):
     out = sh.apply(torch.from_numpy(np.reshape(theta, -1, order='F').copy()))
     got = out.numpy().reshape(chi, d, d, chi + 2, order='F')
     err = np.linalg.norm(got - want) / np.linalg.norm(want)
+    for ns in (2, 3, 6):        # pipelined variant: Theta's right bond in slices, stage 3 accumulating slice by slice
+        out = sh.apply_pipelined(torch.from_numpy(np.reshape(theta, -1, order='F').copy()), nslices=ns)
+        got = out.numpy().reshape(chi, d, d, chi + 2, order='F')
+        err = max(err, np.linalg.norm(got - want) / np.linalg.norm(want))
     res = run_ensemble(lambda t: (t, t * t), 7, rank, world, dist)
     q.put((rank, err, sorted(res.items())))
     dist.destroy_process_group()

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--traj", type=int, default=32)
     ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=0, help="heff: slices of Theta's right bond for apply_pipelined (0 = plain apply)")
     ap.add_argument("--lx", type=int, default=6)
     ap.add_argument("--ly", type=int, default=4)
     ap.add_argument("--sweeps", type=int, default=2)
@@ -44,8 +45,9 @@ def main():
         theta = cr(chi, d, d, chi)
         sh = ShardedHeff(L, R, M1, M2, rank, world, GpuContractor(ctx), "cuda", dist if world > 1 else None)
         th = torch.from_numpy(np.reshape(theta, -1, order='F').copy()).cuda()
+        run = (lambda: sh.apply_pipelined(th, a.pipeline, ctx.stream())) if a.pipeline > 0 else (lambda: sh.apply(th))
         for _ in range(2):
-            out = sh.apply(th)
+            out = run()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -53,7 +55,7 @@ def main():
         t0 = time.perf_counter()
         e0.record()
         for _ in range(a.steps):
-            out = sh.apply(th)
+            out = run()
         e1.record(); torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         dev_s = e0.elapsed_time(e1) * 1e-3       # CUDA events on the device (every stage ends with a device sync, so the
@@ -75,7 +77,7 @@ def main():
                 err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         chk = float(torch.view_as_real(out).abs().sum().item())
         if rank == 0:
-            print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "ms_per_matvec": sec * 1e3,
+            print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "pipeline_slices": a.pipeline, "ms_per_matvec": sec * 1e3,
                               "tflops_total": flops / sec / 1e12, "checksum": chk, "rel_err_vs_einsum": err,
                               "collectives": "NCCL reduce_scatter(T2 over w2) + all_reduce(out)" if world > 1 else "none"}), flush=True)
     elif a.what == "dmrg":
