@@ -99,3 +99,126 @@ def tebd(psi, terms, dt, tmax, save, observers=(), cutoff=1e-12, maxdim=0, mindi
                 ob.measure(step * dt, psi, normal, energy)
                 converged = converged or ob.checkdone()
     return psi, energy
+
+
+# ---------------------------------------------------------------------------------------------
+# Observers (host-side bookkeeping, same convergence rules as the reference)
+# ---------------------------------------------------------------------------------------------
+class TEBDNorm:
+    """tebd.jl:124-152: records the accumulated log-norm; converged when its slope stops changing."""
+
+    def __init__(self, tol=1e-10):
+        self.times, self.measurements, self.tol = [], [], tol
+
+    def measure(self, time, psi, norm, energy):
+        self.times.append(time)
+        self.measurements.append(norm)
+
+    def checkdone(self):
+        if len(self.times) < 3:
+            return False
+        m, t = self.measurements, self.times
+        e1 = (m[-1] - m[-2]) / (t[-1] - t[-2])
+        e2 = (m[-2] - m[-3]) / (t[-2] - t[-3])
+        if abs(e2 + e1) < 1e-8:
+            return abs(e2 - e1) < self.tol
+        return abs((e2 - e1) / (0.5 * (e2 + e1))) < self.tol
+
+
+class TEBDEnergy:
+    """tebd.jl:161-187: records the energy; converged on its relative change."""
+
+    def __init__(self, tol=1e-10):
+        self.times, self.measurements, self.tol = [], [], tol
+
+    def measure(self, time, psi, norm, energy):
+        self.times.append(time)
+        self.measurements.append(energy)
+
+    def checkdone(self):
+        if len(self.times) < 3:
+            return False
+        e1, e2 = self.measurements[-1], self.measurements[-2]
+        if 0.5 * abs(e2 + e1) < 1e-8:
+            return abs(e2 - e1) < self.tol
+        return abs(2 * (e2 - e1) / (e2 + e1)) < self.tol
+
+
+class TEBDOperators:
+    """tebd.jl:195-219: inner(st, psi, oplist, psi) at every save point (device-side tn_inner_oplist)."""
+
+    def __init__(self, terms):
+        self.times, self.measurements, self.terms = [], [], terms
+
+    def measure(self, time, psi, norm, energy):
+        self.times.append(time)
+        self.measurements.append(inner(psi, self.terms, psi))
+
+    def checkdone(self):
+        return False
+
+
+class QJMCOperators:
+    """qjmc.jl:238-264"""
+
+    def __init__(self, terms):
+        self.times, self.measurements, self.terms = [], [], terms
+
+    def measure(self, time, psi, jumps, jumptimes):
+        self.times.append(time)
+        self.measurements.append(inner(psi, self.terms, psi))
+
+
+class QJMCActivity:
+    """qjmc.jl:268-289 (without the HDF5 dump)"""
+
+    def __init__(self):
+        self.time, self.jumps = 0.0, 0
+
+    def measure(self, time, psi, jumps, jumptimes):
+        self.time, self.jumps = time, len(jumps)
+
+
+class QJMCEntropy:
+    """qjmc.jl:297-310: entanglement entropy of every bond at every save point"""
+
+    def __init__(self):
+        self.times, self.measurements = [], []
+
+    def measure(self, time, psi, jumps, jumptimes):
+        self.times.append(time)
+        self.measurements.append([psi.entropy(i) for i in range(1, len(psi))])
+
+
+def qjmc(psi, gates, jump_sites, jump_ops, jump_coeffs, tmax, dt, observers=(), save=0, uniforms=None, rng=None, cutoff=1e-12, maxdim=0,
+         mindim=1, classical=True):
+    """qjmc_simulation(st, psi, H, jumpops, tmax, dt, observers; save, ...) (qjmc.jl:28-167) with observers: the trajectory runs on the
+    device in chunks of ``savesteps`` steps (tn_qjmc_run), the observers are called between the chunks with psi still on the device.
+    ``gates`` is a device GateList of the Trotterised effective Hamiltonian (qjmc_gates, qjmc.jl:9-26).  Random numbers: 3 uniforms per
+    step, from ``uniforms`` (array of 3 * steps) or drawn here from ``rng`` (numpy Generator; default seed 0), so that a chunked run
+    and a single call see the same stream.  Returns (jumps, jumptimes)."""
+    from .api import qjmc_simulation
+    save = dt if save == 0 else save
+    steps = int(np.ceil(round(tmax / dt, 5)))
+    savesteps = max(1, int(np.ceil(round(save / dt))))
+    if uniforms is None:
+        rng = np.random.default_rng(0) if rng is None else rng
+        uniforms = rng.random(3 * steps)
+    uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+    if uniforms.size < 3 * steps:
+        raise _lib.TNError("need 3 uniforms per step")
+    jumps, jumptimes = [], []
+    for ob in observers:
+        ob.measure(0.0, psi, jumps, jumptimes)
+    done = 0
+    while done < steps:
+        n = min(savesteps, steps - done)
+        j, t, _ = qjmc_simulation(psi, gates, jump_sites, jump_ops, jump_coeffs, n, dt, uniforms=uniforms[3 * done:3 * (done + n)],
+                                  cutoff=cutoff, maxdim=maxdim, mindim=mindim, classical=classical)
+        jumps.extend(j)
+        jumptimes.extend(done * dt + x for x in t)
+        done += n
+        if done % savesteps == 0:
+            for ob in observers:
+                ob.measure(done * dt, psi, jumps, jumptimes)
+    return jumps, jumptimes
