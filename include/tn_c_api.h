@@ -196,6 +196,11 @@ int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* co
 int32_t tn_gates_free(tn_gates* g);
 /* applygates!(psi, gates; cutoff, maxdim, mindim): gatelist.jl:191-227 (MPS rank 1 or MPO rank 2) */
 int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc);
+/* applygates(psi, gates; error=true, kwargs...): gatelist.jl:191-223 -- also returns the product over the two-site gates of the
+ * truncation fidelity |<Theta', Theta'_truncated>|^2 (gatelist.jl:160-168); one extra GEMM, dot product and host read per gate.
+ * One-site gates contribute a factor 1 (the reference multiplies by |<O A, U>|^2 with U the gauge-moved tensor, a number that
+ * depends on the phases the SVD happens to pick). */
+int32_t tn_apply_gates_fidelity(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc, double* fidelity_out);
 
 /* One QJMC trajectory, algorithms/mps/qjmc.jl:59-164: per step applygates!, normalize!, emission rates (single-site jump
  * operators jump_ops[k] d x d at jump_sites[k], rates scaled by jump_coeffs[k]^2), jump test and jump update.

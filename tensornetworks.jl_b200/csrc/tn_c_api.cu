@@ -365,6 +365,13 @@ int32_t tn_gates_free(tn_gates* g) { return guard([&] { if (g) { gates_free(g->g
 int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t tr) {
   return guard([&] { apply_gates(psi->m, gates->g, T(tr)); psi->m->ctx->sync(); });
 }
+int32_t tn_apply_gates_fidelity(tn_mps* psi, tn_gates* gates, tn_trunc_t tr, double* fidelity_out) {
+  return guard([&] {
+    TN_CHECK(psi && gates && fidelity_out, "null pointer");
+    apply_gates(psi->m, gates->g, T(tr), fidelity_out);
+    psi->m->ctx->sync();
+  });
+}
 int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* jump_sites, const tn_cplx* jump_ops,
                     const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, const double* uniforms, uint64_t seed,
                     uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* jumps_out,

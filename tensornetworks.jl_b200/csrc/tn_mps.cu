@@ -667,7 +667,8 @@ void gates_free(Gates* g) {
   delete g;
 }
 
-static void applygate(Mps* psi, const Gate& g, bool direction, Trunc tr) {   // gatelist.jl:137-171 with error=false
+// gatelist.jl:137-171.  fid (optional): multiplied by the fidelity |<Theta', Theta'_truncated>|^2 of a two-site gate (error=true, :160-168)
+static void applygate(Mps* psi, const Gate& g, bool direction, Trunc tr, double* fid = nullptr) {
   Ctx* c = psi->ctx; cudaStream_t s = c->stream;
   int d = psi->d, inner = psi->rank == 2 ? d : 1;
   if (g.nsites == 1) {
@@ -685,9 +686,20 @@ static void applygate(Mps* psi, const Gate& g, bool direction, Trunc tr) {   // 
   zgemm_auto(mk((int)(cl * p), (int)(p * cr), (int)cm, A.p, idx1(1), idx1(cl * p), 0, B.p, idx1(1), idx1(cm), 0, th0, idx1(1), idx1(cl * p)), s);
   gate_mix2(th0, th1, g.dev, cl, d, inner, cr, s);
   mps_replacesites2(psi, th1, g.site, direction, false, tr);
+  if (fid) {
+    // contract the two new site tensors again and take the overlap with the untruncated Theta' (th1 is still intact)
+    Tensor& A2 = psi->sites[g.site - 1]; Tensor& B2 = psi->sites[g.site];
+    const long long k = A2.dims.back();
+    zgemm_auto(mk((int)(cl * p), (int)(p * cr), (int)k, A2.p, idx1(1), idx1(cl * p), 0, B2.p, idx1(1), idx1(k), 0, th0, idx1(1), idx1(cl * p)), s);
+    const cplx* xs[1] = {th1};
+    zdots(n, 1, xs, th0, c->dscal + 40, c->partials, s);
+    cplx v = read_scalar(c, 40);
+    *fid *= v.x * v.x + v.y * v.y;
+  }
 }
 
-void apply_gates(Mps* psi, Gates* g, Trunc tr) {   // gatelist.jl:191-227
+void apply_gates(Mps* psi, Gates* g, Trunc tr, double* fid) {   // gatelist.jl:191-227 (fid != nullptr: applygates with error=true)
+  if (fid) *fid = 1.0;
   TN_CHECK(g->d == psi->d, "gate / MPS physical dimension mismatch");
   for (auto& row : g->rows) {
     if (row.empty()) continue;
@@ -699,7 +711,7 @@ void apply_gates(Mps* psi, Gates* g, Trunc tr) {   // gatelist.jl:191-227
       const Gate& gt = row[(direction ? n + 1 - i : i) - 1];
       int ctr = direction ? gt.site + gt.nsites - 1 : gt.site;
       mps_movecenter(psi, ctr, tr);
-      applygate(psi, gt, direction, tr);
+      applygate(psi, gt, direction, tr, fid);
     }
   }
 }

@@ -115,7 +115,7 @@ void zconj_inplace(long long n, cplx* x, cudaStream_t s);
 void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, double* energy, long long* maxbond);
 Gates* gates_create(Ctx* c, int d, int nrows, const int* counts, const int* sites, const int* nsites, const cplx* const* host_gates);
 void gates_free(Gates* g);
-void apply_gates(Mps* psi, Gates* g, Trunc tr);
+void apply_gates(Mps* psi, Gates* g, Trunc tr, double* fid = nullptr);   // fid: product of the gates' truncation fidelities (error=true)
 void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cplx* out_host);
 void inner_oplist(Mps* bra, Mps* ket, int nterms, const int* nops, const int* op_sites, const cplx* ops_host, const cplx* coeffs,
                   cplx* out_host);

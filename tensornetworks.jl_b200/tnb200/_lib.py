@@ -97,6 +97,7 @@ PROTOTYPES = {
     "tn_gates_upload": [P, I32, I32, pI32, pI32, pI32, PP, PP],
     "tn_gates_free": [P],
     "tn_apply_gates": [P, P, tn_trunc_t],
+    "tn_apply_gates_fidelity": [P, P, tn_trunc_t, pF64],
     "tn_qjmc_run": [P, P, I32, pI32, P, pF64, I32, F64, tn_trunc_t, pF64, U64, U64, P, I32, P, pI32, pF64, I32, pI32, I32],
     "tn_inner_oplist": [P, P, I32, pI32, pI32, P, P, P],
     "tn_qjmc_ensemble": [I32, I32, I32, C.POINTER(C.c_uint64), I32, I32, pI64, PP, I32, I32, pI32, pI32, pI32, PP, I32, pI32, P, pF64,

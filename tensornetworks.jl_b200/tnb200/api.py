@@ -554,9 +554,15 @@ def vmps_sweeps(psi, Vs, minsweeps=2, maxsweeps=200, tol=1e-10, numconverges=3, 
     return psi
 
 
-def applygates(psi, gates, cutoff=0.0, maxdim=0, mindim=1):
-    """applygates!(psi, gates; kwargs...): gatelist.jl:225-227."""
-    check(psi.lib.tn_apply_gates(psi.h, gates.h, Trunc(cutoff, maxdim, mindim)))
+def applygates(psi, gates, cutoff=0.0, maxdim=0, mindim=1, error=False):
+    """applygates!(psi, gates; kwargs...): gatelist.jl:225-227; with ``error=True`` applygates(...; error=true) (:191-223), which
+    returns the product of the two-site gates' truncation fidelities."""
+    if not error:
+        check(psi.lib.tn_apply_gates(psi.h, gates.h, Trunc(cutoff, maxdim, mindim)))
+        return None
+    f = C.c_double()
+    check(psi.lib.tn_apply_gates_fidelity(psi.h, gates.h, Trunc(cutoff, maxdim, mindim), C.byref(f)))
+    return f.value
 
 
 def tebd(psi, gates, nsteps, energy_fn=None, nsave=1, cutoff=1e-12, maxdim=0, mindim=1, norm=0.0, observers=()):
