@@ -13,7 +13,8 @@ src/structures/mps/projmps.jl:107-134) = 3 contraction launches on the GPU.
              Theta H2D and result D2H inside the timed region, environments resident (they are the
              state the reference's ProjMPS object carries between calls).
   roofline   dominant kernel tn::zgemm_sk_kernel<4,1,4,4,true> (the two chi^3 contractions), live CUDA events.
-  extras     DMRG sweep wall time on the C2 chain at maxdim 64/128/256 (the other half of BASELINE.json's metric).
+  extras     DMRG sweep wall time on the C2 chain at maxdim 64/128/256 and a bounded QJMC ensemble sample at the C4 shapes
+             (the other parts of BASELINE.json's metric).
   cpu_baseline / --impl reference: the oracle's restatement of the reference's product() in the
              REFERENCE contraction order, NumPy/OpenBLAS with all host threads, bounded sample.
 N > 1: the chi = 1024 matvec does not shard: N independent replicas, scaling "weak".
@@ -121,6 +122,28 @@ def dmrg_sweep_sample(ctx, N=100, chis=(64, 128, 256)):
         out.append({"maxdim": chi, "maxbond": mb.value, "seconds_per_sweep": dt, "energy": e.value, "gpu_launches": c1["launches"] - c0["launches"],
                     "heff_applications": c1["matvecs"] - c0["matvecs"], "svds": c1["svds"] - c0["svds"]})
     return {"config": "C2 XXZ chain N=100 w=5 two-site DMRG, cutoff=1e-12, random chi=8 start, 2 sweeps per maxdim (2nd timed)", "sweeps": out}
+
+
+def qjmc_sample(device, N=64, chi=256, traj=16, workers=16, steps=1):
+    """Third part of BASELINE.json's metric: QJMC trajectory throughput at the C4 shapes (dissipative Ising chain N=64, chi=256,
+    cutoff=0, seeded random canonical start; tools/bench_qjmc.py is the full tool).  A bounded sample: ``traj`` trajectories x
+    ``steps`` steps on ``workers`` worker streams after one warm-up step per worker, wall clock around tn_qjmc_ensemble."""
+    import tnb200
+    from tnb200 import models
+    gamma, dt = 0.1, 5e-3
+    onsite = -1j * (1.0 * models.X + 20.0 * models.Z) - 0.5 * gamma * (models.SM.conj().T @ models.SM)
+    bond = -1j * 10.0 * np.kron(models.Z, models.Z)
+    ss, gg = models.trotter_gates(N, onsite, bond, dt, evol="imag", order=2)
+    tens = models.random_canonical_mps(N, D, chi, seed=1)
+    args = (tens, 1, ss, gg, list(range(1, N + 1)), [models.SM] * N, [np.sqrt(gamma)] * N)
+    kw = dict(workers=workers, device=device, seed=0, obs_op=models.Z, cutoff=0.0, maxdim=chi)
+    tnb200.qjmc_ensemble(*args, 1, dt, list(range(10 ** 6, 10 ** 6 + workers)), save_every=1, **kw)      # warm-up
+    t0 = time.perf_counter()
+    nj, _, _, obs = tnb200.qjmc_ensemble(*args, steps, dt, list(range(traj)), save_every=steps, **kw)
+    sec = time.perf_counter() - t0
+    return {"config": f"C4 shapes: N={N}, chi={chi}, cutoff=0, {traj} trajectories x {steps} step(s), {workers} worker streams on one GPU",
+            "seconds": sec, "traj_steps_per_s": traj * steps / sec, "traj_per_s_at_20_steps": traj * steps / sec / 20.0,
+            "jumps": int(nj.sum()), "mean_sum_z": float(np.real(obs[:, -1, :]).sum() / traj)}
 
 
 class ClockSampler:
@@ -316,6 +339,10 @@ def main():
             pass
         if world == 1 and not args.no_extras:
             line["extras"] = {"dmrg_sweep": dmrg_sweep_sample(ctx)}
+            try:
+                line["extras"]["qjmc"] = qjmc_sample(local)
+            except Exception as e:          # the sample is a by-product: never lose the bench line over it
+                line["extras"]["qjmc"] = {"error": repr(e)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             tf, calls, secs, cores, ref_out = cpu_reference_arm(chi, budget_s=20.0)
             err = float(np.linalg.norm(ref_out.reshape(-1, order='F') - dev_out) / np.linalg.norm(dev_out))
