@@ -12,8 +12,7 @@
 //   until every pair's Gram matrix is diagonal to sqrt(m)*eps.  Then sigma_j = ||W(:,j)||, U = W/sigma,
 //   sorted on device; the truncation rank is computed on device with the reference's exact rule.
 #include "tn_svd.cuh"
-#include <condition_variable>
-#include <mutex>
+#include "tn_rounds.h"
 #include <tuple>
 #include <cmath>
 #include <cstring>
@@ -1124,56 +1123,43 @@ void svd_batched_free(SvdBatch& w) {
 // ================================================================================================
 struct BatchReq { SvdWork* w; const cplx* M; int m, n; long long ld; Trunc tr; int k; };
 struct SvdBatcher {
-  std::mutex mu;
-  std::condition_variable cv;
-  int nactive = 0, nwaiting = 0;
-  unsigned long long round = 0;
-  long long problems = 0;
-  std::vector<BatchReq*> pending;
+  Rounds<BatchReq> rounds;
   typedef std::tuple<int, int, long long, double, long long, long long> Key;   // m, n, ld, cutoff, maxdim, mindim
   std::map<Key, SvdBatch> work;                                               // one stacked workspace per shape group
-  int err_code = 0; std::string err;
+  explicit SvdBatcher(int n) : rounds(n) {}
 };
 
-SvdBatcher* svd_batcher_create(int nworkers) { auto* b = new SvdBatcher(); b->nactive = nworkers; return b; }
+SvdBatcher* svd_batcher_create(int nworkers) { return new SvdBatcher(nworkers); }
 void svd_batcher_destroy(SvdBatcher* b) {
   if (!b) return;
   for (auto& kv : b->work) svd_batched_free(kv.second);
   delete b;
 }
 void svd_batcher_attach(SvdBatcher* b) { tl_batcher = b; }
-long long svd_batcher_rounds(SvdBatcher* b, long long* problems) { if (problems) *problems = b->problems; return (long long)b->round; }
+long long svd_batcher_rounds(SvdBatcher* b, long long* problems) { if (problems) *problems = b->rounds.requests(); return (long long)b->rounds.rounds(); }
 
-// Called with bt.mu held by the thread that completes the round; factorises every parked request on stream s.
-static void batcher_run_round(SvdBatcher& bt, cudaStream_t s) {
-  try {
-    // data-dependent bond dimensions produce many shapes over a long run: drop the cached workspaces now and then (safe here:
-    // every worker synchronised its stream before parking, so nobody still reads the previous round's factors)
-    if (bt.work.size() > 48) { for (auto& kv : bt.work) svd_batched_free(kv.second); bt.work.clear(); }
-    std::map<SvdBatcher::Key, std::vector<BatchReq*>> groups;
-    for (BatchReq* r : bt.pending) groups[SvdBatcher::Key(r->m, r->n, r->ld, r->tr.cutoff, r->tr.maxdim, r->tr.mindim)].push_back(r);
-    for (auto& kv : groups) {
-      std::vector<BatchReq*>& g = kv.second;
-      SvdBatch& wb = bt.work[kv.first];
-      std::vector<const cplx*> ptrs;
-      for (BatchReq* r : g) ptrs.push_back(r->M);
-      svd_batched_factor(wb, (int)g.size(), ptrs.data(), g[0]->m, g[0]->n, g[0]->ld, g[0]->tr, s);   // ends with a stream synchronise
-      for (size_t b = 0; b < g.size(); ++b) {
-        SvdWork& w = *g[b]->w;
-        if (!w.bview) w.bview = new SvdWork();
-        *w.bview = batch_view(wb, (int)b);
-        w.use_view = true;
-        w.k = wb.k[b]; w.m = wb.m; w.n = wb.n; w.sweeps = wb.sweeps;
-        g[b]->k = wb.k[b];
-      }
-      bt.problems += (long long)g.size();
+// One round (called by Rounds with its lock held, by the thread that completes the round): factorises every parked request on stream s.
+static void batcher_run_round(SvdBatcher& bt, std::vector<BatchReq*>& pending, cudaStream_t s) {
+  // data-dependent bond dimensions produce many shapes over a long run: drop the cached workspaces now and then (safe here:
+  // every worker synchronised its stream before parking, so nobody still reads the previous round's factors)
+  if (bt.work.size() > 48) { for (auto& kv : bt.work) svd_batched_free(kv.second); bt.work.clear(); }
+  std::map<SvdBatcher::Key, std::vector<BatchReq*>> groups;
+  for (BatchReq* r : pending) groups[SvdBatcher::Key(r->m, r->n, r->ld, r->tr.cutoff, r->tr.maxdim, r->tr.mindim)].push_back(r);
+  for (auto& kv : groups) {
+    std::vector<BatchReq*>& g = kv.second;
+    SvdBatch& wb = bt.work[kv.first];
+    std::vector<const cplx*> ptrs;
+    for (BatchReq* r : g) ptrs.push_back(r->M);
+    svd_batched_factor(wb, (int)g.size(), ptrs.data(), g[0]->m, g[0]->n, g[0]->ld, g[0]->tr, s);   // ends with a stream synchronise
+    for (size_t b = 0; b < g.size(); ++b) {
+      SvdWork& w = *g[b]->w;
+      if (!w.bview) w.bview = new SvdWork();
+      *w.bview = batch_view(wb, (int)b);
+      w.use_view = true;
+      w.k = wb.k[b]; w.m = wb.m; w.n = wb.n; w.sweeps = wb.sweeps;
+      g[b]->k = wb.k[b];
     }
-  } catch (const tn::Error& e) { bt.err_code = e.code; bt.err = e.what(); }
-  catch (const std::exception& e) { bt.err_code = -3; bt.err = e.what(); }
-  bt.pending.clear();
-  bt.nwaiting = 0;
-  bt.round++;
-  bt.cv.notify_all();
+  }
 }
 
 static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
@@ -1182,14 +1168,8 @@ static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld,
   // before the workspace can be overwritten by the next round
   TN_CUDA(cudaStreamSynchronize(s));
   BatchReq rq{&w, M, m, n, ld, tr, 0};
-  std::unique_lock<std::mutex> lk(bt.mu);
-  if (bt.err_code) throw tn::Error(bt.err_code, bt.err);
-  bt.pending.push_back(&rq);
-  bt.nwaiting++;
-  const unsigned long long my = bt.round;
-  if (bt.nwaiting >= bt.nactive) batcher_run_round(bt, s);
-  else bt.cv.wait(lk, [&] { return bt.round != my; });
-  if (bt.err_code) throw tn::Error(bt.err_code, bt.err);
+  try { bt.rounds.submit(&rq, [&](std::vector<BatchReq*>& pending) { batcher_run_round(bt, pending, s); }); }
+  catch (const std::runtime_error& e) { throw tn::Error(-3, std::string("svd batching round: ") + e.what()); }
   return rq.k;
 }
 
@@ -1197,9 +1177,7 @@ void svd_batcher_detach(cudaStream_t s) {
   SvdBatcher* b = tl_batcher;
   if (!b) return;
   tl_batcher = nullptr;
-  std::unique_lock<std::mutex> lk(b->mu);
-  b->nactive--;
-  if (b->nactive > 0 && b->nwaiting >= b->nactive && !b->pending.empty()) batcher_run_round(*b, s);
+  b->rounds.leave([&](std::vector<BatchReq*>& pending) { batcher_run_round(*b, pending, s); });
 }
 
 }  // namespace tn
