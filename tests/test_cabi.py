@@ -43,3 +43,23 @@ def test_product_package_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_null_handles_are_errors_not_crashes():
+    """Every entry point that takes a handle rejects NULL with TN_ERR_INVALID and a message (no GPU needed: the check comes first)."""
+    import ctypes as C
+    import tnb200
+    from tnb200 import _lib
+    lib = tnb200.load()
+    v = _lib.tn_cplx()
+    k = C.c_int64()
+    tr = _lib.tn_trunc_t(0.0, 0, 1)
+    calls = [lambda: lib.tn_mps_norm(None, C.byref(v)), lambda: lib.tn_mps_normalize(None), lambda: lib.tn_mps_movecenter(None, 1, tr),
+             lambda: lib.tn_env_movecenter(None, 1), lambda: lib.tn_env_calculate(None, C.byref(v)), lambda: lib.tn_envsum_movecenter(None, 1),
+             lambda: lib.tn_apply_gates(None, None, tr), lambda: lib.tn_mps_maxbonddim(None, C.byref(k)), lambda: lib.tn_sync(None),
+             lambda: lib.tn_mpo_compress(None, tr)]
+    for f in calls:
+        assert f() == -1
+        assert b"null" in lib.tn_last_error()
+    # the free functions accept NULL like free()
+    assert lib.tn_mps_free(None) == 0 and lib.tn_env_free(None) == 0 and lib.tn_gates_free(None) == 0 and lib.tn_envsum_free(None) == 0
