@@ -150,13 +150,24 @@ class GMPS:
     def movecenter(self, idx, cutoff=0.0, maxdim=0, mindim=1):   # gmps.jl:90-112
         check(self.lib.tn_mps_movecenter(self.h, int(idx), Trunc(cutoff, maxdim, mindim)))
 
+    def _span_size(self, site, nsites):
+        """number of elements of the tensor spanning sites site .. site+nsites-1 (host buffers are checked before they cross the ABI)"""
+        if not (1 <= site and site + nsites - 1 <= self._N):
+            raise _lib.TNError("site out of range")
+        dims = self.dims()
+        return int(dims[site - 1][0]) * (self.dim ** self.rank) ** nsites * int(dims[site + nsites - 2][-1])
+
     def replacesites(self, A, site, direction=False, normalize=False, cutoff=0.0, maxdim=0, mindim=1):   # gmps.jl:199-267
         A = _f(A)
+        if A.size != self._span_size(int(site), 2):
+            raise _lib.TNError("replacesites: A does not have the size of the two-site tensor at this site")
         check(self.lib.tn_mps_replacesites(self.h, _ptr(A), int(site), int(bool(direction)), int(bool(normalize)),
                                            Trunc(cutoff, maxdim, mindim)))
 
     def applyop(self, site, op):                  # mps.jl:141-152
         op = _f(op)
+        if op.shape != (self.dim, self.dim):
+            raise _lib.TNError("applyop: the operator must be d x d")
         check(self.lib.tn_mps_applyop(self.h, int(site), _ptr(op)))
 
     def spectrum(self, site):                     # singular values across bond (site, site+1); gmps.jl:184-189
@@ -245,6 +256,8 @@ class ProjMPS:
         if nsites not in (1, 2):
             raise _lib.TNError("nsites must be 1 or 2")
         A = _f(A)
+        if A.shape != self._local_shape(direction, nsites):
+            raise _lib.TNError(f"product: A has shape {A.shape}, the sites at the centre need {self._local_shape(direction, nsites)}")
         if out is None:
             out = np.zeros(A.shape, dtype=np.complex128, order='F')
         elif not (out.dtype == np.complex128 and out.flags.f_contiguous and out.size == A.size):
@@ -257,6 +270,8 @@ class ProjMPS:
 
     def _local_shape(self, direction, nsites):
         site = self.center - nsites + 1 if direction else self.center
+        if not (1 <= site and site + nsites - 1 <= len(self.ket)):
+            raise _lib.TNError("the sites fall outside the chain")
         dims = self.ket.dims()
         return (int(dims[site - 1][0]),) + (self.ket.dim,) * nsites + (int(dims[site + nsites - 2][-1]),)
 
@@ -274,6 +289,8 @@ class ProjMPS:
     def eigsolve(self, A0, direction=False, krylovdim=3, maxiter=2, tol=1e-14):
         """KrylovKit eigsolve(Heff, A0, 1, :SR; ...) as called at dmrg.jl:51-53."""
         A0 = _f(A0)
+        if A0.shape != self._local_shape(direction, 2):
+            raise _lib.TNError(f"eigsolve: A0 has shape {A0.shape}, the sites at the centre need {self._local_shape(direction, 2)}")
         out = np.zeros(A0.shape, dtype=np.complex128, order='F')
         e, n = C.c_double(), C.c_int32()
         check(self.lib.tn_eigsolve(self.h, _ptr(A0), int(bool(direction)), tn_lanczos_t(krylovdim, maxiter, tol), C.byref(e), _ptr(out), C.byref(n)))
@@ -318,6 +335,8 @@ class ProjMPSSum:
 
     def product(self, A, direction=False, nsites=2):
         A = _f(A)
+        if A.shape != self.projs[0]._local_shape(direction, nsites):
+            raise _lib.TNError(f"product: A has shape {A.shape}, the sites at the centre need {self.projs[0]._local_shape(direction, nsites)}")
         out = np.zeros(A.shape, dtype=np.complex128, order='F')
         check(self.lib.tn_envsum_product(self.h, _ptr(A), int(bool(direction)), int(nsites), _ptr(out)))
         return out
