@@ -27,6 +27,7 @@ typedef struct tn_mps tn_mps;     /* GMPS of rank 1 (MPS) or 2 (MPO): structures
 typedef struct tn_env tn_env;     /* ProjMPS: structures/mps/projmps.jl:1-8 */
 typedef struct tn_gates tn_gates; /* GateList: structures/mps/gatelist.jl:8-13 */
 typedef struct tn_envsum tn_envsum; /* ProjMPSSum: structures/mps/projmpssum.jl:1-4 */
+typedef struct tn_imps tn_imps;   /* iGMPS of rank 1 in Vidal form: structures/mps/igmps.jl:8-17 */
 
 /* kwargs of svd(): tensors.jl:170-172 (cutoff=0, maxdim=0 meaning unlimited, mindim=1) */
 typedef struct { double cutoff; int64_t maxdim; int64_t mindim; } tn_trunc_t;
@@ -201,6 +202,20 @@ int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc);
  * One-site gates contribute a factor 1 (the reference multiplies by |<O A, U>|^2 with U the gauge-moved tensor, a number that
  * depends on the phases the SVD happens to pick). */
 int32_t tn_apply_gates_fidelity(tn_mps* psi, tn_gates* gates, tn_trunc_t trunc, double* fidelity_out);
+
+/* ---- infinite TEBD (Vidal form): algorithms/mps/itebd.jl:71-119 for a two-site unit cell -------------------------------- */
+/* iGMPS upload: L = 2 cell tensors (D_{i-1}, d, D_i) with D_2 = D_0, and the singular values to the LEFT of each tensor
+ * (sing_ptrs[i]: D_{i-1} doubles), as the reference stores them (itebd.jl:78-83).  dims: L x 3 row-major. */
+int32_t tn_imps_create(tn_ctx* ctx, int32_t d, int32_t L, const int64_t* dims, const tn_cplx* const* site_ptrs,
+                       const double* const* sing_ptrs, tn_imps** out);
+int32_t tn_imps_free(tn_imps* p);
+int32_t tn_imps_dims(tn_imps* p, int64_t* dims /* L x 3 */);
+/* tensors[site], singulars[site] and norms[site] (any output may be NULL) */
+int32_t tn_imps_download(tn_imps* p, int32_t site, tn_cplx* tensor_out, double* singulars_out, double* norm_out);
+/* nsteps passes of _itebd_apply_gates_mps!(psi, gate, mindim, maxdim, cutoff) (itebd.jl:71-119): per pass the gate
+ * (o1,i1,o2,i2) on bond (1,2) then on bond (2,1); Theta = S_a G_a S_b G_b S_a, truncated SVD, G_a = S_a^-1 U, G_b = V^H S_a^-1,
+ * S_b normalised with the log of its norm added to norms[b]. */
+int32_t tn_itebd_apply_gate(tn_imps* p, const tn_cplx* gate_host, int32_t nsteps, tn_trunc_t trunc);
 
 /* One QJMC trajectory, algorithms/mps/qjmc.jl:59-164: per step applygates!, normalize!, emission rates (single-site jump
  * operators jump_ops[k] d x d at jump_sites[k], rates scaled by jump_coeffs[k]^2), jump test and jump update.

@@ -4,7 +4,7 @@ This package is a NumPy/SciPy restatement (column-major semantics, complex128,
 LAPACK ``zgesdd``) of the reference's algorithm for the path named in
 BASELINE.json: ``src/tensors.jl``, ``src/structures/mps/{gmps,mps,mpo,oplist,
 projmps,projmpssum,abstractprojmps,gatelist}.jl`` and
-``src/algorithms/mps/{dmrg,tebd,qjmc,vmps}.jl``.  Every function cites the reference
+``src/algorithms/mps/{dmrg,tebd,qjmc,vmps}.jl`` (and the gate step of ``itebd.jl``).  Every function cites the reference
 file:line it follows.
 
 PARITY UNPINNED BY THE REFERENCE: the reference ships no tests, fixtures or
@@ -35,5 +35,6 @@ from .gatelist import GateList, trotterize, applygate, applygates  # noqa: F401
 from .lanczos import eigsolve_lowest  # noqa: F401
 from .dmrg import dmrg  # noqa: F401
 from .vmps import vmps, vmps_sweeps  # noqa: F401
+from .itebd import IGMPS, iMPS, itebd_gate, itebd_apply_gates_mps  # noqa: F401
 from .tebd import tebd  # noqa: F401
 from .qjmc import qjmc_simulation, qjmc_gates, qjmc_emission_rates  # noqa: F401

@@ -532,6 +532,50 @@ int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* the
   });
 }
 
+// ---- infinite TEBD (Vidal form, two-site cell) ------------------------------------------------------------------
+struct tn_imps { IMps* m; };
+int32_t tn_imps_create(tn_ctx* ctx, int32_t d, int32_t L, const int64_t* dims, const tn_cplx* const* site_ptrs, const double* const* sing_ptrs,
+                       tn_imps** out) {
+  return guard([&] {
+    TN_CHECK(ctx && dims && site_ptrs && sing_ptrs && out, "tn_imps_create: null pointer");
+    std::vector<long long> dd((size_t)3 * L);
+    for (size_t i = 0; i < dd.size(); ++i) dd[i] = dims[i];
+    auto* h = new tn_imps();
+    try { h->m = imps_create(&ctx->c, d, L, dd.data(), reinterpret_cast<const cplx* const*>(site_ptrs), sing_ptrs); } catch (...) { delete h; throw; }
+    *out = h;
+  });
+}
+int32_t tn_imps_free(tn_imps* p) { return guard([&] { if (p) { imps_free(p->m); delete p; } }); }
+int32_t tn_imps_dims(tn_imps* p, int64_t* dims) {
+  return guard([&] {
+    TN_CHECK(p && dims, "tn_imps_dims: null pointer");
+    for (int i = 0; i < p->m->L; ++i) for (int k = 0; k < 3; ++k) dims[3 * i + k] = p->m->gam[i].dims[k];
+  });
+}
+int32_t tn_imps_download(tn_imps* p, int32_t site, tn_cplx* tensor_out, double* singulars_out, double* norm_out) {
+  return guard([&] {
+    TN_CHECK(p, "tn_imps_download: null handle");
+    IMps* m = p->m; Ctx* c = m->ctx;
+    TN_CHECK(site >= 1 && site <= m->L, "site index out of range");
+    if (tensor_out) TN_CUDA(cudaMemcpyAsync(tensor_out, m->gam[site - 1].p, (size_t)m->gam[site - 1].size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    if (singulars_out) TN_CUDA(cudaMemcpyAsync(singulars_out, m->sing[site - 1], (size_t)m->nsing[site - 1] * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    if (norm_out) *norm_out = m->norms[site - 1];
+  });
+}
+int32_t tn_itebd_apply_gate(tn_imps* p, const tn_cplx* gate_host, int32_t nsteps, tn_trunc_t tr) {
+  return guard([&] {
+    TN_CHECK(p && gate_host && nsteps >= 0, "tn_itebd_apply_gate: bad arguments");
+    IMps* m = p->m; Ctx* c = m->ctx;
+    const size_t ne = (size_t)m->d * m->d * m->d * m->d;
+    cplx* g = c->scratch[15].get(ne, c->stream);
+    TN_CUDA(cudaMemcpyAsync(g, gate_host, ne * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+    for (int i = 0; i < nsteps; ++i) itebd_apply_gate2(m, g, T(tr));
+    c->sync();
+  });
+}
+
 int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites, const tn_cplx* ops_host,
                         const tn_cplx* coeffs, tn_cplx* out) {
   return guard([&] { TN_CHECK(psi && phi, "tn_inner_oplist: null handle");

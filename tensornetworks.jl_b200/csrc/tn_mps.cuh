@@ -135,4 +135,16 @@ void envsum_project_phi(EnvSum* es, int site, int nsites, cplx* out);           
 void dmrg_halfsweep_sum(Mps* psi, EnvSum* es, bool direction, int nsites, Lanczos lz, Trunc tr, double* energy, long long* maxbond);
 void vmps_halfsweep(Mps* psi, EnvSum* es, bool direction, int nsites, Trunc tr, long long* maxbond);
 
+// --- infinite TEBD, two-site cell (tn_itebd.cu) -----------------------------------------------------------------------
+struct IMps {                      // iGMPS of rank 1 (igmps.jl:8-17): singulars[i] sits to the left of tensors[i], periodic cell
+  Ctx* ctx; int d, L;
+  std::vector<Tensor> gam;          // Gamma_i (D_{i-1}, d, D_i)
+  std::vector<double*> sing;        // device, length D_{i-1}
+  std::vector<long long> nsing;
+  std::vector<double> norms;        // accumulated log-norms (itebd.jl:106-108)
+};
+IMps* imps_create(Ctx* c, int d, int L, const long long* dims, const cplx* const* host_sites, const double* const* host_sing);
+void imps_free(IMps* m);
+void itebd_apply_gate2(IMps* m, const cplx* gate_dev, Trunc tr);
+
 }  // namespace tn

@@ -153,6 +153,26 @@ void zaxpy_dev(long long n, cplx alpha, const cplx* h, const cplx* x, cplx* y, c
   count_launch(1);
 }
 
+__global__ void __launch_bounds__(256) scale_lr_kernel(const cplx* __restrict__ in, cplx* __restrict__ out, long long nl, long long nlm, long long total,
+                                                       const double* __restrict__ sl, int invl, const double* __restrict__ sr, int invr) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    double f = 1.0;
+    if (sl) { double v = sl[e % nl]; f *= invl ? 1.0 / v : v; }
+    if (sr) { double v = sr[e / nlm]; f *= invr ? 1.0 / v : v; }
+    cplx x = in[e];
+    out[e] = make_double2(x.x * f, x.y * f);
+  }
+}
+void scale_lr(const cplx* in, cplx* out, long long nl, long long nm, long long nr, const double* sl, bool invl, const double* sr, bool invr,
+              cudaStream_t s) {
+  const long long total = nl * nm * nr;
+  if (total <= 0) return;
+  int blocks = (int)std::min<long long>(148 * 8, (total + 255) / 256);
+  scale_lr_kernel<<<std::max(blocks, 1), 256, 0, s>>>(in, out, nl, nl * nm, total, sl, invl ? 1 : 0, sr, invr ? 1 : 0);
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
+
 // ---- gate mix -------------------------------------------------------------------------------
 // Tensor viewed as (l, i1, p1, i2, p2, r) with p1,p2 of extent `inner` (1 for an MPS).  One thread
 // per (l, p1, p2, r) point applies the d^2 x d^2 gate to the d^2 (i1,i2) fibre: reads and writes are

@@ -21,6 +21,11 @@ void zaxpy(long long n, cplx alpha, const cplx* x, cplx* y, cudaStream_t s);
 // y += alpha * h[0] * x   (h in device memory: a dot product that never visits the host)
 void zaxpy_dev(long long n, cplx alpha, const cplx* h, const cplx* x, cplx* y, cudaStream_t s);
 
+// out(l, m, r) = f(sl[l]) * in(l, m, r) * f(sr[r]) with real scale vectors (nullptr = 1) and f(x) = x or 1/x: the diagonal
+// singular-value matrices of a Vidal-form MPS (itebd.jl:78-83, :101-102) applied without forming diag() or a GEMM
+void scale_lr(const cplx* in, cplx* out, long long nl, long long nm, long long nr, const double* sl, bool invl, const double* sr, bool invr,
+              cudaStream_t s);
+
 // Two-site gate mix (reference gatelist.jl:149-154):
 //   out(l, o1, [p1], o2, [p2], r) = sum_{i1,i2} G(o1,i1,o2,i2) * in(l, i1, [p1], i2, [p2], r)
 // d = physical dim, inner = d for rank-2 (extra passive physical index per site) else 1.

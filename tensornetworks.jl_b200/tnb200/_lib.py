@@ -94,6 +94,11 @@ PROTOTYPES = {
     "tn_mps_upload_site_dev": [P, I32, pI64, P],
     "tn_memcpy_dev": [P, P, P, I64],
     "tn_eigsolve_fn": [P, I64, P, P, tn_lanczos_t, APPLY_FN, P, pF64, pI32],
+    "tn_imps_create": [P, I32, I32, pI64, PP, PP, PP],
+    "tn_imps_free": [P],
+    "tn_imps_dims": [P, pI64],
+    "tn_imps_download": [P, I32, P, pF64, pF64],
+    "tn_itebd_apply_gate": [P, P, I32, tn_trunc_t],
     "tn_gates_upload": [P, I32, I32, pI32, pI32, pI32, PP, PP],
     "tn_gates_free": [P],
     "tn_apply_gates": [P, P, tn_trunc_t],

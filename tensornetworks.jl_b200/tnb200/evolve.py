@@ -3,6 +3,8 @@ operator lists given as ``terms`` = [(ops, sites, coeff)] with d x d operator ma
 (gatelist.jl:75-121 + oplist.jl:134-183; 2^2 x 2^2 matrix exponentials), everything that touches the MPS on the device
 (tn_apply_gates, tn_mps_norm, tn_mps_normalize, tn_inner_oplist).  Interaction range <= 2 sites (the C ABI applies one- and
 two-site gates); the projector branch (tebd.jl:22-41,67-73) goes through tnb200.vmps."""
+import ctypes as C
+
 import numpy as np
 import scipy.linalg as sla
 
@@ -222,3 +224,121 @@ def qjmc(psi, gates, jump_sites, jump_ops, jump_coeffs, tmax, dt, observers=(), 
             for ob in observers:
                 ob.measure(done * dt, psi, jumps, jumptimes)
     return jumps, jumptimes
+
+
+# ---------------------------------------------------------------------------------------------
+# Infinite TEBD (Vidal form, two-site cell): algorithms/mps/itebd.jl
+# ---------------------------------------------------------------------------------------------
+class IGMPS:
+    """Device-resident iGMPS of rank 1 (structures/mps/igmps.jl:8-17): ``tensors[i]`` (D_{i-1}, d, D_i), ``singulars[i]`` to the
+    left of ``tensors[i]``, periodic two-site cell."""
+
+    def __init__(self, dim, tensors, singulars=None, ctx=None):
+        from .api import Context, _f
+        self.ctx = ctx or Context.default()
+        self.lib = self.ctx.lib
+        ts = [_f(t) for t in tensors]
+        L = len(ts)
+        if singulars is None:
+            singulars = [np.ones(t.shape[0]) for t in ts]
+        ss = [np.ascontiguousarray(s, dtype=np.float64) for s in singulars]
+        if any(t.ndim != 3 for t in ts) or any(s.shape != (t.shape[0],) for s, t in zip(ss, ts)):
+            raise _lib.TNError("iGMPS: every cell tensor needs 3 indices and one singular value per left-bond state")
+        dims = np.array([t.shape for t in ts], dtype=np.int64).reshape(L, 3)
+        tp = (C.c_void_p * L)(*[t.ctypes.data for t in ts])
+        sp = (C.c_void_p * L)(*[s.ctypes.data for s in ss])
+        h = C.c_void_p()
+        _lib.check(self.lib.tn_imps_create(self.ctx.h, int(dim), L, dims.ctypes.data_as(C.POINTER(C.c_int64)), tp, sp, C.byref(h)))
+        self.h, self.dim, self._L = h, int(dim), L
+
+    @classmethod
+    def product(cls, length, A, ctx=None):
+        """iMPS(length, A): igmps.jl:53-59"""
+        A = np.asarray(A, dtype=np.complex128)
+        return cls(A.shape[0], [A.reshape(1, -1, 1) for _ in range(length)], ctx=ctx)
+
+    def __len__(self):
+        return self._L
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.tn_imps_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def dims(self):
+        d = np.zeros((self._L, 3), dtype=np.int64)
+        _lib.check(self.lib.tn_imps_dims(self.h, d.ctypes.data_as(C.POINTER(C.c_int64))))
+        return d
+
+    def maxbonddim(self):                        # igmps.jl:39
+        return int(self.dims()[:, 0].max())
+
+    def site(self, i):
+        """(tensors[i], singulars[i], norms[i]) downloaded from the device (1-based)"""
+        shape = tuple(int(x) for x in self.dims()[i - 1])
+        t = np.zeros(shape, dtype=np.complex128, order='F')
+        s = np.zeros(shape[0])
+        n = C.c_double()
+        _lib.check(self.lib.tn_imps_download(self.h, int(i), t.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return t, s, n.value
+
+    def apply_gate(self, gate, nsteps=1, cutoff=1e-12, maxdim=0, mindim=1):
+        """nsteps passes of _itebd_apply_gates_mps! (itebd.jl:71-119) with the two-site gate (o1,i1,o2,i2)"""
+        from .api import _f, Trunc
+        g = _f(gate)
+        if g.shape != (self.dim,) * 4:
+            raise _lib.TNError("iTEBD: the gate must have shape (d, d, d, d) for a two-site cell")
+        _lib.check(self.lib.tn_itebd_apply_gate(self.h, g.ctypes.data_as(C.c_void_p), int(nsteps), Trunc(cutoff, maxdim, mindim)))
+
+    def bond_energy(self, h2):
+        """<h> per bond from the Vidal form (exact for a canonical cell): mean over both bonds of <Theta|h|Theta>/<Theta|Theta>,
+        Theta = S_a G_a S_b G_b S_a.  Host-side on the downloaded cell (chi^3 d^2 work)."""
+        (ta, sa, _), (tb, sb, _) = self.site(1), self.site(2)
+        out = []
+        for (A, Sa), (B, Sb) in (((ta, sa), (tb, sb)), ((tb, sb), (ta, sa))):
+            th = np.einsum('l,lsm,m,mtr,r->lstr', Sa, A, Sb, B, Sa)
+            out.append(np.vdot(th, np.einsum('sutv,lutr->lstr', h2, th)) / np.vdot(th, th))
+        return complex(np.mean(out))
+
+
+def itebd(psi, terms, dt, tmax, observers=(), cutoff=1e-12, maxdim=0, mindim=1, evol="imag", save_time=None):
+    """itebd(st, psi, H, dt, tmax, observers; kwargs...) (itebd.jl:3-68) for a two-site cell: the gate is exp(+-dt * h) with h the sum of
+    the terms that start on site 1 of the cell (sitetensor(H, st, 1), itebd.jl:19-20; callers pass -H for imaginary time).  Observers are
+    called as measure(time, psi, energy) at multiples of ``save_time`` with energy = bond_energy of h (the reference measures through
+    infinite environments, igmps.jl:155-340, which stay out of scope)."""
+    d, L = psi.dim, len(psi)
+    if L != 2:
+        raise _lib.TNError("iTEBD on the device supports a two-site unit cell")
+    ident = np.eye(d, dtype=np.complex128)
+    h = np.zeros((d * d, d * d), dtype=np.complex128)
+    for ops, sites, coeff in terms:
+        o, s = _sorted_term(ops, sites)
+        if s[0] != 1:
+            continue
+        if s[-1] > 2:
+            raise _lib.TNError("iTEBD: terms must fit in the two-site cell")
+        mats = [o[s.index(q)] if q in s else ident for q in (1, 2)]
+        h = h + complex(coeff) * np.kron(mats[0], mats[1])
+    u = sla.expm((-1j if evol == "real" else 1) * dt * h)
+    gate = np.ascontiguousarray(u.reshape(d, d, d, d).transpose(0, 2, 1, 3))
+    h2 = h.reshape(d, d, d, d).transpose(0, 2, 1, 3)
+    nsteps = int(round(tmax / dt))
+    every = max(1, int(round((save_time or dt) / dt)))
+    energy = None
+    for ob in observers:
+        ob.measure(0.0, psi, psi.bond_energy(h2))
+    done = 0
+    while done < nsteps:
+        n = min(every, nsteps - done)
+        psi.apply_gate(gate, n, cutoff=cutoff, maxdim=maxdim, mindim=mindim)
+        done += n
+        if observers:
+            energy = psi.bond_energy(h2)
+            for ob in observers:
+                ob.measure(done * dt, psi, energy)
+            if any(getattr(ob, "checkdone", lambda: False)() for ob in observers):
+                break
+    return psi

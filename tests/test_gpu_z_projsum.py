@@ -420,3 +420,35 @@ def test_applygates_fidelity_matches_oracle():
         eg = tnb200.applygates(g, gg, error=True, **kw)
         assert abs(eo - eg) < 1e-9 * max(abs(eo), 1e-30), (eo, eg)
         assert psi.maxbonddim() == g.maxbonddim()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1",
+                    reason="iTEBD gate step on the device: written after the round's GPU time ran out; opt in with TN_RUN_UNVERIFIED=1")
+def test_itebd_step_matches_oracle():
+    """tn_itebd_apply_gate (itebd.jl:71-119, two-site cell) against the oracle: Schmidt values of both bonds, accumulated log-norms and
+    bond energy after the same number of steps; and the exact TFIM energy per site."""
+    from scipy.integrate import quad
+    from oracle.itebd import iMPS, itebd_gate, itebd_apply_gates_mps, bond_energy
+    from tnb200.evolve import IGMPS
+    sh = oracle.spinhalf()
+    g = 2.0
+    H = oracle.OpList(2)
+    H.add(["z", "z"], [1, 2], -1.0)
+    H.add("x", 1, -g)
+    h2 = H.sitetensor(sh, 1)
+    po = iMPS(2, np.array([1.0, 0.3]))
+    pg = IGMPS.product(2, np.array([1.0, 0.3]))
+    for dt, n in ((0.05, 60), (0.01, 60)):
+        gate = itebd_gate(sh, -1 * H, dt)
+        for _ in range(n):
+            itebd_apply_gates_mps(po, gate, maxdim=8, cutoff=1e-12)
+        pg.apply_gate(gate, n, cutoff=1e-12, maxdim=8)
+        for i in (1, 2):
+            t, s, nrm = pg.site(i)
+            assert s.shape == po.singulars[i - 1].shape
+            assert np.max(np.abs(s - po.singulars[i - 1])) < 1e-8
+            assert abs(nrm - po.norms[i - 1]) < 1e-8 * max(1.0, abs(po.norms[i - 1]))
+        assert abs(pg.bond_energy(h2) - bond_energy(po, h2)) < 1e-8
+    exact = -quad(lambda k: np.sqrt(1 + g * g - 2 * g * np.cos(k)), -np.pi, np.pi)[0] / (2 * np.pi)
+    pg.apply_gate(itebd_gate(sh, -1 * H, 0.01), 300, cutoff=1e-12, maxdim=8)
+    assert abs(pg.bond_energy(h2).real - exact) < 1e-4 * abs(exact)
