@@ -452,3 +452,61 @@ def test_itebd_step_matches_oracle():
     exact = -quad(lambda k: np.sqrt(1 + g * g - 2 * g * np.cos(k)), -np.pi, np.pi)[0] / (2 * np.pi)
     pg.apply_gate(itebd_gate(sh, -1 * H, 0.01), 300, cutoff=1e-12, maxdim=8)
     assert abs(pg.bond_energy(h2).real - exact) < 1e-4 * abs(exact)
+
+
+# ---- committed golden vectors of the projector branch (tests/golden/projector_golden.npz; no oracle call on the checked values) ----
+def _golden2():
+    import os
+    P2 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "projector_golden.npz"))
+
+    def lst(prefix):
+        out, i = [], 0
+        while f"{prefix}{i}" in P2:
+            out.append(P2[f"{prefix}{i}"])
+            i += 1
+        return out
+    return P2, lst
+
+
+def test_projector_branch_against_golden():
+    import tnb200
+    P2, lst = _golden2()
+    V, psi, H = tnb200.GMPS(1, 2, lst("pj_V"), 1), tnb200.GMPS(1, 2, lst("pj_psi"), 3), tnb200.GMPS(2, 2, lst("pj_H"), 0)
+    assert relerr(tnb200.ProjMPS(V, None, psi, center=3).project(None, False, 2), P2["pj_project2"]) < 1e-13
+    assert relerr(tnb200.ProjMPS(V, H, psi, center=3).project(None, False, 2), P2["pj_project2_mpo"]) < 1e-13
+    assert relerr(tnb200.ProjMPS(V, H, psi, center=3).project(None, False, 1), P2["pj_project1_mpo"]) < 1e-13
+    sq = tnb200.ProjMPS(V, None, psi, coeff=2.5, center=3, squared=True).product(P2["pj_theta"], False, 2)
+    assert relerr(sq, P2["pj_squared_out"]) < 1e-12
+    p1 = tnb200.ProjMPS(psi, H, psi, coeff=0.7 - 0.2j, center=3).product(P2["pj_A1"], False, 1)
+    assert relerr(p1, P2["pj_product1"]) < 1e-13
+
+
+def test_excited_dmrg_and_vmps_against_golden():
+    import tnb200
+    P2, lst = _golden2()
+    M = tnb200.GMPS(2, 2, lst("ex_mpo"), 0)
+    g0 = tnb200.GMPS(1, 2, lst("ex_gs"), int(P2["ex_gs_center"]))
+    p1 = tnb200.GMPS(1, 2, lst("ex_start"), 1)
+    hist = []
+    tnb200.dmrg(p1, M, g0, coeffs=[1.0, 20.0], maxdim=32, cutoff=1e-14, maxsweeps=30, history=hist)
+    e, want = np.array([h[1] for h in hist]), P2["ex_energy"]
+    assert e.shape == want.shape
+    assert np.max(np.abs((e - want) / want)) < 1e-7 and abs((e[-1] - want[-1]) / want[-1]) < 1e-10
+    a, b = tnb200.GMPS(1, 2, lst("vm_a"), 1), tnb200.GMPS(1, 2, lst("vm_b"), 1)
+    hist = []
+    tnb200.vmps(a, b, maxdim=4, cutoff=0.0, maxsweeps=6, history=hist)
+    c = np.array([h[1] for h in hist])
+    assert np.max(np.abs(c - P2["vm_cost"])) < 1e-8 * np.max(np.abs(P2["vm_cost"]))
+    assert [h[2] for h in hist] == list(P2["vm_maxbond"])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1", reason="iTEBD device step: opt in with TN_RUN_UNVERIFIED=1")
+def test_itebd_against_golden():
+    from tnb200.evolve import IGMPS
+    P2, _ = _golden2()
+    pg = IGMPS.product(2, np.array([1.0, 0.3]))
+    pg.apply_gate(P2["it_gate"], 40, cutoff=1e-12, maxdim=8)
+    for i, key in ((1, "it_sing1"), (2, "it_sing2")):
+        _, s, nrm = pg.site(i)
+        assert s.shape == P2[key].shape and np.max(np.abs(s - P2[key])) < 1e-8
+        assert abs(nrm - P2["it_norms"][i - 1]) < 1e-8 * max(1.0, abs(P2["it_norms"][i - 1]))
