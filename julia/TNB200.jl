@@ -159,6 +159,30 @@ function inner(st::Sitetypes, psi::CuGMPS, oplist::OpList, phi::CuGMPS)
     out
 end
 
+# MPO(st, H): assemble on the host as the reference does (mpo.jl:323-440), compress the bonds on the device (mpo.jl:443-457)
+compress!(O::CuGMPS; cutoff=1e-15, maxdim=0, mindim=1) =
+    check(ccall((:tn_mpo_compress, lib), Int32, (Ptr{Cvoid}, TruncT), O.h, TruncT(cutoff, maxdim, mindim)))
+# applygates(psi, gates; error=true): product of the two-site gates' truncation fidelities (gatelist.jl:160-168,191-223)
+function applygates(psi::CuGMPS, gates::CuGateList; cutoff=0.0, maxdim=0, mindim=1)
+    f = Ref{Cdouble}()
+    check(ccall((:tn_apply_gates_fidelity, lib), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, TruncT, Ref{Cdouble}), psi.h, gates.h, TruncT(cutoff, maxdim, mindim), f))
+    f[]
+end
+# iTEBD, two-site cell (itebd.jl:71-119): upload the iGMPS once, apply the cell gate nsteps times, read singular values / tensors back
+mutable struct CuiGMPS; h::Ptr{Cvoid}; dim::Int; ctx::Ctx; end
+function CuiGMPS(ctx::Ctx, psi::iGMPS)
+    L = length(psi.tensors)
+    dims = Int64[size(psi.tensors[i])[k] for i in 1:L for k in 1:3]
+    tens = [ComplexF64.(t) for t in psi.tensors]; sing = [Float64.(s) for s in psi.singulars]
+    h = Ref{Ptr{Cvoid}}()
+    GC.@preserve tens sing check(ccall((:tn_imps_create, lib), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Ptr{ComplexF64}}, Ptr{Ptr{Float64}}, Ref{Ptr{Cvoid}}),
+        ctx.h, psi.dim, L, dims, [pointer(t) for t in tens], [pointer(s) for s in sing], h))
+    m = CuiGMPS(h[], psi.dim, ctx); finalizer(x -> ccall((:tn_imps_free, lib), Int32, (Ptr{Cvoid},), x.h), m); m
+end
+itebd_apply_gates!(psi::CuiGMPS, gate::Array{ComplexF64,4}, nsteps::Int; cutoff=1e-12, maxdim=0, mindim=1) =
+    check(ccall((:tn_itebd_apply_gate, lib), Int32, (Ptr{Cvoid}, Ptr{ComplexF64}, Int32, TruncT), psi.h, gate, nsteps, TruncT(cutoff, maxdim, mindim)))
+
 # Many trajectories from one initial state (the loop a user writes around qjmc_simulation): tn_qjmc_ensemble hands them out to
 # `workers` host threads / CUDA streams inside the library; trajectory ids key the random numbers, so results do not depend on
 # the worker count or on which GPU ran them (shard ids over processes / GPUs as `ids = rank+1:world:ntraj`).
