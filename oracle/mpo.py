@@ -91,3 +91,31 @@ def MPO(st, H, cutoff=1e-15, maxdim=0, mindim=1):
         O[site] = np.tensordot(S, U, axes=([1], [0]))
         O[site - 1] = np.tensordot(O[site - 1], V, axes=([3], [1]))
     return O
+
+
+def adjoint(O):
+    """mpo.jl:32-39: Hermitian conjugate of an MPO (swap the physical indices, conjugate)."""
+    if O.rank != 2:
+        raise ValueError("The generalised MPS must be of rank 2 (an MPO).")
+    return GMPS(2, O.dim, [np.conj(np.transpose(t, (0, 2, 1, 3))) for t in O.tensors], O.center)
+
+
+def trace(*args):
+    """mpo.jl:229-252: trace of a product of MPOs, tr(O1 O2 ... On) (the measurement at the end of examples/thermal.jl)."""
+    if len(args) < 1:
+        raise ValueError("There must be atleast 1 MPO arguments (rank 2).")
+    if any(a.dim != args[0].dim for a in args) or any(len(a) != len(args[0]) for a in args):
+        raise ValueError("GMPS must share the same physical dim and length.")
+    if any(a.rank != 2 for a in args):
+        raise ValueError("Arguments must be GMPS of rank 2 (MPO).")
+    n = len(args)
+    prod = np.ones((1,) * n, dtype=np.complex128)            # one left bond per argument
+    for site in range(1, len(args[0]) + 1):
+        # prod(b1..bn) A1(b1,o,i,b1') A2(b2,i,i2,b2') ... with the first out index traced against the last in index
+        t = np.tensordot(prod, args[0][site], axes=([0], [0]))            # (b2..bn, o, i, b1')
+        for j in range(1, n):
+            t = np.tensordot(t, args[j][site], axes=([0, t.ndim - 2], [0, 1]))
+        # now (o, b1', ..., i_n, bn'): trace o against i_n (tensors.jl:75-78)
+        t = np.trace(t, axis1=0, axis2=t.ndim - 2)
+        prod = t
+    return prod.reshape(-1)[0]

@@ -342,3 +342,39 @@ def itebd(psi, terms, dt, tmax, observers=(), cutoff=1e-12, maxdim=0, mindim=1, 
             if any(getattr(ob, "checkdone", lambda: False)() for ob in observers):
                 break
     return psi
+
+
+# ---------------------------------------------------------------------------------------------
+# Thermal-state measurement of examples/thermal.jl: energy = trace(H, adjoint(U), U) / trace(adjoint(U), U) (mpo.jl:229-252)
+# ---------------------------------------------------------------------------------------------
+def doubled_state_tensors(U_tensors):
+    """An MPO tensor (w_l, s, t, w_r) is, byte for byte, an MPS tensor (w_l, (s,t), w_r) of physical dimension d^2 (s fastest)."""
+    return [np.reshape(np.asfortranarray(t), (t.shape[0], t.shape[1] * t.shape[2], t.shape[3]), order='F') for t in U_tensors]
+
+
+def doubled_operator_tensors(H_tensors):
+    """MPO of 1 (x) H^T on the doubled sites: H'(w, (s,t), (s',t'), w') = delta(s,s') M(w, t', t, w'), so that
+    tr(H U^dag U) = <<U| H' |U>> for the vectorised U (H then acts on U's second physical index)."""
+    out = []
+    for M in H_tensors:
+        M = np.asarray(M, dtype=np.complex128)
+        w, d, _, w2 = M.shape
+        X = np.einsum('su,wvtx->wstuvx', np.eye(d), M)
+        out.append(np.reshape(X, (w, d * d, d * d, w2), order='F'))
+    return out
+
+
+def thermal_energy(U, H_tensors):
+    """trace(H, adjoint(U), U) / trace(adjoint(U), U) for a device-resident MPO ``U`` (the state exp(-beta H / 2) of
+    examples/thermal.jl) and the host tensors of the Hamiltonian MPO, evaluated as an ordinary expectation value on the doubled
+    sites with the environment kernels (tn_env_create / tn_env_calculate at physical dimension d^2).  The energy is invariant
+    under rescaling U, so the unnormalised evolved MPO can be passed as is."""
+    from .api import GMPS, ProjMPS
+    if U.rank != 2:
+        raise _lib.TNError("thermal_energy: U must be an MPO (rank 2)")
+    d2 = U.dim * U.dim
+    Ud = GMPS(1, d2, doubled_state_tensors(U.tensors), 0, U.ctx)
+    Hd = GMPS(2, d2, doubled_operator_tensors(H_tensors), 0, U.ctx)
+    num = ProjMPS(Ud, Hd, Ud, center=1).calculate()
+    den = ProjMPS(Ud, None, Ud, center=1).calculate()
+    return num / den

@@ -510,3 +510,26 @@ def test_itebd_against_golden():
         _, s, nrm = pg.site(i)
         assert s.shape == P2[key].shape and np.max(np.abs(s - P2[key])) < 1e-8
         assert abs(nrm - P2["it_norms"][i - 1]) < 1e-8 * max(1.0, abs(P2["it_norms"][i - 1]))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1",
+                    reason="thermal energy on doubled sites (d^2 = 4 environments): opt in with TN_RUN_UNVERIFIED=1")
+def test_thermal_example_energy_matches_oracle():
+    """examples/thermal.jl at N = 8: evolve the identity MPO in imaginary time on the device, then
+    trace(H, adjoint(U), U) / trace(adjoint(U), U) through tnb200.evolve.thermal_energy against the oracle's trace()."""
+    import tnb200
+    from tnb200.evolve import thermal_energy
+    sh = oracle.spinhalf()
+    N, dt, steps = 8, 0.02, 15
+    Hl = tfim(N, 1.0, 0.0, 1.0)
+    gl = oracle.trotterize(sh, -1 * Hl, dt)
+    U = oracle.productMPO(sh, ["id"] * N)
+    g = tnb200.GMPS.from_host(U)
+    gg = tnb200.GateList.from_host(2, gl)
+    for _ in range(steps):
+        oracle.applygates(U, gl, cutoff=1e-10, maxdim=16)
+        tnb200.applygates(g, gg, cutoff=1e-10, maxdim=16)
+    M = oracle.MPO(sh, Hl)
+    want = oracle.trace(M, oracle.adjoint(U), U) / oracle.trace(oracle.adjoint(U), U)
+    got = thermal_energy(g, M.tensors)
+    assert abs(got - want) < 1e-8 * abs(want)

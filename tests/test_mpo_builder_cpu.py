@@ -98,3 +98,36 @@ def test_product_cylinder_terms_equal_the_oracle_oplist():
     for Lx, Ly in ((3, 3), (2, 4)):
         Ts = fsm_tensors(Lx * Ly, 2, pm.j1j2_cylinder_terms(Lx, Ly))
         assert np.allclose(_dense(Ts), dense_hamiltonian(sh, j1j2_cylinder(Lx, Ly)).toarray(), atol=1e-12)
+
+
+def test_doubled_site_identity_for_the_thermal_energy():
+    """tr(H U^dag U) / tr(U^dag U) (mpo.jl:229-252, the measurement of examples/thermal.jl) equals <<U|1 (x) H^T|U>> / <<U|U>> on
+    doubled sites -- the form tnb200.evolve.thermal_energy evaluates with the environment kernels."""
+    from gpu_util import random_mpo
+    from oracle.gmps import GMPS
+    from tnb200.evolve import doubled_state_tensors, doubled_operator_tensors
+    sh = oracle.spinhalf()
+    rng = np.random.default_rng(0)
+    N = 5
+    H = oracle.MPO(sh, tfim(N, 1.0, 0.3, 0.7))
+    Hc = random_mpo(rng, N, 2, 3)                        # a non-symmetric complex operator: the transpose matters
+    U = random_mpo(rng, N, 2, 4)
+    for Hx in (H, Hc):
+        want = oracle.trace(Hx, oracle.adjoint(U), U) / oracle.trace(oracle.adjoint(U), U)
+        Ud = GMPS(1, 4, doubled_state_tensors(U.tensors), 0)
+        Hd = GMPS(2, 4, doubled_operator_tensors(Hx.tensors), 0)
+        got = oracle.ProjMPS([Ud, Hd, Ud], rank=2, center=1).calculate() / oracle.ProjMPS([Ud, Ud], rank=1, center=1).calculate()
+        assert abs(got - want) < 1e-12 * abs(want)
+
+
+def test_oracle_trace_matches_dense():
+    from gpu_util import random_mpo
+    rng = np.random.default_rng(1)
+    A, B, C = random_mpo(rng, 4, 2, 3), random_mpo(rng, 4, 2, 2), random_mpo(rng, 4, 2, 4)
+
+    def dense(M):
+        return _dense([M[i] for i in range(1, len(M) + 1)])
+    for args in ((A,), (A, B), (A, B, C)):
+        want = np.trace(np.linalg.multi_dot([dense(x) for x in args]) if len(args) > 1 else dense(args[0]))
+        assert abs(oracle.trace(*args) - want) < 1e-12 * abs(want)
+    assert np.allclose(dense(oracle.adjoint(A)), dense(A).conj().T)
