@@ -71,6 +71,9 @@ int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta_host, int32_t site, 
 int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op_host /* d x d */);   /* mps.jl:141-152 */
 /* singular values across bond (site, site+1) -- the SVD inside entropy(): gmps.jl:184-189 */
 int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out);
+/* applyMPO(O, psi; kwargs...) = O * psi for an MPO and an MPS: mpo.jl:105-143.  Exact site products (bonds w * chi), right-going
+ * gauge sweep, then a truncating movecenter!(phi, 1; trunc).  Returns a new MPS handle (centre 1). */
+int32_t tn_mpo_apply(tn_mps* O, tn_mps* psi, tn_trunc_t trunc, tn_mps** out);
 /* Bond compression of an assembled MPO (or any GMPS): the two truncated-SVD sweeps at the end of MPO(st, H), mpo.jl:443-457
  * (and addMPOs, mpo.jl:296-311) -- right-going O[i] = U S, O[i+1] = V^H O[i+1]; left-going O[i] = S V^H, O[i-1] = O[i-1] U.
  * The reference's default there is cutoff = 1e-15.  Leaves the centre unset. */

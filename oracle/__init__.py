@@ -29,7 +29,7 @@ from .tensors import contract, moveidx, combineidxs, uncombineidxs, svd, tensor_
 from .sitetypes import Sitetypes, spinhalf  # noqa: F401
 from .oplist import OpList  # noqa: F401
 from .gmps import (GMPS, randomMPS, randomGMPS, productMPS, productMPO, inner, applyop)  # noqa: F401
-from .mpo import MPO, adjoint, trace  # noqa: F401
+from .mpo import MPO, adjoint, trace, applyMPO  # noqa: F401
 from .projmps import ProjMPS, ProjMPSSum  # noqa: F401
 from .gatelist import GateList, trotterize, applygate, applygates  # noqa: F401
 from .lanczos import eigsolve_lowest  # noqa: F401

@@ -119,3 +119,23 @@ def trace(*args):
         t = np.trace(t, axis1=0, axis2=t.ndim - 2)
         prod = t
     return prod.reshape(-1)[0]
+
+
+def applyMPO(O, psi, **kw):
+    """mpo.jl:105-143 for an MPO acting on an MPS (``O * psi``): exact site products (bonds w * chi, MPO bond fastest), a
+    right-going gauge sweep while the sites are built, then movecenter!(phi, 1; kwargs...) with the truncation arguments."""
+    if O.rank != 2 or psi.rank != 1:
+        raise ValueError("Unallowed combinations of MPS ranks.")
+    if O.dim != psi.dim or len(O) != len(psi):
+        raise ValueError("GMPS must share the same physical dims and length.")
+    N = len(psi)
+    phi = GMPS.zeros(1, psi.dim, N)
+    for i in range(1, N + 1):
+        M, A = O[i], psi[i]
+        B = np.einsum('wstx,atb->wasxb', M, A)                       # (w, chi, s, w', chi')
+        w, a, s, x, b = B.shape
+        phi[i] = np.reshape(B, (w * a, s, x * b), order='F')         # fused bonds, MPO index fastest (mpo.jl:133-135)
+        if i > 1:
+            phi.moveright(i - 1)
+    phi.movecenter(1, **kw)
+    return phi

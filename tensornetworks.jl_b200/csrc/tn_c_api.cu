@@ -156,6 +156,15 @@ int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, 
     *k_out = (int64_t)s.size();
   });
 }
+int32_t tn_mpo_apply(tn_mps* O, tn_mps* psi, tn_trunc_t tr, tn_mps** out) {
+  return guard([&] {
+    TN_CHECK(O && psi && out, "tn_mpo_apply: null pointer");
+    auto* h = new tn_mps();
+    try { h->m = mpo_apply(O->m, psi->m, T(tr)); } catch (...) { delete h; throw; }
+    psi->m->ctx->sync();
+    *out = h;
+  });
+}
 int32_t tn_mpo_compress(tn_mps* m, tn_trunc_t tr) { return guard([&] { TN_CHECK(m, "tn_mpo_compress: null handle"); TN_CHECK(m != nullptr, "null pointer"); mpo_compress(m->m, T(tr)); m->m->ctx->sync(); }); }
 int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_cplx* ops, tn_cplx* out) {
   return guard([&] { TN_CHECK(m, "tn_expect_local: null handle"); expect_local(m->m, nops, sites, C(ops), C(out)); });

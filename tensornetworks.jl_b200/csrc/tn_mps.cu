@@ -169,6 +169,33 @@ void mpo_compress(Mps* m, Trunc tr) {
   m->center = 0;
 }
 
+// applyMPO(O, psi) = O * psi (mpo.jl:105-143, MPOMPSProduct): exact site products phi[i]((w,a), s, (w',b)) = sum_t M(w,s,t,w') A(a,t,b)
+// (one strided GEMM with K = d per site; fused bonds with the MPO index fastest), a right-going untruncated gauge sweep while the
+// sites are built, then movecenter!(phi, 1; kwargs...) from an unset centre, i.e. a truncating left-going sweep.
+Mps* mpo_apply(Mps* O, Mps* psi, Trunc tr) {
+  Ctx* c = psi->ctx; cudaStream_t s = c->stream;
+  TN_CHECK(O->rank == 2 && psi->rank == 1, "Unallowed combinations of MPS ranks.");
+  TN_CHECK(O->d == psi->d && O->N == psi->N, "GMPS must share the same physical dims and length.");
+  TN_CHECK(O->ctx == psi->ctx, "applyMPO: both arguments must live in the same context");
+  const int N = psi->N, d = psi->d;
+  auto phi = std::make_unique<Mps>();
+  phi->ctx = c; phi->rank = 1; phi->d = d; phi->N = N; phi->center = 0;
+  phi->sites.resize(N);
+  for (int i = 1; i <= N; ++i) {
+    const Tensor& M = O->sites[i - 1]; const Tensor& A = psi->sites[i - 1];
+    const long long W = M.dims[0], X = M.dims[3], a = A.dims[0], b = A.dims[2];
+    // the bond entering site i may have been changed by the gauge move of site i-1: the site is built with the exact product bond
+    // and moveright(i-1) below contracts its S V^H into it, exactly as the reference does
+    c->alloc(phi->sites[i - 1], {W * a, (long long)d, X * b});
+    zgemm_auto(mk((int)(W * d * X), (int)(a * b), d, M.p, idx2((int)(W * d), 1, W * d * d), idx1(W * d), 0,
+                  A.p, idx1(a), idx2((int)a, 1, a * d), 0,
+                  phi->sites[i - 1].p, idx2((int)W, 1, W * a), idx2((int)a, W, W * a * d * X)), s);
+    if (i > 1) moveright(phi.get(), i - 1, Trunc{0.0, 0, 1});
+  }
+  mps_movecenter(phi.get(), 1, tr);
+  return phi.release();
+}
+
 // Split a two-site tensor theta (chi_l, p, p, chi_r), p = d^rank, back into two sites (gmps.jl:215-266).
 void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool normalize, Trunc tr) {
   Ctx* c = m->ctx; cudaStream_t s = c->stream;

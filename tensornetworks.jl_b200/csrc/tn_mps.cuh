@@ -92,6 +92,7 @@ void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool
 void mps_applyop1(Mps* m, int site, const cplx* op_dev);
 void mps_bond_spectrum(Mps* m, int site, std::vector<double>& out);
 void mpo_compress(Mps* m, Trunc tr);   // mpo.jl:443-457
+Mps* mpo_apply(Mps* O, Mps* psi, Trunc tr);   // applyMPO(O, psi): mpo.jl:105-143
 
 // --- environments -----------------------------------------------------------------------------
 Env* env_create(Ctx* c, Mps* bra, Mps* mpo, Mps* ket, cplx coeff, int center);

@@ -190,6 +190,17 @@ class GMPS:
         return out
 
 
+def applyMPO(O, psi, cutoff=0.0, maxdim=0, mindim=1):
+    """applyMPO(O, psi; kwargs...) = O * psi (mpo.jl:105-143): a new device MPS with its centre at site 1."""
+    if O.rank != 2 or psi.rank != 1:
+        raise _lib.TNError("Unallowed combinations of MPS ranks.")
+    h = C.c_void_p()
+    check(psi.lib.tn_mpo_apply(O.h, psi.h, Trunc(cutoff, maxdim, mindim), C.byref(h)))
+    out = GMPS.__new__(GMPS)
+    out.ctx, out.lib, out.h, out.rank, out.dim, out._N = psi.ctx, psi.lib, h, 1, psi.dim, len(psi)
+    return out
+
+
 class ProjMPS:
     """ProjMPS(bra, [mpo,] ket; rank, squared, coeff, center) environment cache: projmps.jl:1-42.
     ``squared=True`` (mpo must be None) is the rank-1 projector penalty ProjMPS(V, psi; rank=2, squared=true)

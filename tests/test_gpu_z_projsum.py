@@ -533,3 +533,19 @@ def test_thermal_example_energy_matches_oracle():
     want = oracle.trace(M, oracle.adjoint(U), U) / oracle.trace(oracle.adjoint(U), U)
     got = thermal_energy(g, M.tensors)
     assert abs(got - want) < 1e-8 * abs(want)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1", reason="applyMPO on the device: opt in with TN_RUN_UNVERIFIED=1")
+def test_applympo_matches_oracle():
+    import tnb200
+    rng = np.random.default_rng(0)
+    N = 7
+    O, psi = random_mpo(rng, N, 2, 3), random_complex_mps(rng, N, 2, 5, center=2)
+    gO, gpsi = tnb200.GMPS.from_host(O), tnb200.GMPS.from_host(psi)
+    for kw in (dict(), dict(cutoff=1e-10), dict(maxdim=6)):
+        want = oracle.applyMPO(O, psi, **kw)
+        got = tnb200.applyMPO(gO, gpsi, **kw)
+        assert got.center == 1 and [int(x[0]) for x in got.dims()] == [t.shape[0] for t in want.tensors]
+        vo, vg = mps_to_dense(want), _dense(got)
+        assert abs(np.vdot(vo, vg) - np.vdot(vo, vo)) < 1e-9 * abs(np.vdot(vo, vo))          # same vector (gauge-independent)
+        assert abs(np.linalg.norm(vg) - np.linalg.norm(vo)) < 1e-9 * np.linalg.norm(vo)

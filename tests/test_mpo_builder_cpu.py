@@ -131,3 +131,21 @@ def test_oracle_trace_matches_dense():
         want = np.trace(np.linalg.multi_dot([dense(x) for x in args]) if len(args) > 1 else dense(args[0]))
         assert abs(oracle.trace(*args) - want) < 1e-12 * abs(want)
     assert np.allclose(dense(oracle.adjoint(A)), dense(A).conj().T)
+
+
+def test_oracle_applympo_matches_dense():
+    """applyMPO (mpo.jl:105-143 restated): O|psi> as a dense vector, canonical form with the centre at site 1, truncation kwargs."""
+    from gpu_util import random_mpo, random_complex_mps
+    from models import mps_to_dense
+    rng = np.random.default_rng(0)
+    N = 6
+    O, psi = random_mpo(rng, N, 2, 3), random_complex_mps(rng, N, 2, 4, center=2)
+    phi = oracle.applyMPO(O, psi)
+    want = _dense([O[i] for i in range(1, N + 1)]) @ mps_to_dense(psi)
+    assert np.linalg.norm(mps_to_dense(phi) - want) < 1e-12 * np.linalg.norm(want)
+    assert phi.center == 1
+    for i in range(2, N + 1):                      # right-orthonormal sites
+        t = phi[i].reshape(phi[i].shape[0], -1)
+        assert np.allclose(t @ t.conj().T, np.eye(t.shape[0]), atol=1e-12)
+    small = oracle.applyMPO(O, psi, maxdim=3)
+    assert small.maxbonddim() <= 3
