@@ -71,6 +71,9 @@ int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta_host, int32_t site, 
 int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op_host /* d x d */);   /* mps.jl:141-152 */
 /* singular values across bond (site, site+1) -- the SVD inside entropy(): gmps.jl:184-189 */
 int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out);
+/* deepcopy(psi) (abstractmps.jl:95-96) and psi *= a (abstractmps.jl:99-109: the centre tensor, or site 1 when the centre is unset) */
+int32_t tn_mps_copy(tn_mps* m, tn_mps** out);
+int32_t tn_mps_scale(tn_mps* m, tn_cplx a);
 /* applyMPO(O, psi; kwargs...) = O * psi for an MPO and an MPS: mpo.jl:105-143.  Exact site products (bonds w * chi), right-going
  * gauge sweep, then a truncating movecenter!(phi, 1; trunc).  Returns a new MPS handle (centre 1). */
 int32_t tn_mpo_apply(tn_mps* O, tn_mps* psi, tn_trunc_t trunc, tn_mps** out);

@@ -156,6 +156,32 @@ int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, 
     *k_out = (int64_t)s.size();
   });
 }
+int32_t tn_mps_copy(tn_mps* m, tn_mps** out) {      // deepcopy(psi): abstractmps.jl:95-96
+  return guard([&] {
+    TN_CHECK(m && out, "tn_mps_copy: null pointer");
+    Mps* src = m->m; Ctx* c = src->ctx;
+    auto cp = std::make_unique<Mps>();
+    cp->ctx = c; cp->rank = src->rank; cp->d = src->d; cp->N = src->N; cp->center = src->center;
+    cp->sites.resize(src->N);
+    for (int i = 0; i < src->N; ++i) {
+      c->alloc(cp->sites[i], src->sites[i].dims);
+      TN_CUDA(cudaMemcpyAsync(cp->sites[i].p, src->sites[i].p, (size_t)src->sites[i].size() * sizeof(cplx), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->sync();
+    auto* h = new tn_mps();
+    h->m = cp.release();
+    *out = h;
+  });
+}
+int32_t tn_mps_scale(tn_mps* m, tn_cplx a) {        // psi * a in place: the centre tensor (site 1 if unset) is multiplied, abstractmps.jl:99-109
+  return guard([&] {
+    TN_CHECK(m, "tn_mps_scale: null handle");
+    Mps* p = m->m;
+    Tensor& t = p->sites[(p->center != 0 ? p->center : 1) - 1];
+    zscal(t.size(), cplx{a.re, a.im}, t.p, p->ctx->stream);
+    p->ctx->sync();
+  });
+}
 int32_t tn_mpo_apply(tn_mps* O, tn_mps* psi, tn_trunc_t tr, tn_mps** out) {
   return guard([&] {
     TN_CHECK(O && psi && out, "tn_mpo_apply: null pointer");

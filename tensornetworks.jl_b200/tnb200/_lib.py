@@ -56,6 +56,8 @@ PROTOTYPES = {
     "tn_mps_bond_spectrum": [P, I32, pF64, I64, pI64],
     "tn_mpo_compress": [P, tn_trunc_t],
     "tn_mpo_apply": [P, P, tn_trunc_t, PP],
+    "tn_mps_copy": [P, PP],
+    "tn_mps_scale": [P, tn_cplx],
     "tn_expect_local": [P, I32, pI32, P, P],
     "tn_svd_trunc": [P, P, I64, I64, tn_trunc_t, P, pF64, P, pI64, pI32],
     "tn_svd_trunc_batched": [P, I32, P, I64, I64, tn_trunc_t, P, pF64, P, pI64, pI32],

@@ -129,6 +129,27 @@ class GMPS:
     def tensors(self):
         return [self[i] for i in range(1, self._N + 1)]
 
+    @classmethod
+    def _wrap(cls, like, h):
+        out = cls.__new__(cls)
+        out.ctx, out.lib, out.h, out.rank, out.dim, out._N = like.ctx, like.lib, h, like.rank, like.dim, like._N
+        return out
+
+    def copy(self):                               # deepcopy(psi): abstractmps.jl:95-96 (device to device)
+        h = C.c_void_p()
+        check(self.lib.tn_mps_copy(self.h, C.byref(h)))
+        return GMPS._wrap(self, h)
+
+    def scale(self, a):                           # psi * a: abstractmps.jl:99-109 (a scaled copy, like the reference)
+        out = self.copy()
+        a = complex(a)
+        check(self.lib.tn_mps_scale(out.h, tn_cplx(a.real, a.imag)))
+        return out
+
+    def overlap(self, psi):
+        """inner(self, psi) = <self|psi> (mpo.jl:181-217 for two MPS) through the overlap environment."""
+        return ProjMPS(self, None, psi, center=1).calculate()
+
     def bonddim(self, site):                      # abstractmps.jl:62-65
         if site < 1 or site > self._N:
             return None
@@ -196,9 +217,7 @@ def applyMPO(O, psi, cutoff=0.0, maxdim=0, mindim=1):
         raise _lib.TNError("Unallowed combinations of MPS ranks.")
     h = C.c_void_p()
     check(psi.lib.tn_mpo_apply(O.h, psi.h, Trunc(cutoff, maxdim, mindim), C.byref(h)))
-    out = GMPS.__new__(GMPS)
-    out.ctx, out.lib, out.h, out.rank, out.dim, out._N = psi.ctx, psi.lib, h, 1, psi.dim, len(psi)
-    return out
+    return GMPS._wrap(psi, h)
 
 
 class ProjMPS:
@@ -535,7 +554,7 @@ def vmps(*psis, minsweeps=2, maxsweeps=200, tol=1e-10, numconverges=3, verbose=F
     Vs = ProjMPSSum([ProjMPS(psi_k, psi0)]); the sweep body (:36-62) runs on the device (tn_vmps_sweep), the cost
     norm(psi)^2 - 2|calculate(Vs)| and the convergence counters (:64-83) host-side."""
     first = psis[0]
-    psi = GMPS(first.rank, first.dim, first.tensors, first.center, first.ctx)
+    psi = GMPS(first.rank, first.dim, first.tensors, first.center, first.ctx)     # deepcopy(psis[1]) (vmps.jl:97)
     if psi.rank != 1:
         raise _lib.TNError("vmps: rank-1 MPS only")
     psi.movecenter(1)

@@ -70,13 +70,52 @@ def trotterize(N, d, terms, dt, order=2, evol="imag"):
     return rows_s, rows_g
 
 
-def tebd(psi, terms, dt, tmax, save, observers=(), cutoff=1e-12, maxdim=0, mindim=1, evol="imag", order=2, norm=0.0, verbose=False):
-    """tebd.jl:3-100 without projectors.  ``psi`` is a device GMPS, ``terms`` the Hamiltonian as passed to the reference
+class MPSProjector:
+    """projector.jl:1-50: |right><left| / constant with constant = <left|right> unless given (device MPSs)."""
+
+    rank = 2
+
+    def __init__(self, left, right=None, constant=0.0):
+        right = left if right is None else right
+        if left.dim != right.dim or len(left) != len(right):
+            raise _lib.TNError("The MPS must share the same physical dimension and length.")
+        self.dim, self.leftMPS, self.rightMPS = left.dim, left, right
+        self.constant = left.overlap(right) if constant == 0.0 else constant
+
+    def apply(self, psi):                       # projector.jl:41-47
+        return self.rightMPS.scale(self.leftMPS.overlap(psi) / self.constant)
+
+
+def project_out(psi, projs, cutoff, maxdim):
+    """tebd.jl:68-73 (and :36-41): psi <- vmps(psi, -1*(P_1*psi), ...); MPO projectors go through applyMPO, MPS projectors through
+    their overlap with psi; the variational sum runs on the device (tn_vmps_sweep)."""
+    from .api import applyMPO, vmps
+    psis = [psi]
+    for P in projs:
+        Ppsi = P.apply(psi) if isinstance(P, MPSProjector) else applyMPO(P, psi)
+        psis.append(Ppsi.scale(-1))
+    return vmps(*psis, cutoff=cutoff, maxdim=maxdim)
+
+
+def tebd(psi, terms, dt, tmax, save, observers=(), projectors=(), cutoff=1e-12, maxdim=0, mindim=1, evol="imag", order=2, norm=0.0,
+         verbose=False, projection_every=10, variational_cutoff=None):
+    """tebd.jl:3-100, including the projector branch (:22-41, :67-73; the returned psi is then a new device MPS).  ``psi`` is a device GMPS, ``terms`` the Hamiltonian as passed to the reference
     (i.e. -H for imaginary time).  Observers are objects with measure(time, psi, norm, energy) and checkdone().
     Returns (psi, energy) like the oracle's restatement."""
     N, d = len(psi), psi.dim
     rs, rg = trotterize(N, d, terms, dt, order=order, evol=evol)
     gates = GateList(d, rs, rg, ctx=psi.ctx)
+    variational_cutoff = cutoff if variational_cutoff is None else variational_cutoff
+    projs = []
+    for proj in projectors:                                   # tebd.jl:26-35
+        if isinstance(proj, MPSProjector) or proj.rank == 2:
+            projs.append(proj)
+        elif proj.rank == 1:
+            projs.append(MPSProjector(proj, proj))
+        else:
+            raise _lib.TNError("Only MPS, MPO and MPSProjectors are supported as projectors.")
+    if projs:                                                 # tebd.jl:36-41
+        psi = project_out(psi, projs, variational_cutoff, maxdim)
     nsteps = int(round(tmax / dt))
     save = dt if save < dt else save
     nsave = int(round(save / dt))
@@ -88,6 +127,8 @@ def tebd(psi, terms, dt, tmax, save, observers=(), cutoff=1e-12, maxdim=0, mindi
     step = 0
     while not converged:
         applygates(psi, gates, cutoff=cutoff, maxdim=maxdim, mindim=mindim)
+        if projs and (step + 1) % projection_every == 0:      # tebd.jl:67-73
+            psi = project_out(psi, projs, variational_cutoff, maxdim)
         normal += float(np.log(np.real(psi.norm())))
         psi.normalize()
         step += 1

@@ -549,3 +549,26 @@ def test_applympo_matches_oracle():
         vo, vg = mps_to_dense(want), _dense(got)
         assert abs(np.vdot(vo, vg) - np.vdot(vo, vo)) < 1e-9 * abs(np.vdot(vo, vo))          # same vector (gauge-independent)
         assert abs(np.linalg.norm(vg) - np.linalg.norm(vo)) < 1e-9 * np.linalg.norm(vo)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1", reason="tebd projector branch on the device: opt in with TN_RUN_UNVERIFIED=1")
+def test_tebd_with_projector_matches_oracle():
+    """tebd.jl:22-41,67-73 on the device (MPSProjector overlap + scaled copy, tn_vmps_sweep) against the oracle and exact diagonalisation."""
+    import tnb200
+    from tnb200.evolve import tebd as gtebd
+    from oracle.tebd import tebd as otebd
+    sh = oracle.spinhalf()
+    N = 8
+    Hl = tfim(N)
+    ev = np.linalg.eigvalsh(dense_hamiltonian(sh, Hl).toarray())
+    g0, _ = oracle.dmrg(oracle.randomMPS(2, N, 4, np.random.default_rng(1)), oracle.MPO(sh, Hl), maxdim=32, cutoff=1e-14, maxsweeps=20)
+    p = oracle.randomMPS(2, N, 4, np.random.default_rng(3))
+    Hm = -1 * Hl
+    terms = [([sh.op(o) for o in ops], sites, c) for ops, sites, c in zip(Hm.ops, Hm.sites, Hm.coeffs)]
+    _, Eo = otebd(sh, p.copy(), Hm, 0.02, 2.0, 1.0, projectors=[g0], cutoff=1e-12, maxdim=16, projection_every=5)
+    psi, Eg = gtebd(tnb200.GMPS.from_host(p), terms, 0.02, 2.0, 1.0, projectors=[tnb200.GMPS.from_host(g0)], cutoff=1e-12, maxdim=16,
+                    projection_every=5)
+    assert abs(Eo - Eg) < 1e-8 * abs(Eo)
+    assert abs(tnb200.GMPS.from_host(g0).overlap(psi)) < 1e-9
+    psi, Eg = gtebd(psi, terms, 0.02, 4.0, 1.0, projectors=[tnb200.GMPS.from_host(g0)], cutoff=1e-12, maxdim=16, projection_every=5)
+    assert abs(-Eg - ev[1]) < 1e-4 * abs(ev[1])

@@ -86,3 +86,18 @@ def test_vmps_truncated_is_best_sweep_approximation():
     assert np.isclose(np.vdot(v, target), np.vdot(v, v), rtol=1e-6)
     costs = [np.real(h[1]) for h in hist]
     assert all(costs[i + 1] <= costs[i] + 1e-9 for i in range(len(costs) - 1))
+
+
+def test_tebd_with_projector_reaches_first_excited_state():
+    """tebd.jl:22-41,67-73: imaginary-time TEBD with the ground state projected out (vmps(psi, -P psi) every few steps) converges
+    to the first excited state (exact diagonalisation)."""
+    from oracle.tebd import tebd, overlap
+    sh = oracle.spinhalf()
+    N = 8
+    Hl = tfim(N)
+    ev = np.linalg.eigvalsh(dense_hamiltonian(sh, Hl).toarray())
+    g0, _ = oracle.dmrg(oracle.randomMPS(2, N, 4, np.random.default_rng(1)), oracle.MPO(sh, Hl), maxdim=32, cutoff=1e-14, maxsweeps=20)
+    p = oracle.randomMPS(2, N, 4, np.random.default_rng(3))
+    psi, E = tebd(sh, p, -1 * Hl, 0.02, 6.0, 1.0, projectors=[g0], cutoff=1e-12, maxdim=16, projection_every=5)
+    assert abs(-E - ev[1]) < 1e-4 * abs(ev[1])          # second-order Trotter error at dt = 0.02
+    assert abs(overlap(g0, psi)) < 1e-10
