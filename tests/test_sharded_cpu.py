@@ -133,7 +133,7 @@ def _dmrg_worker(rank, world, port, q):
     ho, hs = [], []
     oracle.dmrg(p0.copy(), M, maxdim=16, maxsweeps=4, history=ho)
     ps, _ = sharded_dmrg(p0.copy(), [M[i] for i in range(1, 9)], be, rank, world, dist, maxdim=16, maxsweeps=4, history=hs)
-    q.put((rank, max(errs), cal, perr, ho, hs, [t.tobytes() for t in ps.tensors]))
+    q.put((rank, max(errs, default=0.0), cal, perr, ho, hs, [t.tobytes() for t in ps.tensors]))
     dist.destroy_process_group()
 
 
