@@ -642,3 +642,119 @@ class GpuBackend:
         dist.broadcast(self.torch.view_as_real(buf), src=0)
         self.torch.cuda.synchronize()
         check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(raw.data_ptr()), C.c_void_p(buf.data_ptr()), n * 16))
+
+
+# ---------------------------------------------------------------------------------------------
+# Distributed one-sided block Jacobi (the replicated truncated SVD is the bottleneck of the sharded sweep at large chi:
+# DESIGN.md section 9).  The QR preconditioner and the finish (norms, sort, truncation rule, gathers) stay replicated; the
+# Jacobi sweeps on Z = [W; V] are distributed over the column blocks:
+#   * the nb column blocks (32 columns each) are grouped into 2G super-blocks; rank r works on two of them at a time;
+#   * a sweep = (a) the pairs INSIDE every super-block (each rank: its two), (b) 2G-1 meetings of super-block pairs in
+#     round-robin (circle) order; in a meeting the rank rotates all cross pairs of its two super-blocks in k perfect matchings
+#     (k = blocks per super-block), every matching one launch of the Gram / EVD / rotation kernels over its pairs;
+#   * between meetings the super-blocks whose owner changes travel point-to-point (each is one contiguous slab of Z);
+#   * convergence: all_reduce(max) of the largest normalised off-diagonal Gram entry seen in the sweep;
+#   * at the end every rank all-gathers the super-blocks so that Z is complete everywhere and the replicated finish runs.
+# Every pair of column blocks meets exactly once per sweep, as in the single-GPU round-robin order (tools/jacobi_dist_emul.py:
+# same number of sweeps +- 1).  The ``engine`` does the dense work: GpuSvdEngine (C ABI: tn_svd_dist_begin / _step / _finish) or
+# the NumPy stand-in of the gloo tests.
+# ---------------------------------------------------------------------------------------------
+def rr_pairs(n, step):
+    """circle-method round robin: the n/2 disjoint pairs of step ``step`` (n even, 0 <= step < n-1)"""
+    out = []
+    for k in range(n // 2):
+        if n == 2:
+            a, b = 0, 1
+        elif k == 0:
+            a, b = n - 1, step
+        else:
+            a, b = (step + k) % (n - 1), (step - k + n - 1) % (n - 1)
+        out.append((min(a, b), max(a, b)))
+    return out
+
+
+def dist_jacobi_plan(nb, world):
+    """Static plan for nb column blocks on ``world`` ranks: (k, nsb, meetings) with k blocks per super-block, nsb = 2*world
+    super-blocks and meetings[t] = list over ranks of the super-block pair (P, Q) the rank works on in meeting t.
+    nb must be a multiple of 2*world (the caller falls back to fewer ranks otherwise)."""
+    nsb = 2 * world
+    if nb % nsb != 0:
+        raise _lib.TNError("distributed Jacobi: the number of column blocks must be a multiple of 2 * world")
+    k = nb // nsb
+    meetings = [rr_pairs(nsb, t) for t in range(nsb - 1)]
+    return k, nsb, meetings
+
+
+def usable_world(nb, world):
+    """largest number of ranks g <= world with nb % (2 g) == 0 (ranks >= g idle during the sweeps)"""
+    g = world
+    while g > 1 and nb % (2 * g) != 0:
+        g -= 1
+    return g
+
+
+def dist_jacobi_sweeps(engine, nb, tol, rank, world, dist, max_sweeps=60):
+    """Runs the distributed sweeps on the engine's Z (already prepared by engine.begin on every rank with identical content).
+    Returns the number of sweeps.  On return Z is complete and identical on every rank."""
+    g = usable_world(nb, world)
+    if g == 1:                                  # nothing to distribute: every rank runs the whole sweep redundantly
+        sweeps = 0
+        for _ in range(max_sweeps):
+            off = 0.0
+            for st in range(nb - 1):
+                off = max(off, engine.step(rr_pairs(nb, st)))
+            sweeps += 1
+            if off <= tol:
+                break
+        return sweeps
+    k, nsb, meetings = dist_jacobi_plan(nb, g)
+    active = rank < g
+    owner = {}                                  # super-block -> rank holding its current version
+    for r, (P, Q) in enumerate(meetings[0]):
+        owner[P] = r
+        owner[Q] = r
+
+    def blocks(sb):
+        return range(sb * k, (sb + 1) * k)
+
+    def move(sb, src, dst):
+        """super-block ``sb`` travels src -> dst (one contiguous slab of Z)"""
+        if src == dst:
+            return []
+        ops = []
+        if rank == src:
+            ops.append(("send", sb, dst))
+        if rank == dst:
+            ops.append(("recv", sb, src))
+        return ops
+
+    sweeps = 0
+    for _ in range(max_sweeps):
+        off = 0.0
+        for t, meeting in enumerate(meetings):
+            # who needs what for this meeting
+            ops = []
+            for r, (P, Q) in enumerate(meeting):
+                for sb in (P, Q):
+                    ops += move(sb, owner[sb], r)
+                    owner[sb] = r
+            engine.exchange(ops, k, dist)
+            if active:
+                P, Q = meeting[rank]
+                if t == 0 and k > 1:            # (a) pairs inside the two super-blocks this rank holds at the start of the sweep
+                    kk = k if k % 2 == 0 else k + 1
+                    for st in range(kk - 1):
+                        pairs = []
+                        for sb in (P, Q):
+                            pairs += [(sb * k + a, sb * k + b) for a, b in rr_pairs(kk, st) if a < k and b < k]
+                        if pairs:
+                            off = max(off, engine.step(pairs))
+                for shift in range(k):          # (b) cross pairs of the meeting: k perfect matchings
+                    off = max(off, engine.step([(P * k + i, Q * k + (i + shift) % k) for i in range(k)]))
+        off = engine.all_reduce_max(off, dist)
+        sweeps += 1
+        if off <= tol:
+            break
+    # make Z complete everywhere: every super-block is broadcast from its last owner
+    engine.gather_all([(sb, owner[sb]) for sb in range(nsb)], k, dist)
+    return sweeps
