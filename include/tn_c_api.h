@@ -188,6 +188,20 @@ int32_t tn_mps_replacesites_dev(tn_mps* m, const void* theta_dev, int32_t site, 
 int32_t tn_mps_upload_site_dev(tn_mps* m, int32_t site, const int64_t* dims, const void* data_dev);
 /* device-to-device copy ordered on the context's stream (completed on return) */
 int32_t tn_memcpy_dev(tn_ctx* ctx, void* dst_dev, const void* src_dev, int64_t nbytes);
+/* The truncated SVD in three calls for a caller that owns the Jacobi pair schedule (distributed sweeps over several GPUs,
+ * tnb200/sharded.py: every rank begins on the same matrix, rotates the column-block pairs its schedule assigns to it, exchanges
+ * column blocks with its peers, and finishes on the complete Z).  begin: init + the two QR steps; returns the device address of
+ * Z = [W; V] (leading dimension ldz, zrows rows, nblocks blocks of 32 columns; block b starts at Z + b*32*ldz) and the convergence
+ * threshold.  step: Gram -> EVD -> rotation over npairs disjoint block pairs (pairs: npairs x 2), returns the largest normalised
+ * off-diagonal Gram entry seen.  finish: norms, sort, the reference's truncation rule (tensors.jl:201-215).  factors: U (m x k),
+ * S (k doubles), Vh (k x n) into device buffers (any may be NULL); tn_mps_replacesites_factored = replacesites! with the factors
+ * left in the context (gmps.jl:215-266). */
+int32_t tn_svd_dist_begin(tn_ctx* ctx, const void* mat_dev, int64_t m, int64_t n, void** Z_dev, int64_t* ldz, int64_t* zrows,
+                          int32_t* nblocks, double* tol);
+int32_t tn_svd_dist_step(tn_ctx* ctx, const int32_t* pairs, int32_t npairs, double* offmax);
+int32_t tn_svd_dist_finish(tn_ctx* ctx, tn_trunc_t trunc, int32_t sweeps, int64_t* k_out);
+int32_t tn_svd_dist_factors(tn_ctx* ctx, void* U_dev, void* S_dev, void* Vh_dev);
+int32_t tn_mps_replacesites_factored(tn_mps* m, int32_t site, int32_t direction, int32_t normalize);
 /* KrylovKit eigsolve(f, x0, 1, :SR; krylovdim, maxiter, tol, ishermitian=true) (dmrg.jl:51-53) for a caller-supplied Hermitian
  * linear map on n-element complex128 device vectors.  apply(user, in_dev, out_dev) is entered with in_dev complete; all its writes
  * to out_dev must be complete (or enqueued on the context's stream) when it returns 0.  Non-zero aborts with TN_ERR_INVALID. */

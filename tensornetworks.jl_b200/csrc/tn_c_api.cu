@@ -550,6 +550,46 @@ int32_t tn_memcpy_dev(tn_ctx* ctx, void* dst_dev, const void* src_dev, int64_t n
     ctx->c.sync();
   });
 }
+// ---- truncated SVD in three calls with a caller-owned pair schedule (distributed Jacobi sweeps) ---------------------------------
+int32_t tn_svd_dist_begin(tn_ctx* ctx, const void* mat_dev, int64_t m, int64_t n, void** Z_dev, int64_t* ldz, int64_t* zrows,
+                          int32_t* nblocks, double* tol) {
+  return guard([&] {
+    TN_CHECK(ctx && mat_dev && Z_dev && ldz && zrows && nblocks && tol, "tn_svd_dist_begin: null pointer");
+    Ctx* c = &ctx->c;
+    const int nb = svd_dist_begin(c->svd, (const cplx*)mat_dev, (int)m, (int)n, m, c->stream); c->svds++;
+    *Z_dev = (void*)c->svd.Z; *ldz = c->svd.ldz; *zrows = c->svd.jrows + c->svd.ncols_pad; *nblocks = nb; *tol = svd_dist_tol(c->svd);
+  });
+}
+int32_t tn_svd_dist_step(tn_ctx* ctx, const int32_t* pairs, int32_t npairs, double* offmax) {
+  return guard([&] {
+    TN_CHECK(ctx && pairs && offmax, "tn_svd_dist_step: null pointer");
+    *offmax = svd_dist_step(ctx->c.svd, pairs, npairs, ctx->c.stream);
+  });
+}
+int32_t tn_svd_dist_finish(tn_ctx* ctx, tn_trunc_t tr, int32_t sweeps, int64_t* k_out) {
+  return guard([&] {
+    TN_CHECK(ctx && k_out, "tn_svd_dist_finish: null pointer");
+    *k_out = svd_dist_finish(ctx->c.svd, T(tr), sweeps, ctx->c.stream);
+  });
+}
+int32_t tn_svd_dist_factors(tn_ctx* ctx, void* U_dev, void* S_dev, void* Vh_dev) {
+  return guard([&] {
+    TN_CHECK(ctx, "tn_svd_dist_factors: null handle");
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    if (U_dev) svd_gather_U(c->svd, (cplx*)U_dev, c->svd.m, false, s);
+    if (Vh_dev) svd_gather_Vh(c->svd, (cplx*)Vh_dev, c->svd.k, false, s);
+    if (S_dev) svd_copy_S(c->svd, (double*)S_dev, s);
+    c->sync();
+  });
+}
+int32_t tn_mps_replacesites_factored(tn_mps* m, int32_t site, int32_t direction, int32_t normalize) {
+  return guard([&] {
+    TN_CHECK(m, "tn_mps_replacesites_factored: null handle");
+    mps_replacesites2_factored(m->m, site, direction != 0, normalize != 0);
+    m->m->ctx->sync();
+  });
+}
+
 int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* theta_out_dev, tn_lanczos_t lz, tn_apply_fn apply, void* user,
                        double* eig, int32_t* numops) {
   return guard([&] { TN_CHECK(ctx, "tn_eigsolve_fn: null handle");

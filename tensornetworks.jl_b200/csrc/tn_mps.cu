@@ -213,6 +213,24 @@ void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool
   if (normalize) mps_normalize(m);
 }
 
+// The part of mps_replacesites2 after the factorisation, for factors that are already in the context's SvdWork (a caller that
+// ran the SVD itself, e.g. the distributed sweeps): same gathers, same centre / normalisation.
+void mps_replacesites2_factored(Mps* m, int site, bool direction, bool normalize) {
+  Ctx* c = m->ctx; cudaStream_t s = c->stream;
+  TN_CHECK(site >= 1 && site + 1 <= m->N, "replacesites: site out of range");
+  Tensor& A = m->sites[site - 1]; Tensor& B = m->sites[site];
+  long long chil = A.dims.front(), chir = B.dims.back(), p = m->phys();
+  long long rows = chil * p, cols = p * chir;
+  TN_CHECK(c->svd.m == rows && c->svd.n == cols, "replacesites: the factorisation in the context does not belong to these sites");
+  const int k = c->svd.k;
+  std::vector<long long> da = A.dims, db = B.dims; da.back() = k; db.front() = k;
+  c->alloc(A, da); c->alloc(B, db);
+  svd_gather_U(c->svd, A.p, rows, direction, s);
+  svd_gather_Vh(c->svd, B.p, k, !direction, s);
+  m->center = direction ? site : site + 1;
+  if (normalize) mps_normalize(m);
+}
+
 void mps_applyop1(Mps* m, int site, const cplx* op_dev) {   // mps.jl:141-152
   Ctx* c = m->ctx;
   Tensor& A = m->sites[site - 1];

@@ -89,6 +89,7 @@ cplx mps_norm(Mps* m);
 void mps_normalize(Mps* m);
 void mps_movecenter(Mps* m, int idx, Trunc tr);
 void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool normalize, Trunc tr);
+void mps_replacesites2_factored(Mps* m, int site, bool direction, bool normalize);
 void mps_applyop1(Mps* m, int site, const cplx* op_dev);
 void mps_bond_spectrum(Mps* m, int site, std::vector<double>& out);
 void mpo_compress(Mps* m, Trunc tr);   // mpo.jl:443-457

@@ -844,6 +844,7 @@ void svd_copy_S(SvdWork& w, double* S, cudaStream_t s) {
 void svd_free(SvdWork& w) {
   if (w.Z) cudaFree(w.Z);
   if (w.skip) cudaFree(w.skip);
+  if (w.dtab) cudaFree(w.dtab);
   if (w.Gpart) cudaFree(w.Gpart);
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
@@ -852,6 +853,134 @@ void svd_free(SvdWork& w) {
   for (auto& kv : w.tables) cudaFree(kv.second);
   delete w.bview;
   w = SvdWork{};
+}
+
+// ================================================================================================
+// Factorisation in three calls for a caller that owns the Jacobi pair schedule (the distributed sweeps of tnb200/sharded.py:
+// every rank prepares the same Z, rotates the column-block pairs its schedule assigns to it, exchanges column blocks with its
+// peers between the steps, and finishes on the complete Z):
+//   svd_dist_begin  = svd_factor up to, not including, the Jacobi sweeps (init, the two QR steps, Z = [R2^H ; I])
+//   svd_dist_step   = one Gram -> EVD -> rotation launch sequence over a caller-supplied list of column-block pairs
+//   svd_dist_finish = column norms, sort, truncation rule (the tail of svd_factor); the gathers then work as usual
+// (A copy of the corresponding parts of svd_factor / jacobi_sweeps, kept separate until it has been validated on the GPU.)
+// ================================================================================================
+int svd_dist_begin(SvdWork& w, const cplx* M, int m, int n, long long ld, cudaStream_t s) {
+  TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
+  w.use_view = false;
+  w.m = m; w.n = n;
+  w.transposed = m < n;
+  w.rows = w.transposed ? n : m;
+  w.ncols = w.transposed ? m : n;
+  w.nsv = w.ncols;
+  w.ncols_pad = ((w.ncols + JP - 1) / JP) * JP;
+  TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
+  const int npad = w.ncols_pad;
+  w.precond = precond_enabled() && npad > JP;
+  if (w.s_cap < (size_t)npad) {
+    if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
+    TN_CUDA(cudaMallocAsync((void**)&w.sig, npad * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.sig2, npad * sizeof(double), s));
+    TN_CUDA(cudaMallocAsync((void**)&w.perm, npad * sizeof(int), s));
+    w.s_cap = npad;
+  }
+  if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.cflag, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
+  int blocks;
+  if (!w.precond) {
+    w.jrows = w.rows;
+    w.ldz = pad_ld(w.rows + npad);
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
+    launch_1d((long long)w.ldz * npad, blocks);
+    svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Z, w.rows, w.ncols, npad, w.ldz);
+    TN_CUDA(cudaGetLastError());
+    count_launch(1);
+  } else {
+    ensure(w.Q1, w.Q1_cap, (size_t)w.rows * npad, s);
+    launch_1d((long long)w.rows * npad, blocks);
+    svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Q1, w.rows, w.ncols, npad, w.rows);
+    count_launch(1);
+    bgs_qr(w, w.Q1, w.rows, w.rows, npad, s);
+    ensure(w.Q2, w.Q2_cap, (size_t)npad * npad, s);
+    launch_1d((long long)npad * npad, blocks);
+    conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Q2, npad);
+    count_launch(1);
+    bgs_qr(w, w.Q2, npad, npad, npad, s);
+    w.jrows = npad;
+    w.ldz = pad_ld(2 * npad);
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
+    conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Z, w.ldz);
+    set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
+    TN_CUDA(cudaGetLastError());
+    count_launch(2);
+  }
+  w.sweeps = 0;
+  TN_CUDA(cudaStreamSynchronize(s));
+  return npad / JB;
+}
+
+double svd_dist_tol(const SvdWork& w) { return 3.0 * std::sqrt((double)w.jrows) * 2.220446049250313e-16; }
+
+// pairs_host: npairs x 2 column-block indices (disjoint blocks).  Returns max |g_pq| / sqrt(g_pp g_qq) over these pairs before the rotation.
+double svd_dist_step(SvdWork& w, const int* pairs_host, int npairs, cudaStream_t s) {
+  TN_CHECK(npairs >= 1 && w.Z != nullptr, "svd step: nothing to do / factorisation not begun");
+  const int jrows = w.jrows, nb = w.ncols_pad / JB;
+  for (int i = 0; i < 2 * npairs; ++i) TN_CHECK(pairs_host[i] >= 0 && pairs_host[i] < nb, "svd step: column block out of range");
+  int ksplit = std::max(1, std::min(std::min(std::min(16, max_split()), jrows / 64), (2 * 148) / npairs));
+  int kchunk = ((jrows + ksplit - 1) / ksplit + 7) / 8 * 8;
+  ksplit = (jrows + kchunk - 1) / kchunk;
+  ensure(w.Gpart, w.G_cap, (size_t)std::max(npairs, 32) * JP * JP, s);
+  ensure(w.J, w.J_cap, (size_t)npairs * JP * JP, s);
+  ensure(w.skip, w.skip_cap, (size_t)npairs, s);
+  ensure(w.dtab, w.dtab_cap, (size_t)2 * npairs, s);
+  TN_CUDA(cudaMemcpyAsync(w.dtab, pairs_host, (size_t)2 * npairs * sizeof(int), cudaMemcpyHostToDevice, s));
+  const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
+  TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem));
+  const double tol = svd_dist_tol(w);
+  const long long colblk = (long long)JB * w.ldz;
+  TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
+  Idx2 cols{JB, (long long)w.ldz, colblk, w.dtab, 2};
+  GemmDesc g{};
+  g.M = JP; g.N = JP; g.K = jrows;
+  g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
+  g.B = w.Z; g.bk = idx1(1); g.bn = cols; g.conjB = 0;
+  g.C = w.Gpart; g.cm = idx1(1); g.cn = idx1(JP);
+  g.alpha = make_double2(1, 0); g.beta = make_double2(0, 0);
+  g.batch = npairs; g.bsA = 0; g.bsB = 0; g.bsC = (long long)JP * JP;
+  g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
+  if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)npairs * JP * JP * sizeof(cplx), s));
+  zgemm_auto(g, s);
+  jacobi_evd64_kernel<<<npairs, EVD_THREADS, evd_smem, s>>>(w.Gpart, 1, 0, w.J, tol, w.offmax, 1, JP, w.skip);
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+  GemmDesc a{};
+  a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;
+  a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
+  a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
+  a.C = w.Z; a.cm = idx1(1); a.cn = cols;
+  a.alpha = make_double2(1, 0); a.beta = make_double2(0, 0);
+  a.batch = npairs; a.bsA = 0; a.bsB = (long long)JP * JP; a.bsC = 0;
+  a.ksplit = 1; a.kchunk = JP; a.ssC = 0;
+  a.skip = w.skip;
+  zgemm_auto(a, s);
+  unsigned long long bits = 0;
+  TN_CUDA(cudaMemcpyAsync(&bits, w.offmax, 8, cudaMemcpyDeviceToHost, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  double off; std::memcpy(&off, &bits, 8);
+  return off;
+}
+
+int svd_dist_finish(SvdWork& w, Trunc tr, int sweeps, cudaStream_t s) {
+  const int npad = w.ncols_pad;
+  colnorm2_kernel<<<npad, 128, 0, s>>>(w.Z, w.jrows, w.ldz, w.sig2);
+  int npow2 = 64; while (npow2 < npad) npow2 <<= 1;
+  TN_CUDA(cudaFuncSetAttribute(sort_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12));
+  sort_trunc_kernel<<<1, 1024, npow2 * 12, s>>>(w.sig2, npad, npow2, w.sig, w.perm, w.nsv, tr.cutoff, tr.maxdim, tr.mindim, w.kout);
+  TN_CUDA(cudaGetLastError());
+  count_launch(2);
+  int k = 0;
+  TN_CUDA(cudaMemcpyAsync(&k, w.kout, 4, cudaMemcpyDeviceToHost, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  w.k = k; w.sweeps = sweeps;
+  return k;
 }
 
 // ================================================================================================

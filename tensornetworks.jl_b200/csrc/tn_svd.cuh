@@ -12,6 +12,7 @@ struct Trunc { double cutoff; long long maxdim; long long mindim; };
 struct SvdWork {
   cplx* Z = nullptr; size_t Z_cap = 0;            // [W ; V] stacked, (rows + ncols) x ncols, ld >= rows + ncols
   int* skip = nullptr; size_t skip_cap = 0;        // per-pair flags: Gram block already diagonal, rotation skipped
+  int* dtab = nullptr; size_t dtab_cap = 0;        // pair list of a caller-scheduled step (svd_dist_step)
   cplx* Gpart = nullptr; size_t G_cap = 0;        // split-K Gram partials
   cplx* J = nullptr; size_t J_cap = 0;            // per-pair 64x64 rotations
   double* sig = nullptr; int* perm = nullptr; size_t s_cap = 0;   // sorted singular values + permutation
@@ -49,6 +50,11 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
 // first k singular values (device -> device copy)
 void svd_copy_S(SvdWork& w, double* S, cudaStream_t s);
 void svd_free(SvdWork& w);
+// Factorisation in three calls for a caller that owns the pair schedule (distributed sweeps): see tn_svd.cu.
+int svd_dist_begin(SvdWork& w, const cplx* M, int m, int n, long long ld, cudaStream_t s);      // returns the number of 32-column blocks
+double svd_dist_tol(const SvdWork& w);
+double svd_dist_step(SvdWork& w, const int* pairs_host, int npairs, cudaStream_t s);
+int svd_dist_finish(SvdWork& w, Trunc tr, int sweeps, cudaStream_t s);
 
 // Workspace of a batched factorisation: B same-shape problems stacked side by side (tn_svd.cu, "Batched factorisation").
 struct SvdBatch {

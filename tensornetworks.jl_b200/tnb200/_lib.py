@@ -96,6 +96,11 @@ PROTOTYPES = {
     "tn_mps_replacesites_dev": [P, P, I32, I32, I32, tn_trunc_t],
     "tn_mps_upload_site_dev": [P, I32, pI64, P],
     "tn_memcpy_dev": [P, P, P, I64],
+    "tn_svd_dist_begin": [P, P, I64, I64, PP, pI64, pI64, pI32, pF64],
+    "tn_svd_dist_step": [P, pI32, I32, pF64],
+    "tn_svd_dist_finish": [P, tn_trunc_t, I32, pI64],
+    "tn_svd_dist_factors": [P, P, P, P],
+    "tn_mps_replacesites_factored": [P, I32, I32, I32],
     "tn_eigsolve_fn": [P, I64, P, P, tn_lanczos_t, APPLY_FN, P, pF64, pI32],
     "tn_imps_create": [P, I32, I32, pI64, PP, PP, PP],
     "tn_imps_free": [P],

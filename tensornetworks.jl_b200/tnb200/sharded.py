@@ -459,11 +459,13 @@ class ShardedProjMPS:
 
 
 def sharded_dmrg(psi, mpo_host, be, rank=0, world=1, dist=None, krylovdim=3, kryloviter=2, minsweeps=1, maxsweeps=1000, tol=1e-10,
-                 tolgrad=1e-5, numconverges=4, verbose=False, cutoff=1e-12, maxdim=1000, mindim=1, coeff=1.0, history=None):
+                 tolgrad=1e-5, numconverges=4, verbose=False, cutoff=1e-12, maxdim=1000, mindim=1, coeff=1.0, history=None,
+                 svd_engine=None):
     """dmrg(psi, H; nsites=2, kwargs...) (algorithms/mps/dmrg.jl:1-154) with the environments and the H_eff application
     sharded over the MPO bond on ``world`` ranks.  Every rank runs this function with the same arguments and ends with the
     same psi: after each bond the two new site tensors of rank 0 are broadcast, so rounding differences between the
-    replicated SVDs cannot make the replicas drift apart."""
+    replicated SVDs cannot make the replicas drift apart.  ``svd_engine`` (GpuSvdEngine): distribute the Jacobi sweeps of the
+    truncated SVD over the ranks as well (dist_svd_replacesites) instead of factorising redundantly on every rank."""
     N = be.length(psi)
     be.movecenter(psi, 1)
     Hs = ShardedProjMPS(psi, mpo_host, be, rank, world, dist, center=1, coeff=coeff)
@@ -487,7 +489,10 @@ def sharded_dmrg(psi, mpo_host, be, rank=0, world=1, dist=None, krylovdim=3, kry
             be.contract(cl * d, d * cr, cm, A, _i1(1), _i1(cl * d), 0, B, _i1(1), _i1(cm), 0, th0, _i1(1), _i1(cl * d))
             Hs.prepare(site1)
             cost = be.eigsolve(Hs.product, th0, th1, n, krylovdim, kryloviter, 1e-14)
-            be.replacesites(psi, th1, site1, direction, True, cutoff, maxdim, mindim)
+            if svd_engine is not None:
+                dist_svd_replacesites(be, svd_engine, psi, th1, site1, direction, True, cutoff, maxdim, mindim, rank, world, dist)
+            else:
+                be.replacesites(psi, th1, site1, direction, True, cutoff, maxdim, mindim)
             if world > 1:
                 be.broadcast_site(psi, site1, dist)
                 be.broadcast_site(psi, site1 + 1, dist)
@@ -757,4 +762,97 @@ def dist_jacobi_sweeps(engine, nb, tol, rank, world, dist, max_sweeps=60):
             break
     # make Z complete everywhere: every super-block is broadcast from its last owner
     engine.gather_all([(sb, owner[sb]) for sb in range(nsb)], k, dist)
+    return sweeps
+
+
+class GpuSvdEngine:
+    """Dense side of dist_jacobi_sweeps on one GPU: tn_svd_dist_begin / _step / _finish on the context's SVD workspace; column
+    super-blocks travel through torch staging buffers (tn_memcpy_dev <-> NCCL point-to-point / broadcast)."""
+
+    JB = 32
+
+    def __init__(self, ctx, device):
+        import torch
+        self.torch, self.ctx, self.lib, self.device = torch, ctx, ctx.lib, device
+        self.Z = self.ldz = self.zrows = self.nb = self.tol = None
+
+    def begin(self, mat, m, n):
+        """mat: object with data_ptr() of the m x n column-major matrix on the device.  Returns (nblocks, tol)."""
+        Z, ldz, zr, nb, tol = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int32(), C.c_double()
+        check(self.lib.tn_svd_dist_begin(self.ctx.h, C.c_void_p(mat.data_ptr()), int(m), int(n), C.byref(Z), C.byref(ldz), C.byref(zr),
+                                         C.byref(nb), C.byref(tol)))
+        self.Z, self.ldz, self.zrows, self.nb, self.tol = Z.value, ldz.value, zr.value, nb.value, tol.value
+        return self.nb, self.tol
+
+    def step(self, pairs):
+        arr = np.ascontiguousarray(np.asarray(pairs, dtype=np.int32).reshape(-1))
+        off = C.c_double()
+        check(self.lib.tn_svd_dist_step(self.ctx.h, arr.ctypes.data_as(C.POINTER(C.c_int32)), len(pairs), C.byref(off)))
+        return off.value
+
+    def finish(self, cutoff, maxdim, mindim, sweeps):
+        from ._lib import tn_trunc_t
+        k = C.c_int64()
+        check(self.lib.tn_svd_dist_finish(self.ctx.h, tn_trunc_t(float(cutoff), int(maxdim), int(mindim)), int(sweeps), C.byref(k)))
+        return k.value
+
+    # -- column super-blocks: slab sb of k blocks = k*32*ldz contiguous elements of Z
+    def _slab(self, sb, k):
+        n = k * self.JB * self.ldz
+        return self.Z + 16 * sb * n, n
+
+    def _stage_out(self, sb, k):
+        ptr, n = self._slab(sb, k)
+        t = self.torch.empty(2 * n, dtype=self.torch.float64, device=self.device)
+        self.torch.cuda.synchronize()
+        check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(t.data_ptr()), C.c_void_p(ptr), 16 * n))
+        return t
+
+    def _stage_in(self, sb, k, t):
+        ptr, n = self._slab(sb, k)
+        self.torch.cuda.synchronize()
+        check(self.lib.tn_memcpy_dev(self.ctx.h, C.c_void_p(ptr), C.c_void_p(t.data_ptr()), 16 * n))
+
+    def exchange(self, ops, k, dist):
+        if not ops:
+            return
+        reqs, recvs = [], []
+        for kind, sb, peer in ops:
+            if kind == "send":
+                reqs.append(dist.P2POp(dist.isend, self._stage_out(sb, k), peer))
+            else:
+                _, n = self._slab(sb, k)
+                t = self.torch.empty(2 * n, dtype=self.torch.float64, device=self.device)
+                reqs.append(dist.P2POp(dist.irecv, t, peer))
+                recvs.append((sb, t))
+        for w in dist.batch_isend_irecv(reqs):
+            w.wait()
+        self.torch.cuda.synchronize()
+        for sb, t in recvs:
+            self._stage_in(sb, k, t)
+
+    def all_reduce_max(self, v, dist):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def gather_all(self, owners, k, dist):
+        for sb, src in owners:
+            t = self._stage_out(sb, k)
+            dist.broadcast(t, src=src)
+            self.torch.cuda.synchronize()
+            self._stage_in(sb, k, t)
+
+
+def dist_svd_replacesites(be, engine, psi, theta, site, direction, normalize, cutoff, maxdim, mindim, rank, world, dist):
+    """replacesites!(psi, theta, site, direction, normalize; trunc) (gmps.jl:215-266) with the Jacobi sweeps of the truncated SVD
+    distributed over the ranks; every rank ends with the same two site tensors (the finish runs on identical, complete factors)."""
+    _, (cl, d, _) = be.site(psi, site)
+    _, (_, _, cr) = be.site(psi, site + 1)
+    rows, cols = cl * d, d * cr
+    be.sync()
+    nb, tol = engine.begin(theta, rows, cols)
+    sweeps = dist_jacobi_sweeps(engine, nb, tol, rank, world, dist)
+    engine.finish(cutoff, maxdim, mindim, sweeps)
+    check(be.lib.tn_mps_replacesites_factored(psi.h, int(site), int(bool(direction)), int(bool(normalize))))
     return sweeps

@@ -572,3 +572,49 @@ def test_tebd_with_projector_matches_oracle():
     assert abs(tnb200.GMPS.from_host(g0).overlap(psi)) < 1e-9
     psi, Eg = gtebd(psi, terms, 0.02, 4.0, 1.0, projectors=[tnb200.GMPS.from_host(g0)], cutoff=1e-12, maxdim=16, projection_every=5)
     assert abs(-Eg - ev[1]) < 1e-4 * abs(ev[1])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1",
+                    reason="three-call SVD with a caller-owned pair schedule (distributed Jacobi): opt in with TN_RUN_UNVERIFIED=1")
+def test_three_call_svd_with_external_schedule_matches_fused_svd():
+    """tn_svd_dist_begin / _step / _finish driven by dist_jacobi_sweeps at world 1 (round-robin schedule from Python) against the fused
+    tn_svd_trunc and LAPACK; then the sharded DMRG sweep with the SVD engine against the fused sweep."""
+    import torch
+    import tnb200
+    from tnb200.sharded import GpuSvdEngine, GpuBackend, dist_jacobi_sweeps, sharded_dmrg
+    from models import xxz
+    ctx = tnb200.Context.default()
+    eng = GpuSvdEngine(ctx, "cuda")
+    rng = np.random.default_rng(5)
+    for (m, n, kw) in ((200, 200, dict()), (300, 130, dict(cutoff=1e-10)), (96, 260, dict(maxdim=50))):
+        x = crandn(rng, m, n)
+        u, s, vh = np.linalg.svd(x, full_matrices=False)
+        x = (u * (s[0] * np.exp(-np.arange(len(s)) * (16.0 / len(s))))) @ vh
+        xd = torch.from_numpy(np.reshape(x, -1, order='F').copy()).cuda()
+        torch.cuda.synchronize()
+        nb, tol = eng.begin(xd, m, n)
+        sweeps = dist_jacobi_sweeps(eng, nb, tol, 0, 1, None)
+        k = eng.finish(kw.get("cutoff", 0.0), kw.get("maxdim", 0), 1, sweeps)
+        _, So, _ = oracle.svd(x, 2, **kw)
+        so = np.real(np.diag(So))
+        assert k == len(so) and sweeps < 30
+        U = torch.zeros(m * k, dtype=torch.complex128, device="cuda")
+        S = torch.zeros(k, dtype=torch.float64, device="cuda")
+        Vh = torch.zeros(k * n, dtype=torch.complex128, device="cuda")
+        torch.cuda.synchronize()
+        import ctypes as C
+        tnb200._lib.check(ctx.lib.tn_svd_dist_factors(ctx.h, C.c_void_p(U.data_ptr()), C.c_void_p(S.data_ptr()), C.c_void_p(Vh.data_ptr())))
+        Uh, Sh, Vhh = U.cpu().numpy().reshape(m, k, order='F'), S.cpu().numpy(), Vh.cpu().numpy().reshape(k, n, order='F')
+        assert np.max(np.abs(Sh - so)) < 1e-12 * so[0]
+        uu, ss, vv = np.linalg.svd(x, full_matrices=False)
+        assert np.linalg.norm((Uh * Sh) @ Vhh - (uu[:, :k] * ss[:k]) @ vv[:k]) < 1e-11 * ss[0] * np.sqrt(k)
+    sh = oracle.spinhalf()
+    N = 10
+    M = oracle.MPO(sh, xxz(N, 1.0))
+    p0 = oracle.randomMPS(2, N, 4, np.random.default_rng(1))
+    hg, hs = [], []
+    tnb200.dmrg(tnb200.GMPS.from_host(p0), tnb200.GMPS.from_host(M), maxdim=24, maxsweeps=3, history=hg)
+    sharded_dmrg(tnb200.GMPS.from_host(p0), [M[i] for i in range(1, N + 1)], GpuBackend(ctx, "cuda"), maxdim=24, maxsweeps=3, history=hs,
+                 svd_engine=eng)
+    for a, b in zip(hg, hs):
+        assert a[2] == b[2] and abs(a[1] - b[1]) < 1e-10 * abs(a[1])
