@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--lx", type=int, default=6)
     ap.add_argument("--ly", type=int, default=4)
     ap.add_argument("--sweeps", type=int, default=2)
+    ap.add_argument("--dist-svd", action="store_true", help="dmrg: distribute the Jacobi sweeps of the truncated SVD over the ranks")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -83,7 +84,7 @@ def main():
     elif a.what == "dmrg":
         # Sharded DMRG sweeps on the J1-J2 cylinder (C5 shapes when --lx 12 --ly 6 --chi 4096): every rank holds its w-slice
         # of every environment block; energies must agree with the single-GPU fused sweep (--check, small sizes only).
-        from tnb200.sharded import GpuBackend, sharded_dmrg
+        from tnb200.sharded import GpuBackend, GpuSvdEngine, sharded_dmrg
         from tnb200.mpo import MPO
         Nn = a.lx * a.ly
         gH = MPO(Nn, d, tnb200.models.j1j2_cylinder_terms(a.lx, a.ly), ctx=ctx)
@@ -99,7 +100,7 @@ def main():
         t0 = time.perf_counter()
         # cutoff = 0 keeps the bond dimension at chi, so the shapes are data-independent
         sharded_dmrg(psi, mpo_host, be, rank, world, dist if world > 1 else None, cutoff=0.0, maxdim=a.chi, minsweeps=a.sweeps,
-                     maxsweeps=a.sweeps, history=hist)
+                     maxsweeps=a.sweeps, history=hist, svd_engine=GpuSvdEngine(ctx, "cuda") if a.dist_svd else None)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         t = torch.tensor([wall], dtype=torch.float64, device="cuda")
@@ -112,7 +113,7 @@ def main():
             ref = [h[1] for h in h2]
         if rank == 0:
             print(json.dumps({"what": "dmrg_mpo_bond_sharded", "n_gpus": world, "lattice": [a.lx, a.ly], "sites": Nn, "chi": a.chi, "w_max": wmax,
-                              "sweeps": a.sweeps, "s_per_sweep": float(t.item()) / a.sweeps, "energies": [h[1] for h in hist],
+                              "sweeps": a.sweeps, "distributed_svd": bool(a.dist_svd), "s_per_sweep": float(t.item()) / a.sweeps, "energies": [h[1] for h in hist],
                               "maxbond": [h[2] for h in hist], "single_gpu_energies": ref,
                               "collectives": "NCCL reduce_scatter (block updates, T2) + all_reduce (H_eff result) + broadcast (new sites)" if world > 1 else "none",
                               "mem_allocated_gb": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)

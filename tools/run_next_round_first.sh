@@ -17,7 +17,9 @@ if [ "$N" = "1" ]; then
 else
   RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519"
   timeout 300 $RUN tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check > gpurun_out/next_sharded_dmrg_$N.jsonl 2> gpurun_out/next_sharded_dmrg_$N.err
+  timeout 300 $RUN tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check --dist-svd >> gpurun_out/next_sharded_dmrg_$N.jsonl 2>> gpurun_out/next_sharded_dmrg_$N.err
   timeout 500 $RUN tools/bench_multigpu.py --what dmrg --lx 12 --ly 6 --chi 1024 --sweeps 1 >> gpurun_out/next_sharded_dmrg_$N.jsonl 2>> gpurun_out/next_sharded_dmrg_$N.err
+  timeout 500 $RUN tools/bench_multigpu.py --what dmrg --lx 12 --ly 6 --chi 1024 --sweeps 1 --dist-svd >> gpurun_out/next_sharded_dmrg_$N.jsonl 2>> gpurun_out/next_sharded_dmrg_$N.err
   # sharded matvec: plain vs pipelined reduce_scatter (must print the same checksum)
   for P in 0 4 8; do timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 24 --steps 3 --pipeline $P >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err; done
   cat gpurun_out/next_sharded_dmrg_$N.jsonl gpurun_out/next_sharded_heff_$N.jsonl; tail -5 gpurun_out/next_sharded_dmrg_$N.err
