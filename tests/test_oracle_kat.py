@@ -220,3 +220,22 @@ def test_qjmc_ensemble_average_follows_the_lindblad_equation(classical):
         oracle.qjmc_simulation(sh, p, H, J, steps * dt, dt, uniforms=rng.random, classical=classical, cutoff=0, maxdim=0)
         acc += np.real(oracle.inner(sh, p, zs, p))
     assert np.max(np.abs(acc / M - exact)) < 0.15, (acc / M, exact)
+
+
+def test_thermal_mpo_energy_matches_exact_canonical_ensemble():
+    """examples/thermal.jl: the identity MPO evolved to beta/2 with the Trotter gates (rank-2 applygates!), energy =
+    trace(H, adjoint(U), U) / trace(adjoint(U), U) (mpo.jl:229-252), against tr(H exp(-beta H)) / tr(exp(-beta H)) from exact
+    diagonalisation (N = 6, beta = 1)."""
+    sh = oracle.spinhalf()
+    N, beta, dt = 6, 1.0, 0.01
+    Hl = tfim(N, 1.0, 0.0, 1.0)
+    gl = oracle.trotterize(sh, -1 * Hl, dt)
+    U = oracle.productMPO(sh, ["id"] * N)
+    for _ in range(int(round(beta / 2 / dt))):
+        oracle.applygates(U, gl, cutoff=1e-12, maxdim=64)
+    M = oracle.MPO(sh, Hl)
+    E = oracle.trace(M, oracle.adjoint(U), U) / oracle.trace(oracle.adjoint(U), U)
+    ev = np.linalg.eigvalsh(dense_hamiltonian(sh, Hl).toarray())
+    w = np.exp(-beta * (ev - ev[0]))
+    exact = float(np.sum(ev * w) / np.sum(w))
+    assert abs(E.imag) < 1e-10 and abs(E.real - exact) < 2e-4 * abs(exact)        # second-order Trotter error at dt = 0.01
