@@ -6,7 +6,15 @@
 N=${1:-1}
 mkdir -p gpurun_out
 if [ "$N" = "1" ]; then
-  TN_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests -q -m gpu > gpurun_out/next_gpu_tests.log 2>&1; tail -5 gpurun_out/next_gpu_tests.log
+  timeout 600 python -m pytest tests -q -m gpu > gpurun_out/next_gpu_tests.log 2>&1; tail -5 gpurun_out/next_gpu_tests.log
+  # the opt-in tests (device code that has never run on a GPU), one process each so that a crash in one cannot hide the others
+  : > gpurun_out/next_unverified.log
+  for T in qjmc_ensemble_batching_rounds sharded_heff_pipelined qjmc_front_end_with_observers applygates_fidelity itebd_step itebd_against_golden \
+           thermal_example_energy applympo_matches tebd_with_projector three_call_svd; do
+    echo "== $T" >> gpurun_out/next_unverified.log
+    TN_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_z_projsum.py -q -k "$T" >> gpurun_out/next_unverified.log 2>&1
+  done
+  grep -E "^==|passed|failed|error" gpurun_out/next_unverified.log
   timeout 120 python tools/bench_multigpu.py --what dmrg --lx 6 --ly 4 --chi 256 --sweeps 2 --check > gpurun_out/next_sharded_dmrg_1.jsonl 2> gpurun_out/next_sharded_dmrg_1.err
   cat gpurun_out/next_sharded_dmrg_1.jsonl; tail -3 gpurun_out/next_sharded_dmrg_1.err
   # QJMC C4 shapes: plain multi-stream ensemble vs batching rounds
