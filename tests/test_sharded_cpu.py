@@ -218,3 +218,50 @@ def test_distributed_jacobi_sweeps(world):
     m0 = outs[0][0]
     if world == 2:
         assert m0[3] == m0[2] * 3
+
+
+def test_distributed_jacobi_schedule_visits_every_block_pair_once_per_sweep():
+    """Pure schedule check (no arithmetic, no communication): over the ranks, one sweep of dist_jacobi_sweeps rotates every pair of
+    column blocks exactly once, a step never touches a block twice, and the moves keep every super-block with exactly one owner."""
+    sys.path.insert(0, os.path.join(ROOT, "tensornetworks.jl_b200"))
+    from tnb200.sharded import dist_jacobi_sweeps, usable_world
+
+    class Recorder:
+        def __init__(self):
+            self.steps, self.sends, self.recvs = [], [], []
+
+        def step(self, pairs):
+            flat = [b for p in pairs for b in p]
+            assert len(flat) == len(set(flat)), "a step touches a block twice"
+            self.steps.append(list(pairs))
+            return 1.0                       # never converged: exactly max_sweeps sweeps
+
+        def exchange(self, ops, k, dist):
+            for kind, sb, peer in ops:
+                (self.sends if kind == "send" else self.recvs).append((sb, peer))
+
+        def all_reduce_max(self, v, dist):
+            return v
+
+        def gather_all(self, owners, k, dist):
+            assert sorted(sb for sb, _ in owners) == list(range(len(owners)))
+
+    for nb, world in ((8, 2), (12, 3), (16, 4), (16, 2), (8, 3), (6, 3), (4, 8)):
+        recs = []
+        for rank in range(world):
+            r = Recorder()
+            assert dist_jacobi_sweeps(r, nb, 0.0, rank, world, None, max_sweeps=1) == 1
+            recs.append(r)
+        g = usable_world(nb, world)
+        seen = {}
+        ranks = range(g) if g > 1 else range(1)          # g == 1: every rank runs the whole (identical) sweep
+        for rank in ranks:
+            for st in recs[rank].steps:
+                for p, q in st:
+                    key = (min(p, q), max(p, q))
+                    seen[key] = seen.get(key, 0) + 1
+        assert len(seen) == nb * (nb - 1) // 2 and set(seen.values()) == {1}, (nb, world, len(seen))
+        # every send has its matching receive
+        sends = sorted((sb, src, dst) for src, r in enumerate(recs) for sb, dst in r.sends)
+        recvs = sorted((sb, src, dst) for dst, r in enumerate(recs) for sb, src in r.recvs)
+        assert sends == recvs
