@@ -200,6 +200,80 @@ class ShardedHeff:
         return self.out
 
 
+class BalancedShardedHeff:
+    """ShardedHeff with the two chi^3 stages split evenly for ANY MPO bond dimension (w = 20 on 8 GPUs is a 3/3/3/3/2/2/2/2 split of
+    whole bond values, an 83 % ceiling).  Stage 1 shards the fused row index (a, w) of L -- rank g owns rows [m0, m1) of the
+    (chi w) x chi matrix, whatever bond values they straddle: its GEMM writes them at their natural place in a zeroed
+    T1(a, w_first..w_last, s1', s2', b'), so stage 2 is the ordinary small contraction over those bond values.  Stage 3 shards the
+    fused contraction index k = (b', w2): the reduce_scatter hands out equal flat chunks of T2p(a, s1, s2, [b', w2]) and every rank
+    holds the matching rows of R in (k, a') layout.  Same collectives as ShardedHeff."""
+
+    def __init__(self, L, R, M1, M2, rank, world, contract, device, dist=None):
+        import torch
+        self.torch, self.dist, self.rank, self.world, self.contract = torch, dist, rank, world, contract
+        ca, w, cb = L.shape
+        ca2, w2, cb2 = R.shape
+        d = M1.shape[1]
+        d2 = d * d
+        self.dims = (ca, cb, ca2, cb2, d, w, w2)
+        mtot = ca * w
+        m0, m1 = (mtot * rank) // world, (mtot * (rank + 1)) // world
+        self.mloc = m1 - m0
+        w_first = m0 // ca if self.mloc > 0 else 0
+        w_last = (m1 - 1) // ca if self.mloc > 0 else 0
+        self.nw = w_last - w_first + 1
+        self.r0 = m0 - ca * w_first
+        ktot = cb2 * w2
+        self.c = (ktot + world - 1) // world
+        k0, k1 = min(rank * self.c, ktot), min((rank + 1) * self.c, ktot)
+        Lmat = np.reshape(L, (mtot, cb), order='F')
+        Wfull = dense_w(M1, M2)
+        Wg = Wfull.reshape(w, d2, d2 * w2, order='F')[w_first:w_last + 1].reshape(self.nw * d2, d2 * w2, order='F')
+        Rk = np.reshape(np.transpose(R, (2, 1, 0)), (ktot, ca2), order='F')        # rows k = b' + chi * w2
+        Rg = np.zeros((self.c, ca2), dtype=np.complex128)
+        Rg[:k1 - k0] = Rk[k0:k1]
+
+        def dev(x):
+            return torch.from_numpy(np.ascontiguousarray(np.reshape(x, -1, order='F'))).to(device)
+        self.Lg, self.Wg, self.Rg = dev(np.asfortranarray(Lmat[m0:m1])), dev(Wg), dev(Rg)
+        z = lambda n: torch.zeros(max(int(n), 1), dtype=torch.complex128, device=device)
+        self.T1 = z(ca * self.nw * d2 * cb2)           # rows outside [r0, r0 + mloc) stay zero
+        self.T2p = z(ca * d2 * self.c * world)
+        self.T2g = z(ca * d2 * self.c)
+        self.out = z(ca * d2 * ca2)
+
+    def apply(self, theta):
+        torch, dist = self.torch, self.dist
+        ca, cb, ca2, cb2, d, w, w2 = self.dims
+        d2, ct = d * d, self.contract
+        ld1 = ca * self.nw
+        if self.mloc > 0:
+            # T1[r0 + m, (s1',s2',b')] = L_g[m, b] Theta[b, (s1',s2',b')]
+            ct(self.mloc, d2 * cb2, cb, self.Lg, (BIG, 1, 0), (BIG, self.mloc, 0), theta, (BIG, 1, 0), (BIG, cb, 0),
+               self.T1[self.r0:], (BIG, 1, 0), (BIG, ld1, 0))
+            # T2p(a,s1,s2,b',w2) = sum_{(w,s1',s2')} T1(a,(w,s1',s2'),b') W_g[(w,s1',s2'),(s1,s2,w2)]
+            ct(ca * cb2, d2 * w2, self.nw * d2, self.T1, (ca, 1, ld1 * d2), (BIG, ca, 0), self.Wg, (BIG, 1, 0), (BIG, self.nw * d2, 0),
+               self.T2p, (ca, 1, ca * d2), (d2, ca, ca * d2 * cb2))
+        else:
+            self.T2p.zero_()
+        ct.sync()
+        if self.world > 1:
+            dist.reduce_scatter_tensor(torch.view_as_real(self.T2g), torch.view_as_real(self.T2p), op=dist.ReduceOp.SUM)
+        else:
+            self.T2g.copy_(self.T2p[:self.T2g.numel()])
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        # out[(a,s1,s2), a'] = sum_k T2g[(a,s1,s2), k] R_g[k, a']
+        ct(ca * d2, ca2, self.c, self.T2g, (BIG, 1, 0), (BIG, ca * d2, 0), self.Rg, (BIG, 1, 0), (BIG, self.c, 0),
+           self.out, (BIG, 1, 0), (BIG, ca * d2, 0))
+        ct.sync()
+        if self.world > 1:
+            dist.all_reduce(torch.view_as_real(self.out), op=dist.ReduceOp.SUM)
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+        return self.out
+
+
 # ---------------------------------------------------------------------------------------------
 # QJMC ensembles
 # ---------------------------------------------------------------------------------------------

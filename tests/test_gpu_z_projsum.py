@@ -618,3 +618,22 @@ def test_three_call_svd_with_external_schedule_matches_fused_svd():
                  svd_engine=eng)
     for a, b in zip(hg, hs):
         assert a[2] == b[2] and abs(a[1] - b[1]) < 1e-10 * abs(a[1])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TN_RUN_UNVERIFIED") != "1", reason="balanced sharded matvec: opt in with TN_RUN_UNVERIFIED=1")
+def test_balanced_sharded_heff_world1_matches_einsum():
+    import torch
+    import tnb200
+    from tnb200.sharded import BalancedShardedHeff, GpuContractor
+    rng = np.random.default_rng(0)
+    chi, d, w, w1, w2 = 48, 2, 7, 6, 5
+    L, R = crandn(rng, chi, w, chi), crandn(rng, chi, w2, chi)
+    M1, M2 = crandn(rng, w, d, d, w1), crandn(rng, w1, d, d, w2)
+    theta = crandn(rng, chi, d, d, chi)
+    want = np.einsum('awb,wstx,xuvy,btvc,eyc->asue', L, M1, M2, theta, R)
+    ctx = tnb200.Context.default()
+    sh = BalancedShardedHeff(L, R, M1, M2, 0, 1, GpuContractor(ctx), "cuda")
+    th = torch.from_numpy(np.reshape(theta, -1, order='F').copy()).cuda()
+    torch.cuda.synchronize()
+    out = sh.apply(th).cpu().numpy().reshape(chi, d, d, chi, order='F')
+    assert relerr(out, want) < 1e-13

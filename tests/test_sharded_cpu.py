@@ -58,6 +58,10 @@ def _worker(rank, world, port, q):
         out = sh.apply_pipelined(torch.from_numpy(np.reshape(theta, -1, order='F').copy()), nslices=ns)
         got = out.numpy().reshape(chi, d, d, chi + 2, order='F')
         err = max(err, np.linalg.norm(got - want) / np.linalg.norm(want))
+    from tnb200.sharded import BalancedShardedHeff
+    bal = BalancedShardedHeff(L, R, M1, M2, rank, world, NumpyContractor(), "cpu", dist)      # rows of (a,w) / flat (b',w2) chunks
+    got = bal.apply(torch.from_numpy(np.reshape(theta, -1, order='F').copy())).numpy().reshape(chi, d, d, chi + 2, order='F')
+    err = max(err, np.linalg.norm(got - want) / np.linalg.norm(want))
     res = run_ensemble(lambda t: (t, t * t), 7, rank, world, dist)
     q.put((rank, err, sorted(res.items())))
     dist.destroy_process_group()

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import tnb200
-from tnb200.sharded import ShardedHeff, GpuContractor, run_ensemble
+from tnb200.sharded import ShardedHeff, BalancedShardedHeff, GpuContractor, run_ensemble
 
 
 def main():
@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--pipeline", type=int, default=0, help="heff: slices of Theta's right bond for apply_pipelined (0 = plain apply)")
+    ap.add_argument("--balanced", action="store_true", help="heff: BalancedShardedHeff (even split of the fused (a,w) rows / (b',w2) contraction index)")
     ap.add_argument("--lx", type=int, default=6)
     ap.add_argument("--ly", type=int, default=4)
     ap.add_argument("--sweeps", type=int, default=2)
@@ -44,7 +45,8 @@ def main():
         L, R = cr(chi, w, chi), cr(chi, w, chi)
         M1, M2 = cr(w, d, d, w), cr(w, d, d, w)
         theta = cr(chi, d, d, chi)
-        sh = ShardedHeff(L, R, M1, M2, rank, world, GpuContractor(ctx), "cuda", dist if world > 1 else None)
+        cls = BalancedShardedHeff if a.balanced else ShardedHeff
+        sh = cls(L, R, M1, M2, rank, world, GpuContractor(ctx), "cuda", dist if world > 1 else None)
         th = torch.from_numpy(np.reshape(theta, -1, order='F').copy()).cuda()
         run = (lambda: sh.apply_pipelined(th, a.pipeline, ctx.stream())) if a.pipeline > 0 else (lambda: sh.apply(th))
         for _ in range(2):
@@ -78,7 +80,7 @@ def main():
                 err = float(np.linalg.norm(got - want) / np.linalg.norm(want))
         chk = float(torch.view_as_real(out).abs().sum().item())
         if rank == 0:
-            print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "pipeline_slices": a.pipeline, "ms_per_matvec": sec * 1e3,
+            print(json.dumps({"what": "heff_mpo_bond_sharded", "n_gpus": world, "chi": chi, "w": w, "pipeline_slices": a.pipeline, "balanced": bool(a.balanced), "ms_per_matvec": sec * 1e3,
                               "tflops_total": flops / sec / 1e12, "checksum": chk, "rel_err_vs_einsum": err,
                               "collectives": "NCCL reduce_scatter(T2 over w2) + all_reduce(out)" if world > 1 else "none"}), flush=True)
     elif a.what == "dmrg":

@@ -10,7 +10,7 @@ if [ "$N" = "1" ]; then
   # the opt-in tests (device code that has never run on a GPU), one process each so that a crash in one cannot hide the others
   : > gpurun_out/next_unverified.log
   for T in qjmc_ensemble_batching_rounds sharded_heff_pipelined qjmc_front_end_with_observers applygates_fidelity itebd_step itebd_against_golden \
-           thermal_example_energy applympo_matches tebd_with_projector three_call_svd; do
+           thermal_example_energy applympo_matches tebd_with_projector three_call_svd balanced_sharded_heff; do
     echo "== $T" >> gpurun_out/next_unverified.log
     TN_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_gpu_z_projsum.py -q -k "$T" >> gpurun_out/next_unverified.log 2>&1
   done
@@ -30,5 +30,8 @@ else
   timeout 500 $RUN tools/bench_multigpu.py --what dmrg --lx 12 --ly 6 --chi 1024 --sweeps 1 --dist-svd >> gpurun_out/next_sharded_dmrg_$N.jsonl 2>> gpurun_out/next_sharded_dmrg_$N.err
   # sharded matvec: plain vs pipelined reduce_scatter (must print the same checksum)
   for P in 0 4 8; do timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 24 --steps 3 --pipeline $P >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err; done
+  # w = 20 (the C5 MPO): whole-bond-value split vs the balanced split
+  timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 20 --steps 3 >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err
+  timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 20 --steps 3 --balanced >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err
   cat gpurun_out/next_sharded_dmrg_$N.jsonl gpurun_out/next_sharded_heff_$N.jsonl; tail -5 gpurun_out/next_sharded_dmrg_$N.err
 fi
