@@ -102,7 +102,7 @@ int32_t tn_mps_upload(tn_ctx* ctx, int32_t rank, int32_t d, int32_t N, const int
     std::vector<long long> dd((size_t)N * (rank + 2));
     for (size_t i = 0; i < dd.size(); ++i) dd[i] = dims[i];
     auto* h = new tn_mps();
-    h->m = mps_create(&ctx->c, rank, d, N, dd.data(), reinterpret_cast<const cplx* const*>(site_ptrs), center);
+    try { h->m = mps_create(&ctx->c, rank, d, N, dd.data(), reinterpret_cast<const cplx* const*>(site_ptrs), center); } catch (...) { delete h; throw; }
     *out = h;
   });
 }
@@ -294,7 +294,7 @@ int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cpl
   return guard([&] { TN_CHECK(ctx && bra && ket, "tn_env_create: null handle");
     TN_CHECK(ctx && bra && ket && out, "null pointer");
     auto* h = new tn_env();
-    h->e = env_create(&ctx->c, bra->m, mpo ? mpo->m : nullptr, ket->m, cplx{coeff.re, coeff.im}, center);
+    try { h->e = env_create(&ctx->c, bra->m, mpo ? mpo->m : nullptr, ket->m, cplx{coeff.re, coeff.im}, center); } catch (...) { delete h; throw; }
     *out = h;
   });
 }
@@ -392,7 +392,7 @@ int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* co
                         const tn_cplx* const* gate_ptrs, tn_gates** out) {
   return guard([&] { TN_CHECK(ctx, "tn_gates_upload: null handle");
     auto* h = new tn_gates();
-    h->g = gates_create(&ctx->c, d, nrows, counts, sites, nsites, reinterpret_cast<const cplx* const*>(gate_ptrs));
+    try { h->g = gates_create(&ctx->c, d, nrows, counts, sites, nsites, reinterpret_cast<const cplx* const*>(gate_ptrs)); } catch (...) { delete h; throw; }
     *out = h;
   });
 }
@@ -424,7 +424,7 @@ int32_t tn_env_create_squared(tn_ctx* ctx, tn_mps* V, tn_mps* psi, tn_cplx coeff
   return guard([&] { TN_CHECK(ctx && V && psi, "tn_env_create_squared: null handle");
     TN_CHECK(ctx && V && psi && out, "null pointer");
     auto* h = new tn_env();
-    h->e = env_create_squared(&ctx->c, V->m, psi->m, cplx{coeff.re, coeff.im}, center);
+    try { h->e = env_create_squared(&ctx->c, V->m, psi->m, cplx{coeff.re, coeff.im}, center); } catch (...) { delete h; throw; }
     *out = h;
   });
 }
