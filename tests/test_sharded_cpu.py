@@ -62,6 +62,9 @@ def _worker(rank, world, port, q):
     bal = BalancedShardedHeff(L, R, M1, M2, rank, world, NumpyContractor(), "cpu", dist)      # rows of (a,w) / flat (b',w2) chunks
     got = bal.apply(torch.from_numpy(np.reshape(theta, -1, order='F').copy())).numpy().reshape(chi, d, d, chi + 2, order='F')
     err = max(err, np.linalg.norm(got - want) / np.linalg.norm(want))
+    for ns in (2, 5):                                  # balanced + pipelined
+        got = bal.apply_pipelined(torch.from_numpy(np.reshape(theta, -1, order='F').copy()), nslices=ns).numpy().reshape(chi, d, d, chi + 2, order='F')
+        err = max(err, np.linalg.norm(got - want) / np.linalg.norm(want))
     res = run_ensemble(lambda t: (t, t * t), 7, rank, world, dist)
     q.put((rank, err, sorted(res.items())))
     dist.destroy_process_group()

@@ -33,5 +33,6 @@ else
   # w = 20 (the C5 MPO): whole-bond-value split vs the balanced split
   timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 20 --steps 3 >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err
   timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 20 --steps 3 --balanced >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err
+  timeout 200 $RUN tools/bench_multigpu.py --what heff --chi 2048 --w 20 --steps 3 --balanced --pipeline 4 >> gpurun_out/next_sharded_heff_$N.jsonl 2>> gpurun_out/next_sharded_heff_$N.err
   cat gpurun_out/next_sharded_dmrg_$N.jsonl gpurun_out/next_sharded_heff_$N.jsonl; tail -5 gpurun_out/next_sharded_dmrg_$N.err
 fi
