@@ -49,6 +49,21 @@ struct tn_mps { Mps* m; };
 struct tn_env { Env* e; };
 struct tn_gates { Gates* g; };
 struct tn_envsum { EnvSum* s; };
+struct tn_imps { IMps* m; };
+
+
+// Every handle remembers the device of its context; an entry point makes that device current for the calling thread before it
+// touches the handle, so that two contexts on different GPUs can be used from one process / thread.
+static inline void use_device_idx(int dev) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != dev) TN_CUDA(cudaSetDevice(dev));
+}
+static inline void use_device(tn_ctx* h) { use_device_idx(h->c.device); }
+static inline void use_device(tn_mps* h) { use_device_idx(h->m->ctx->device); }
+static inline void use_device(tn_env* h) { use_device_idx(h->e->ctx->device); }
+static inline void use_device(tn_gates* h) { use_device_idx(h->g->ctx->device); }
+static inline void use_device(tn_envsum* h) { use_device_idx(h->s->ctx->device); }
+static inline void use_device(tn_imps* h) { use_device_idx(h->m->ctx->device); }
 
 static thread_local std::string g_err;
 
@@ -83,10 +98,10 @@ int32_t tn_ctx_destroy(tn_ctx* ctx) {
     delete ctx;
   });
 }
-int32_t tn_sync(tn_ctx* ctx) { return guard([&] { TN_CHECK(ctx, "tn_sync: null handle"); ctx->c.sync(); }); }
-int32_t tn_ctx_stream(tn_ctx* ctx, void** s) { return guard([&] { TN_CHECK(ctx, "tn_ctx_stream: null handle"); *s = (void*)ctx->c.stream; }); }
+int32_t tn_sync(tn_ctx* ctx) { return guard([&] { TN_CHECK(ctx, "tn_sync: null handle"); use_device(ctx); ctx->c.sync(); }); }
+int32_t tn_ctx_stream(tn_ctx* ctx, void** s) { return guard([&] { TN_CHECK(ctx, "tn_ctx_stream: null handle"); use_device(ctx); *s = (void*)ctx->c.stream; }); }
 int32_t tn_counters(tn_ctx* ctx, int64_t* launches, int64_t* matvecs, int64_t* svds) {
-  return guard([&] { TN_CHECK(ctx, "tn_counters: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_counters: null handle"); use_device(ctx);
     if (launches) *launches = zgemm_launch_count();
     if (matvecs) *matvecs = ctx->c.matvecs;
     if (svds) *svds = ctx->c.svds;
@@ -96,7 +111,7 @@ int32_t tn_counters(tn_ctx* ctx, int64_t* launches, int64_t* matvecs, int64_t* s
 // ---- MPS ---------------------------------------------------------------------------------------
 int32_t tn_mps_upload(tn_ctx* ctx, int32_t rank, int32_t d, int32_t N, const int64_t* dims, const tn_cplx* const* site_ptrs,
                       int32_t center, tn_mps** out) {
-  return guard([&] { TN_CHECK(ctx, "tn_mps_upload: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_mps_upload: null handle"); use_device(ctx);
     TN_CHECK(ctx && dims && site_ptrs && out, "null pointer");
     TN_CHECK(center >= 0 && center <= N, "center out of range");
     std::vector<long long> dd((size_t)N * (rank + 2));
@@ -108,27 +123,27 @@ int32_t tn_mps_upload(tn_ctx* ctx, int32_t rank, int32_t d, int32_t N, const int
 }
 int32_t tn_mps_free(tn_mps* m) { return guard([&] { if (m) { mps_free(m->m); delete m; } }); }
 int32_t tn_mps_info(tn_mps* m, int32_t* rank, int32_t* d, int32_t* N, int32_t* center) {
-  return guard([&] { TN_CHECK(m, "tn_mps_info: null handle"); if (rank) *rank = m->m->rank; if (d) *d = m->m->d; if (N) *N = m->m->N; if (center) *center = m->m->center; });
+  return guard([&] { TN_CHECK(m, "tn_mps_info: null handle"); use_device(m); if (rank) *rank = m->m->rank; if (d) *d = m->m->d; if (N) *N = m->m->N; if (center) *center = m->m->center; });
 }
 int32_t tn_mps_dims(tn_mps* m, int64_t* dims) {
-  return guard([&] { TN_CHECK(m, "tn_mps_dims: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_dims: null handle"); use_device(m);
     int r = m->m->rank + 2;
     for (int i = 0; i < m->m->N; ++i) for (int k = 0; k < r; ++k) dims[(size_t)i * r + k] = m->m->sites[i].dims[k];
   });
 }
-int32_t tn_mps_download_site(tn_mps* m, int32_t site, tn_cplx* out) { return guard([&] { TN_CHECK(m, "tn_mps_download_site: null handle"); mps_download_site(m->m, site, C(out)); }); }
+int32_t tn_mps_download_site(tn_mps* m, int32_t site, tn_cplx* out) { return guard([&] { TN_CHECK(m, "tn_mps_download_site: null handle"); use_device(m); mps_download_site(m->m, site, C(out)); }); }
 int32_t tn_mps_upload_site(tn_mps* m, int32_t site, const int64_t* dims, const tn_cplx* data) {
-  return guard([&] { TN_CHECK(m, "tn_mps_upload_site: null handle"); std::vector<long long> dd(dims, dims + m->m->rank + 2); mps_upload_site(m->m, site, dd.data(), C(data)); });
+  return guard([&] { TN_CHECK(m, "tn_mps_upload_site: null handle"); use_device(m); std::vector<long long> dd(dims, dims + m->m->rank + 2); mps_upload_site(m->m, site, dd.data(), C(data)); });
 }
 int32_t tn_mps_set_center(tn_mps* m, int32_t center) {
-  return guard([&] { TN_CHECK(m, "tn_mps_set_center: null handle"); TN_CHECK(center >= 0 && center <= m->m->N, "center out of range"); m->m->center = center; });
+  return guard([&] { TN_CHECK(m, "tn_mps_set_center: null handle"); use_device(m); TN_CHECK(center >= 0 && center <= m->m->N, "center out of range"); m->m->center = center; });
 }
-int32_t tn_mps_maxbonddim(tn_mps* m, int64_t* out) { return guard([&] { TN_CHECK(m, "tn_mps_maxbonddim: null handle"); *out = m->m->maxbonddim(); }); }
-int32_t tn_mps_norm(tn_mps* m, tn_cplx* out) { return guard([&] { TN_CHECK(m, "tn_mps_norm: null handle"); cplx v = mps_norm(m->m); out->re = v.x; out->im = v.y; }); }
-int32_t tn_mps_normalize(tn_mps* m) { return guard([&] { TN_CHECK(m, "tn_mps_normalize: null handle"); mps_normalize(m->m); }); }
-int32_t tn_mps_movecenter(tn_mps* m, int32_t idx, tn_trunc_t tr) { return guard([&] { TN_CHECK(m, "tn_mps_movecenter: null handle"); mps_movecenter(m->m, idx, T(tr)); }); }
+int32_t tn_mps_maxbonddim(tn_mps* m, int64_t* out) { return guard([&] { TN_CHECK(m, "tn_mps_maxbonddim: null handle"); use_device(m); *out = m->m->maxbonddim(); }); }
+int32_t tn_mps_norm(tn_mps* m, tn_cplx* out) { return guard([&] { TN_CHECK(m, "tn_mps_norm: null handle"); use_device(m); cplx v = mps_norm(m->m); out->re = v.x; out->im = v.y; }); }
+int32_t tn_mps_normalize(tn_mps* m) { return guard([&] { TN_CHECK(m, "tn_mps_normalize: null handle"); use_device(m); mps_normalize(m->m); }); }
+int32_t tn_mps_movecenter(tn_mps* m, int32_t idx, tn_trunc_t tr) { return guard([&] { TN_CHECK(m, "tn_mps_movecenter: null handle"); use_device(m); mps_movecenter(m->m, idx, T(tr)); }); }
 int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta, int32_t site, int32_t direction, int32_t normalize, tn_trunc_t tr) {
-  return guard([&] { TN_CHECK(m, "tn_mps_replacesites: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_replacesites: null handle"); use_device(m);
     Mps* p = m->m; Ctx* c = p->ctx;
     TN_CHECK(site >= 1 && site + 1 <= p->N, "replacesites: site out of range");
     long long n = p->chiL(site) * p->phys() * p->phys() * p->chiR(site + 1);
@@ -139,7 +154,7 @@ int32_t tn_mps_replacesites(tn_mps* m, const tn_cplx* theta, int32_t site, int32
   });
 }
 int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op) {
-  return guard([&] { TN_CHECK(m, "tn_mps_applyop: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_applyop: null handle"); use_device(m);
     Mps* p = m->m; Ctx* c = p->ctx;
     TN_CHECK(site >= 1 && site <= p->N, "site out of range");
     cplx* d = c->scratch[15].get((size_t)p->d * p->d, c->stream);
@@ -149,7 +164,7 @@ int32_t tn_mps_applyop(tn_mps* m, int32_t site, const tn_cplx* op) {
   });
 }
 int32_t tn_mps_bond_spectrum(tn_mps* m, int32_t site, double* out, int64_t cap, int64_t* k_out) {
-  return guard([&] { TN_CHECK(m, "tn_mps_bond_spectrum: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_bond_spectrum: null handle"); use_device(m);
     std::vector<double> s; mps_bond_spectrum(m->m, site, s);
     TN_CHECK((int64_t)s.size() <= cap, "spectrum buffer too small");
     std::memcpy(out, s.data(), s.size() * sizeof(double));
@@ -175,7 +190,7 @@ int32_t tn_mps_copy(tn_mps* m, tn_mps** out) {      // deepcopy(psi): abstractmp
 }
 int32_t tn_mps_scale(tn_mps* m, tn_cplx a) {        // psi * a in place: the centre tensor (site 1 if unset) is multiplied, abstractmps.jl:99-109
   return guard([&] {
-    TN_CHECK(m, "tn_mps_scale: null handle");
+    TN_CHECK(m, "tn_mps_scale: null handle"); use_device(m);
     Mps* p = m->m;
     Tensor& t = p->sites[(p->center != 0 ? p->center : 1) - 1];
     zscal(t.size(), cplx{a.re, a.im}, t.p, p->ctx->stream);
@@ -191,15 +206,15 @@ int32_t tn_mpo_apply(tn_mps* O, tn_mps* psi, tn_trunc_t tr, tn_mps** out) {
     *out = h;
   });
 }
-int32_t tn_mpo_compress(tn_mps* m, tn_trunc_t tr) { return guard([&] { TN_CHECK(m, "tn_mpo_compress: null handle"); TN_CHECK(m != nullptr, "null pointer"); mpo_compress(m->m, T(tr)); m->m->ctx->sync(); }); }
+int32_t tn_mpo_compress(tn_mps* m, tn_trunc_t tr) { return guard([&] { TN_CHECK(m, "tn_mpo_compress: null handle"); use_device(m); TN_CHECK(m != nullptr, "null pointer"); mpo_compress(m->m, T(tr)); m->m->ctx->sync(); }); }
 int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_cplx* ops, tn_cplx* out) {
-  return guard([&] { TN_CHECK(m, "tn_expect_local: null handle"); expect_local(m->m, nops, sites, C(ops), C(out)); });
+  return guard([&] { TN_CHECK(m, "tn_expect_local: null handle"); use_device(m); expect_local(m->m, nops, sites, C(ops), C(out)); });
 }
 
 // ---- SVD ---------------------------------------------------------------------------------------
 int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t tr, tn_cplx* U, double* S, tn_cplx* Vh,
                      int64_t* k_out, int32_t* sweeps_out) {
-  return guard([&] { TN_CHECK(ctx, "tn_svd_trunc: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_svd_trunc: null handle"); use_device(ctx);
     Ctx* c = &ctx->c; cudaStream_t s = c->stream;
     TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
     cplx* dM = c->scratch[0].get((size_t)(m * n), s);
@@ -220,7 +235,7 @@ int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_t
 
 int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_t m, int64_t n, tn_trunc_t tr, tn_cplx* U, double* S,
                              tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out) {
-  return guard([&] { TN_CHECK(ctx, "tn_svd_trunc_batched: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_svd_trunc_batched: null handle"); use_device(ctx);
     Ctx* c = &ctx->c; cudaStream_t s = c->stream;
     TN_CHECK(B >= 1 && m >= 1 && n >= 1 && mats && U && S && Vh && k_out, "batched svd: bad arguments");
     const size_t mn = (size_t)(m * n), kmax = (size_t)std::min(m, n);
@@ -252,7 +267,7 @@ static Idx2 I2(tn_idx2_t i) { return Idx2{(int)std::min<int64_t>(i.n0, 0x7ffffff
 int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const tn_cplx* A, int64_t ae, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
                             const tn_cplx* B, int64_t be, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB, tn_cplx* Cc, int64_t ce,
                             tn_idx2_t cm, tn_idx2_t cn, tn_cplx alpha) {
-  return guard([&] { TN_CHECK(ctx, "tn_contract_strided: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_contract_strided: null handle"); use_device(ctx);
     Ctx* c = &ctx->c; cudaStream_t s = c->stream;
     cplx* dA = c->scratch[0].get((size_t)ae, s);
     cplx* dB = c->scratch[1].get((size_t)be, s);
@@ -276,7 +291,7 @@ int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const 
 int32_t tn_contract_strided_dev(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const void* A, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,
                                 const void* B, tn_idx2_t bk, tn_idx2_t bn, int32_t conjB, void* Cc, tn_idx2_t cm, tn_idx2_t cn,
                                 tn_cplx alpha, tn_cplx beta) {
-  return guard([&] { TN_CHECK(ctx, "tn_contract_strided_dev: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_contract_strided_dev: null handle"); use_device(ctx);
     TN_CHECK(M >= 0 && N >= 0 && K >= 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "contract: extent out of range");
     GemmDesc g{};
     g.M = (int)M; g.N = (int)N; g.K = (int)K;
@@ -291,7 +306,7 @@ int32_t tn_contract_strided_dev(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, co
 
 // ---- environments ------------------------------------------------------------------------------
 int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cplx coeff, int32_t center, tn_env** out) {
-  return guard([&] { TN_CHECK(ctx && bra && ket, "tn_env_create: null handle");
+  return guard([&] { TN_CHECK(ctx && bra && ket, "tn_env_create: null handle"); use_device(ctx);
     TN_CHECK(ctx && bra && ket && out, "null pointer");
     auto* h = new tn_env();
     try { h->e = env_create(&ctx->c, bra->m, mpo ? mpo->m : nullptr, ket->m, cplx{coeff.re, coeff.im}, center); } catch (...) { delete h; throw; }
@@ -299,22 +314,22 @@ int32_t tn_env_create(tn_ctx* ctx, tn_mps* bra, tn_mps* mpo, tn_mps* ket, tn_cpl
   });
 }
 int32_t tn_env_free(tn_env* e) { return guard([&] { if (e) { env_free(e->e); delete e; } }); }
-int32_t tn_env_buildleft(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_buildleft: null handle"); env_buildleft(e->e, idx); }); }
-int32_t tn_env_buildright(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_buildright: null handle"); env_buildright(e->e, idx); }); }
-int32_t tn_env_movecenter(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_movecenter: null handle"); env_movecenter(e->e, idx); }); }
-int32_t tn_env_center(tn_env* e, int32_t* out) { return guard([&] { TN_CHECK(e, "tn_env_center: null handle"); *out = e->e->center; }); }
+int32_t tn_env_buildleft(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_buildleft: null handle"); use_device(e); env_buildleft(e->e, idx); }); }
+int32_t tn_env_buildright(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_buildright: null handle"); use_device(e); env_buildright(e->e, idx); }); }
+int32_t tn_env_movecenter(tn_env* e, int32_t idx) { return guard([&] { TN_CHECK(e, "tn_env_movecenter: null handle"); use_device(e); env_movecenter(e->e, idx); }); }
+int32_t tn_env_center(tn_env* e, int32_t* out) { return guard([&] { TN_CHECK(e, "tn_env_center: null handle"); use_device(e); *out = e->e->center; }); }
 int32_t tn_env_block_dims(tn_env* e, int32_t idx, int64_t* dims3) {
-  return guard([&] { TN_CHECK(e, "tn_env_block_dims: null handle"); const Tensor& t = env_block(e->e, idx); for (int k = 0; k < 3; ++k) dims3[k] = t.dims[k]; });
+  return guard([&] { TN_CHECK(e, "tn_env_block_dims: null handle"); use_device(e); const Tensor& t = env_block(e->e, idx); for (int k = 0; k < 3; ++k) dims3[k] = t.dims[k]; });
 }
 int32_t tn_env_block_download(tn_env* e, int32_t idx, tn_cplx* out) {
-  return guard([&] { TN_CHECK(e, "tn_env_block_download: null handle");
+  return guard([&] { TN_CHECK(e, "tn_env_block_download: null handle"); use_device(e);
     const Tensor& t = env_block(e->e, idx);
     TN_CUDA(cudaMemcpyAsync(out, t.p, (size_t)t.size() * sizeof(cplx), cudaMemcpyDeviceToHost, e->e->ctx->stream));
     e->e->ctx->sync();
   });
 }
 int32_t tn_env_block_upload(tn_env* eh, int32_t idx, const int64_t* dims3, const tn_cplx* data) {
-  return guard([&] { TN_CHECK(eh, "tn_env_block_upload: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_block_upload: null handle"); use_device(eh);
     Env* e = eh->e; Ctx* c = e->ctx;
     TN_CHECK(idx >= 1 && idx <= e->ket->N, "block index out of range");
     Tensor& t = e->blocks[idx - 1];
@@ -324,7 +339,7 @@ int32_t tn_env_block_upload(tn_env* eh, int32_t idx, const int64_t* dims3, const
   });
 }
 int32_t tn_env_set_center(tn_env* eh, int32_t center) {
-  return guard([&] { TN_CHECK(eh, "tn_env_set_center: null handle"); TN_CHECK(center >= 0 && center <= eh->e->ket->N, "center out of range"); eh->e->center = center; });
+  return guard([&] { TN_CHECK(eh, "tn_env_set_center: null handle"); use_device(eh); TN_CHECK(center >= 0 && center <= eh->e->ket->N, "center out of range"); eh->e->center = center; });
 }
 static int product_site(Env* e, int direction) {   // projmps.jl:109
   TN_CHECK(e->center >= 1, "the environment centre is not set");
@@ -333,21 +348,21 @@ static int product_site(Env* e, int direction) {   // projmps.jl:109
   return site;
 }
 int32_t tn_env_product(tn_env* eh, const tn_cplx* theta, int32_t direction, tn_cplx* out) {
-  return guard([&] { TN_CHECK(eh, "tn_env_product: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_product: null handle"); use_device(eh);
     Env* e = eh->e;
     int site = product_site(e, direction);
     env_product_host(e, C(theta), site, C(out));
   });
 }
 int32_t tn_env_product_dev(tn_env* eh, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps) {
-  return guard([&] { TN_CHECK(eh, "tn_env_product_dev: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_product_dev: null handle"); use_device(eh);
     Env* e = eh->e;
     int site = product_site(e, direction);
     for (int r = 0; r < std::max(1, reps); ++r) env_product_dev(e, (const cplx*)theta_dev, site, (cplx*)out_dev);
   });
 }
 int32_t tn_env_product_profile(tn_env* eh, const void* theta_dev, int32_t direction, void* out_dev, int32_t reps, double* stage_ms3) {
-  return guard([&] { TN_CHECK(eh, "tn_env_product_profile: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_product_profile: null handle"); use_device(eh);
     Env* e = eh->e; Ctx* c = e->ctx;
     int site = product_site(e, direction);
     reps = std::max(1, reps);
@@ -361,11 +376,11 @@ int32_t tn_env_product_profile(tn_env* eh, const void* theta_dev, int32_t direct
     for (auto& x : ev) cudaEventDestroy(x);
   });
 }
-int32_t tn_env_calculate(tn_env* e, tn_cplx* out) { return guard([&] { TN_CHECK(e, "tn_env_calculate: null handle"); cplx v = env_calculate(e->e); out->re = v.x; out->im = v.y; }); }
+int32_t tn_env_calculate(tn_env* e, tn_cplx* out) { return guard([&] { TN_CHECK(e, "tn_env_calculate: null handle"); use_device(e); cplx v = env_calculate(e->e); out->re = v.x; out->im = v.y; }); }
 
 // ---- drivers -----------------------------------------------------------------------------------
 int32_t tn_dmrg_sweep(tn_mps* psi, tn_env* env, int32_t direction, tn_lanczos_t lz, tn_trunc_t tr, double* energy, int64_t* maxbond) {
-  return guard([&] { TN_CHECK(psi && env, "tn_dmrg_sweep: null handle");
+  return guard([&] { TN_CHECK(psi && env, "tn_dmrg_sweep: null handle"); use_device(psi);
     long long mb = 0;
     dmrg_halfsweep(psi->m, env->e, direction != 0, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, T(tr), energy, &mb);
     psi->m->ctx->sync();
@@ -373,7 +388,7 @@ int32_t tn_dmrg_sweep(tn_mps* psi, tn_env* env, int32_t direction, tn_lanczos_t 
   });
 }
 int32_t tn_eigsolve(tn_env* eh, const tn_cplx* theta0, int32_t direction, tn_lanczos_t lz, double* eig, tn_cplx* theta_out, int32_t* numops) {
-  return guard([&] { TN_CHECK(eh, "tn_eigsolve: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_eigsolve: null handle"); use_device(eh);
     Env* e = eh->e; Ctx* c = e->ctx; cudaStream_t s = c->stream;
     int site = product_site(e, direction);
     long long n = e->ket->chiL(site) * e->ket->d * e->ket->d * e->ket->chiR(site + 1);
@@ -390,7 +405,7 @@ int32_t tn_eigsolve(tn_env* eh, const tn_cplx* theta0, int32_t direction, tn_lan
 }
 int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* counts, const int32_t* sites, const int32_t* nsites,
                         const tn_cplx* const* gate_ptrs, tn_gates** out) {
-  return guard([&] { TN_CHECK(ctx, "tn_gates_upload: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_gates_upload: null handle"); use_device(ctx);
     auto* h = new tn_gates();
     try { h->g = gates_create(&ctx->c, d, nrows, counts, sites, nsites, reinterpret_cast<const cplx* const*>(gate_ptrs)); } catch (...) { delete h; throw; }
     *out = h;
@@ -398,10 +413,10 @@ int32_t tn_gates_upload(tn_ctx* ctx, int32_t d, int32_t nrows, const int32_t* co
 }
 int32_t tn_gates_free(tn_gates* g) { return guard([&] { if (g) { gates_free(g->g); delete g; } }); }
 int32_t tn_apply_gates(tn_mps* psi, tn_gates* gates, tn_trunc_t tr) {
-  return guard([&] { TN_CHECK(psi && gates, "tn_apply_gates: null handle"); apply_gates(psi->m, gates->g, T(tr)); psi->m->ctx->sync(); });
+  return guard([&] { TN_CHECK(psi && gates, "tn_apply_gates: null handle"); use_device(psi); apply_gates(psi->m, gates->g, T(tr)); psi->m->ctx->sync(); });
 }
 int32_t tn_apply_gates_fidelity(tn_mps* psi, tn_gates* gates, tn_trunc_t tr, double* fidelity_out) {
-  return guard([&] { TN_CHECK(psi && gates, "tn_apply_gates_fidelity: null handle");
+  return guard([&] { TN_CHECK(psi && gates, "tn_apply_gates_fidelity: null handle"); use_device(psi);
     TN_CHECK(psi && gates && fidelity_out, "null pointer");
     apply_gates(psi->m, gates->g, T(tr), fidelity_out);
     psi->m->ctx->sync();
@@ -411,7 +426,7 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
                     const double* jump_coeffs, int32_t steps, double dt, tn_trunc_t tr, const double* uniforms, uint64_t seed,
                     uint64_t trajectory, const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* jumps_out,
                     double* jumptimes_out, int32_t jump_cap, int32_t* njumps_out, int32_t classical) {
-  return guard([&] { TN_CHECK(psi && gates, "tn_qjmc_run: null handle");
+  return guard([&] { TN_CHECK(psi && gates, "tn_qjmc_run: null handle"); use_device(psi);
     int nj = qjmc_run(psi->m, gates->g, njump, jump_sites, C(jump_ops), jump_coeffs, steps, dt, T(tr), uniforms, seed, trajectory,
                       obs_op ? C(obs_op) : nullptr, save_every, obs_out ? C(obs_out) : nullptr, jumps_out, jumptimes_out, jump_cap,
                       classical != 0);
@@ -421,7 +436,7 @@ int32_t tn_qjmc_run(tn_mps* psi, tn_gates* gates, int32_t njump, const int32_t* 
 
 // ---- projector sums / squared projectors / project / one-site branch / vmps (tn_projsum.cu) ----------------------
 int32_t tn_env_create_squared(tn_ctx* ctx, tn_mps* V, tn_mps* psi, tn_cplx coeff, int32_t center, tn_env** out) {
-  return guard([&] { TN_CHECK(ctx && V && psi, "tn_env_create_squared: null handle");
+  return guard([&] { TN_CHECK(ctx && V && psi, "tn_env_create_squared: null handle"); use_device(ctx);
     TN_CHECK(ctx && V && psi && out, "null pointer");
     auto* h = new tn_env();
     try { h->e = env_create_squared(&ctx->c, V->m, psi->m, cplx{coeff.re, coeff.im}, center); } catch (...) { delete h; throw; }
@@ -465,21 +480,21 @@ static void envsum_project_host(EnvSum* es, int direction, int nsites, tn_cplx* 
   c->sync();
 }
 int32_t tn_env_product_n(tn_env* eh, const tn_cplx* A, int32_t direction, int32_t nsites, tn_cplx* out) {
-  return guard([&] { TN_CHECK(eh, "tn_env_product_n: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_product_n: null handle"); use_device(eh);
     TN_CHECK(eh && A && out, "null pointer");
     EnvSum one{eh->e->ctx, {eh->e}, eh->e->center};
     envsum_product_host(&one, A, direction, nsites, out);
   });
 }
 int32_t tn_env_project(tn_env* eh, int32_t direction, int32_t nsites, tn_cplx* out) {
-  return guard([&] { TN_CHECK(eh, "tn_env_project: null handle");
+  return guard([&] { TN_CHECK(eh, "tn_env_project: null handle"); use_device(eh);
     TN_CHECK(eh && out, "null pointer");
     EnvSum one{eh->e->ctx, {eh->e}, eh->e->center};
     envsum_project_host(&one, direction, nsites, out);
   });
 }
 int32_t tn_envsum_create(tn_ctx* ctx, int32_t n, tn_env* const* envs, int32_t center, tn_envsum** out) {
-  return guard([&] { TN_CHECK(ctx, "tn_envsum_create: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_envsum_create: null handle"); use_device(ctx);
     TN_CHECK(ctx && envs && out && n >= 1, "ProjMPSSum: bad arguments");
     std::vector<Env*> v;
     for (int i = 0; i < n; ++i) { TN_CHECK(envs[i] != nullptr, "ProjMPSSum: null projection"); v.push_back(envs[i]->e); }
@@ -489,17 +504,17 @@ int32_t tn_envsum_create(tn_ctx* ctx, int32_t n, tn_env* const* envs, int32_t ce
   });
 }
 int32_t tn_envsum_free(tn_envsum* s) { return guard([&] { if (s) { envsum_free(s->s); delete s; } }); }
-int32_t tn_envsum_movecenter(tn_envsum* s, int32_t idx) { return guard([&] { TN_CHECK(s, "tn_envsum_movecenter: null handle"); envsum_movecenter(s->s, idx); }); }
-int32_t tn_envsum_calculate(tn_envsum* s, tn_cplx* out) { return guard([&] { TN_CHECK(s, "tn_envsum_calculate: null handle"); cplx v = envsum_calculate(s->s); out->re = v.x; out->im = v.y; }); }
+int32_t tn_envsum_movecenter(tn_envsum* s, int32_t idx) { return guard([&] { TN_CHECK(s, "tn_envsum_movecenter: null handle"); use_device(s); envsum_movecenter(s->s, idx); }); }
+int32_t tn_envsum_calculate(tn_envsum* s, tn_cplx* out) { return guard([&] { TN_CHECK(s, "tn_envsum_calculate: null handle"); use_device(s); cplx v = envsum_calculate(s->s); out->re = v.x; out->im = v.y; }); }
 int32_t tn_envsum_product(tn_envsum* s, const tn_cplx* A, int32_t direction, int32_t nsites, tn_cplx* out) {
-  return guard([&] { TN_CHECK(s, "tn_envsum_product: null handle"); TN_CHECK(s && A && out, "null pointer"); envsum_product_host(s->s, A, direction, nsites, out); });
+  return guard([&] { TN_CHECK(s, "tn_envsum_product: null handle"); use_device(s); TN_CHECK(s && A && out, "null pointer"); envsum_product_host(s->s, A, direction, nsites, out); });
 }
 int32_t tn_envsum_project(tn_envsum* s, int32_t direction, int32_t nsites, tn_cplx* out) {
-  return guard([&] { TN_CHECK(s, "tn_envsum_project: null handle"); TN_CHECK(s && out, "null pointer"); envsum_project_host(s->s, direction, nsites, out); });
+  return guard([&] { TN_CHECK(s, "tn_envsum_project: null handle"); use_device(s); TN_CHECK(s && out, "null pointer"); envsum_project_host(s->s, direction, nsites, out); });
 }
 int32_t tn_dmrg_sweep_sum(tn_mps* psi, tn_envsum* Hs, int32_t direction, int32_t nsites, tn_lanczos_t lz, tn_trunc_t tr,
                           double* energy, int64_t* maxbond) {
-  return guard([&] { TN_CHECK(psi && Hs, "tn_dmrg_sweep_sum: null handle");
+  return guard([&] { TN_CHECK(psi && Hs, "tn_dmrg_sweep_sum: null handle"); use_device(psi);
     TN_CHECK(psi && Hs, "null pointer");
     long long mb = 0;
     dmrg_halfsweep_sum(psi->m, Hs->s, direction != 0, nsites, Lanczos{lz.krylovdim, lz.maxiter, lz.tol}, T(tr), energy, &mb);
@@ -508,7 +523,7 @@ int32_t tn_dmrg_sweep_sum(tn_mps* psi, tn_envsum* Hs, int32_t direction, int32_t
   });
 }
 int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsites, tn_trunc_t tr, int64_t* maxbond) {
-  return guard([&] { TN_CHECK(psi && Vs, "tn_vmps_sweep: null handle");
+  return guard([&] { TN_CHECK(psi && Vs, "tn_vmps_sweep: null handle"); use_device(psi);
     TN_CHECK(psi && Vs, "null pointer");
     long long mb = 0;
     vmps_halfsweep(psi->m, Vs->s, direction != 0, nsites, T(tr), &mb);
@@ -519,7 +534,7 @@ int32_t tn_vmps_sweep(tn_mps* psi, tn_envsum* Vs, int32_t direction, int32_t nsi
 
 // ---- device-pointer entry points for callers that orchestrate the sweep themselves (multi-GPU sharded DMRG) -------
 int32_t tn_mps_site_ptr(tn_mps* m, int32_t site, void** dev_out) {
-  return guard([&] { TN_CHECK(m, "tn_mps_site_ptr: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_site_ptr: null handle"); use_device(m);
     TN_CHECK(m && dev_out, "null pointer");
     TN_CHECK(site >= 1 && site <= m->m->N, "site index out of range");
     m->m->ctx->sync();
@@ -527,14 +542,14 @@ int32_t tn_mps_site_ptr(tn_mps* m, int32_t site, void** dev_out) {
   });
 }
 int32_t tn_mps_replacesites_dev(tn_mps* m, const void* theta_dev, int32_t site, int32_t direction, int32_t normalize, tn_trunc_t tr) {
-  return guard([&] { TN_CHECK(m, "tn_mps_replacesites_dev: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_replacesites_dev: null handle"); use_device(m);
     TN_CHECK(m && theta_dev, "null pointer");
     mps_replacesites2(m->m, (const cplx*)theta_dev, site, direction != 0, normalize != 0, T(tr));
     m->m->ctx->sync();
   });
 }
 int32_t tn_mps_upload_site_dev(tn_mps* m, int32_t site, const int64_t* dims, const void* data_dev) {
-  return guard([&] { TN_CHECK(m, "tn_mps_upload_site_dev: null handle");
+  return guard([&] { TN_CHECK(m, "tn_mps_upload_site_dev: null handle"); use_device(m);
     Mps* p = m->m; Ctx* c = p->ctx;
     TN_CHECK(site >= 1 && site <= p->N, "site index out of range");
     std::vector<long long> dd(dims, dims + p->rank + 2);
@@ -544,7 +559,7 @@ int32_t tn_mps_upload_site_dev(tn_mps* m, int32_t site, const int64_t* dims, con
   });
 }
 int32_t tn_memcpy_dev(tn_ctx* ctx, void* dst_dev, const void* src_dev, int64_t nbytes) {
-  return guard([&] { TN_CHECK(ctx, "tn_memcpy_dev: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_memcpy_dev: null handle"); use_device(ctx);
     TN_CHECK(ctx && dst_dev && src_dev && nbytes >= 0, "memcpy: bad arguments");
     TN_CUDA(cudaMemcpyAsync(dst_dev, src_dev, (size_t)nbytes, cudaMemcpyDeviceToDevice, ctx->c.stream));
     ctx->c.sync();
@@ -574,7 +589,7 @@ int32_t tn_svd_dist_finish(tn_ctx* ctx, tn_trunc_t tr, int32_t sweeps, int64_t* 
 }
 int32_t tn_svd_dist_factors(tn_ctx* ctx, void* U_dev, void* S_dev, void* Vh_dev) {
   return guard([&] {
-    TN_CHECK(ctx, "tn_svd_dist_factors: null handle");
+    TN_CHECK(ctx, "tn_svd_dist_factors: null handle"); use_device(ctx);
     Ctx* c = &ctx->c; cudaStream_t s = c->stream;
     if (U_dev) svd_gather_U(c->svd, (cplx*)U_dev, c->svd.m, false, s);
     if (Vh_dev) svd_gather_Vh(c->svd, (cplx*)Vh_dev, c->svd.k, false, s);
@@ -584,7 +599,7 @@ int32_t tn_svd_dist_factors(tn_ctx* ctx, void* U_dev, void* S_dev, void* Vh_dev)
 }
 int32_t tn_mps_replacesites_factored(tn_mps* m, int32_t site, int32_t direction, int32_t normalize) {
   return guard([&] {
-    TN_CHECK(m, "tn_mps_replacesites_factored: null handle");
+    TN_CHECK(m, "tn_mps_replacesites_factored: null handle"); use_device(m);
     mps_replacesites2_factored(m->m, site, direction != 0, normalize != 0);
     m->m->ctx->sync();
   });
@@ -592,7 +607,7 @@ int32_t tn_mps_replacesites_factored(tn_mps* m, int32_t site, int32_t direction,
 
 int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* theta_out_dev, tn_lanczos_t lz, tn_apply_fn apply, void* user,
                        double* eig, int32_t* numops) {
-  return guard([&] { TN_CHECK(ctx, "tn_eigsolve_fn: null handle");
+  return guard([&] { TN_CHECK(ctx, "tn_eigsolve_fn: null handle"); use_device(ctx);
     TN_CHECK(ctx && theta0_dev && theta_out_dev && apply && eig && n >= 1, "eigsolve: bad arguments");
     Ctx* c = &ctx->c;
     int ops = 0;
@@ -608,7 +623,6 @@ int32_t tn_eigsolve_fn(tn_ctx* ctx, int64_t n, const void* theta0_dev, void* the
 }
 
 // ---- infinite TEBD (Vidal form, two-site cell) ------------------------------------------------------------------
-struct tn_imps { IMps* m; };
 int32_t tn_imps_create(tn_ctx* ctx, int32_t d, int32_t L, const int64_t* dims, const tn_cplx* const* site_ptrs, const double* const* sing_ptrs,
                        tn_imps** out) {
   return guard([&] {
@@ -629,7 +643,7 @@ int32_t tn_imps_dims(tn_imps* p, int64_t* dims) {
 }
 int32_t tn_imps_download(tn_imps* p, int32_t site, tn_cplx* tensor_out, double* singulars_out, double* norm_out) {
   return guard([&] {
-    TN_CHECK(p, "tn_imps_download: null handle");
+    TN_CHECK(p, "tn_imps_download: null handle"); use_device(p);
     IMps* m = p->m; Ctx* c = m->ctx;
     TN_CHECK(site >= 1 && site <= m->L, "site index out of range");
     if (tensor_out) TN_CUDA(cudaMemcpyAsync(tensor_out, m->gam[site - 1].p, (size_t)m->gam[site - 1].size() * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
@@ -653,7 +667,7 @@ int32_t tn_itebd_apply_gate(tn_imps* p, const tn_cplx* gate_host, int32_t nsteps
 
 int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites, const tn_cplx* ops_host,
                         const tn_cplx* coeffs, tn_cplx* out) {
-  return guard([&] { TN_CHECK(psi && phi, "tn_inner_oplist: null handle");
+  return guard([&] { TN_CHECK(psi && phi, "tn_inner_oplist: null handle"); use_device(psi);
     TN_CHECK(psi && phi && (nterms == 0 || (nops && op_sites && ops_host && coeffs && out)), "inner: null pointer");
     TN_CHECK(psi->m->ctx == phi->m->ctx, "inner: both MPSs must live in the same context");
     inner_oplist(psi->m, phi->m, nterms, nops, op_sites, C(ops_host), C(coeffs), C(out));

@@ -6,6 +6,7 @@
 #include <string>
 #include <stdexcept>
 #include <vector>
+#include <mutex>
 
 namespace tn {
 
@@ -23,6 +24,16 @@ struct Error : std::runtime_error {
       throw tn::Error(-2, std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + \
                               ":" + std::to_string(__LINE__));                                      \
   } while (0)
+
+// Function attributes (opt-in shared memory sizes) are per device: run `fn` once for each device a kernel is launched on.
+struct DeviceOnce {
+  std::once_flag flags[32];
+  template <class F> void run(F&& fn) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::call_once(flags[dev & 31], fn);
+  }
+};
 
 #define TN_CHECK(cond, msg)                   \
   do {                                        \

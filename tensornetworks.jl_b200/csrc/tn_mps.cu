@@ -716,6 +716,7 @@ void gates_free(Gates* g) {
 static void applygate(Mps* psi, const Gate& g, bool direction, Trunc tr, double* fid = nullptr) {
   Ctx* c = psi->ctx; cudaStream_t s = c->stream;
   int d = psi->d, inner = psi->rank == 2 ? d : 1;
+  TN_CHECK(g.site >= 1 && g.site + g.nsites - 1 <= psi->N, "gate site out of range for this MPS");
   if (g.nsites == 1) {
     mps_applyop1(psi, g.site, g.dev);
     // replacesites!, one-site branch (gmps.jl:204-213): move the centre one site on, untruncated
@@ -746,6 +747,8 @@ static void applygate(Mps* psi, const Gate& g, bool direction, Trunc tr, double*
 void apply_gates(Mps* psi, Gates* g, Trunc tr, double* fid) {   // gatelist.jl:191-227 (fid != nullptr: applygates with error=true)
   if (fid) *fid = 1.0;
   TN_CHECK(g->d == psi->d, "gate / MPS physical dimension mismatch");
+  for (auto& row : g->rows)      // validate the whole list before the first gate changes psi
+    for (auto& gt : row) TN_CHECK(gt.site >= 1 && gt.site + gt.nsites - 1 <= psi->N, "gate site out of range for this MPS");
   for (auto& row : g->rows) {
     if (row.empty()) continue;
     int firstsite = row.front().site;
@@ -780,11 +783,14 @@ void expect_local(Mps* psi, int nops, const int* sites, const cplx* ops_host, cp
   Ctx* c = psi->ctx; cudaStream_t s = c->stream;
   TN_CHECK(psi->rank == 1, "expect_local: rank-1 MPS only");
   int d = psi->d, N = psi->N;
+  TN_CHECK(nops >= 0 && nops <= 1 << 20, "bad operator count");
+  if (nops == 0) return;
+  for (int k = 0; k < nops; ++k) TN_CHECK(sites[k] >= 1 && sites[k] <= N, "expect_local: operator site out of range");
   cplx* ops = c->scratch[15].get((size_t)nops * d * d + 64, s);
   TN_CUDA(cudaMemcpyAsync(ops, ops_host, (size_t)nops * d * d * sizeof(cplx), cudaMemcpyHostToDevice, s));
   Env* e = env_create(c, psi, nullptr, psi, ONE, 1);
-  TN_CHECK(nops >= 1 && nops <= 1 << 20, "bad operator count");
   cplx* dall; TN_CUDA(cudaMallocAsync((void**)&dall, sizeof(cplx) * nops, s));
+  TN_CUDA(cudaMemsetAsync(dall, 0, sizeof(cplx) * nops, s));
   for (int site = 1; site <= N; ++site) {
     bool any = false;
     for (int k = 0; k < nops; ++k) if (sites[k] == site) any = true;

@@ -4,6 +4,7 @@
 // the norm-based mode draws slot 0 (jump test against the decayed norm^2) and slot 1 (channel).
 #include "tn_mps.cuh"
 #include <cmath>
+#include <algorithm>
 
 namespace tn {
 
@@ -22,6 +23,8 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
   Ctx* c = psi->ctx;
   int d = psi->d, N = psi->N;
   TN_CHECK(psi->rank == 1, "qjmc: psi must be an MPS");
+  TN_CHECK(njump >= 0, "qjmc: negative jump-operator count");
+  for (int k = 0; k < njump; ++k) TN_CHECK(jump_sites[k] >= 1 && jump_sites[k] <= N, "qjmc: jump-operator site out of range");
   // escape operators L^dag L (qjmc.jl:11-20) and device copies of the jump operators
   std::vector<cplx> esc((size_t)njump * d * d);
   for (int k = 0; k < njump; ++k)
@@ -35,8 +38,10 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
         }
         esc[(size_t)k * d * d + i + d * j] = cplx{xr, xi};
       }
-  cplx* djump; TN_CUDA(cudaMalloc((void**)&djump, sizeof(cplx) * (size_t)njump * d * d));
-  TN_CUDA(cudaMemcpyAsync(djump, jump_ops, sizeof(cplx) * (size_t)njump * d * d, cudaMemcpyHostToDevice, c->stream));
+  struct DevBuf { cplx* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } djump_holder;     // released on every exit path
+  TN_CUDA(cudaMalloc((void**)&djump_holder.p, sizeof(cplx) * (size_t)std::max(njump, 1) * d * d));
+  cplx* djump = djump_holder.p;
+  if (njump > 0) TN_CUDA(cudaMemcpyAsync(djump, jump_ops, sizeof(cplx) * (size_t)njump * d * d, cudaMemcpyHostToDevice, c->stream));
   std::vector<cplx> ex(njump);
   std::vector<double> rates(njump);
   std::vector<int> all_sites(N);
@@ -46,6 +51,7 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
   double time = 0;
   auto draw = [&](int step, int slot) { return uniforms ? uniforms[(size_t)3 * step + slot] : counter_uniform(seed, traj, step, slot); };
   auto emission_rates = [&]() {                                    // qjmc.jl:170-220 on the normalised state
+    if (njump == 0) return 0.0;                                    // no channels: rates is empty, the trajectory never jumps
     expect_local(psi, njump, jump_sites, esc.data(), ex.data());
     double er = 0;
     for (int k = 0; k < njump; ++k) {
@@ -71,7 +77,7 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
       jump = r0 > prob;                                            // qjmc.jl:69
       if (jump) er = emission_rates();                             // qjmc.jl:71
     }
-    if (jump) {
+    if (jump && njump > 0) {
       double r = draw(i - 1, classical ? 2 : 1), cum = 0;          // qjmc.jl:74 / :99
       int idx = njump - 1;
       for (int k = 0; k < njump; ++k) { cum += rates[k]; if (r < cum / er) { idx = k; break; } }
@@ -88,7 +94,6 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
       expect_local(psi, N, all_sites.data(), obs_ops.data(), obs_out + (size_t)(i / save_every - 1) * N);
   }
   c->sync();
-  cudaFree(djump);
   return njumps;
 }
 

@@ -543,9 +543,9 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
   ensure(w.skip, w.skip_cap, (size_t)np, s);                // per-pair "already converged" flags
   const int* tab = pair_table(w, nb, s);
-  static bool evd_cfg = false;
+  static DeviceOnce evd_cfg;
   const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
-  if (!evd_cfg) { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem)); evd_cfg = true; }
+  evd_cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem)); });
   // Convergence threshold on |g_pq| / sqrt(g_pp g_qq).  The DMMA Gram blocks carry a rounding error of about sqrt(K) eps
   // (K = jrows accumulations, split-K partials summed in arbitrary order), so a threshold of exactly sqrt(K) eps makes
   // the last sweeps chase noise (9-11 sweeps run to run at n = 2048); 3 sqrt(K) eps sits just above that floor and is
@@ -630,9 +630,9 @@ static GemmDesc gd(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int con
 //   Q (rows x npad, ld = ldq) is overwritten by the orthonormal factor, R (npad x npad, ld = npad) receives the
 //   upper-triangular factor.  Everything is GEMM-shaped (tn_zgemm.cu) plus the 64x64 Cholesky kernel.
 static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, int chol_passes, cudaStream_t s) {
-  static bool cfg = false;
+  static DeviceOnce cfg;
   const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
-  if (!cfg) { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); cfg = true; }
+  cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); });
   TN_CUDA(cudaMemsetAsync(R, 0, (size_t)npad * npad * sizeof(cplx), s));
   ensure(w.Gpart, w.G_cap, (size_t)32 * JP * JP, s);
   int ksplit = std::max(1, std::min(std::min(32, max_split()), rows / 64));   // one 64 x 64 tile per panel: spread its K range over many SMs
@@ -764,8 +764,8 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   }
   colnorm2_kernel<<<npad, 128, 0, s>>>(w.Z, w.jrows, w.ldz, w.sig2);
   int npow2 = 64; while (npow2 < npad) npow2 <<= 1;
-  static bool sort_cfg = false;
-  if (!sort_cfg) { TN_CUDA(cudaFuncSetAttribute(sort_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12)); sort_cfg = true; }
+  static DeviceOnce sort_cfg;
+  sort_cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(sort_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12)); });
   sort_trunc_kernel<<<1, 1024, npow2 * 12, s>>>(w.sig2, npad, npow2, w.sig, w.perm, w.nsv, tr.cutoff, tr.maxdim, tr.mindim, w.kout);
   TN_CUDA(cudaGetLastError());
   count_launch(2);

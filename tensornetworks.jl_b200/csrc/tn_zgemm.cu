@@ -391,12 +391,9 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 static void launch2(const GemmDesc& d, cudaStream_t stream) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
-  static bool configured = false;
+  static DeviceOnce configured;
   auto kern = zgemm_kernel<WARPS_M, WARPS_N, TM, TN, KMODE>;
-  if (!configured) {
-    TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
-  }
+  configured.run([&] { TN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES)); });
   if (d.M <= 0 || d.N <= 0 || d.batch <= 0) return;
   unsigned tm = (d.M + Cfg::BM - 1) / Cfg::BM, tn_ = (d.N + Cfg::BN - 1) / Cfg::BN;
   GemmDesc dd = d;
@@ -405,16 +402,17 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
   dd.swap_raster = (d.batch * d.ksplit == 1 && (long long)d.M > (long long)d.N && tm <= 65535 && tn_ > 1) ? 1 : 0;
   if (d.streamk) {
     // stream-K: only when the plain launch would leave a partial last wave (or less than one wave) of CTAs
-    static int slots = 0;
+    static int slots = 0;          // identical B200s: the value of the first device holds for all
+    static DeviceOnce sk_configured;
     auto kern_sk = zgemm_sk_kernel<WARPS_M, WARPS_N, TM, TN, KMODE>;
-    if (slots == 0) {
+    sk_configured.run([&] {
       TN_CUDA(cudaFuncSetAttribute(kern_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
       int per_sm = 0, dev = 0, sms = 0;
       TN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_sk, Cfg::THREADS, Cfg::SMEM_BYTES));
       TN_CUDA(cudaGetDevice(&dev));
       TN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       slots = std::max(1, per_sm * sms);
-    }
+    });
     const long long T = (long long)tm * tn_;
     const int KT = (d.K + Cfg::BK - 1) / Cfg::BK;
     const long long waves = (T + slots - 1) / slots;

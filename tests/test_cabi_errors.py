@@ -22,6 +22,18 @@ def test_errors_are_reported_not_fatal():
         tnb200.ProjMPS(psi, H, psi)                         # projmps.jl:30 "GMPS must share the same length."
     with pytest.raises(tnb200.TNError):
         tnb200.dmrg(H, H)                                   # dmrg.jl:132 "Psi must be a GMPS of rank 1 (vector)."
+    # gate / jump / operator sites beyond the chain are rejected before psi is touched (gatelist.jl:209-217 would throw a BoundsError)
+    g2 = rng.standard_normal((2, 2, 2, 2)) + 0j
+    for bad in (2, 0, 7):
+        with pytest.raises(tnb200.TNError, match="out of range"):
+            tnb200.applygates(psi, tnb200.GateList(2, [[bad]], [[g2]]), cutoff=0.0)
+    with pytest.raises(tnb200.TNError, match="out of range"):
+        tnb200.applygates(psi, tnb200.GateList(2, [[3]], [[np.eye(2) + 0j]]), cutoff=0.0)
+    with pytest.raises(tnb200.TNError, match="out of range"):
+        psi.expect([np.eye(2) + 0j], [3])
+    gl = tnb200.GateList(2, [[1]], [[g2]])
+    with pytest.raises(tnb200.TNError, match="out of range"):
+        tnb200.qjmc_simulation(psi, gl, [4], [np.eye(2) + 0j], [1.0], 1, 0.01, uniforms=np.zeros(3))
     # the library is still usable afterwards
     psi.movecenter(2)
     assert abs(abs(psi.norm()) - np.linalg.norm(np.tensordot(t[0], t[1], axes=([2], [0])))) < 1e-12
