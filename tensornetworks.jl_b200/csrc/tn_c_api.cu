@@ -692,9 +692,11 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     std::mutex err_mu; std::string err; int err_code = 0;
     // TN_QJMC_BATCH=1: the workers' truncated SVDs are collected into batching rounds (tn_svd.cuh: SvdBatcher) -- every round
     // factorises the pending SVD of every active trajectory, grouped by shape, in one batched pipeline instead of nw
-    // concurrent single-problem pipelines.  Off by default until it has been timed on the GPU.
+    // concurrent single-problem pipelines.  On by default (C4 shapes on a B200, 32 trajectories x 2 steps: 1.00 -> 2.49
+    // trajectory-steps/s and 11x fewer launches, profiles/r02_first_run_qjmc_batching_and_sharded1.jsonl); TN_QJMC_BATCH=0
+    // restores the independent multi-stream workers.
     const char* benv = getenv("TN_QJMC_BATCH");
-    SvdBatcher* batcher = (benv && benv[0] == '1' && nw > 1) ? svd_batcher_create(nw) : nullptr;
+    SvdBatcher* batcher = (!(benv && benv[0] == '0') && nw > 1) ? svd_batcher_create(nw) : nullptr;
     auto worker = [&]() {
       Ctx c;
       Gates* g = nullptr; Mps* psi = nullptr;

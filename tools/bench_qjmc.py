@@ -56,7 +56,7 @@ def main():
     sec = float(t.item())
     if rank == 0:
         print(json.dumps({"what": "qjmc_ensemble", "n_gpus": world, "sites": N, "chi": chi, "steps_per_traj": a.steps, "trajectories": a.traj,
-                          "workers_per_gpu": a.workers, "svd_batching_rounds": os.environ.get("TN_QJMC_BATCH", "0") == "1", "seconds": sec, "traj_per_s": a.traj / sec, "traj_steps_per_s": a.traj * a.steps / sec,
+                          "workers_per_gpu": a.workers, "svd_batching_rounds": os.environ.get("TN_QJMC_BATCH", "1") != "0", "seconds": sec, "traj_per_s": a.traj / sec, "traj_steps_per_s": a.traj * a.steps / sec,
                           "jumps_total": int(stats[0].item()), "mean_sum_z": float(stats[1].item() / max(1.0, stats[2].item())),
                           "gpu_launches": int(stats[3].item()), "scaling": "weak-free (independent trajectories, no data-path collective)"}), flush=True)
     if world > 1:
