@@ -541,7 +541,7 @@ def main():
     if rank == 0:
         if extras:
             line["extras"] = extras
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N = 1 only (at N > 1 the other ranks' processes share the host cores)
             rows = min(REF_ROWS, chi)
             tf, calls, secs, cores, ref_out = cpu_reference_sample(chi, w, M1, M2, 4, 1, rows=rows, budget_s=25.0)
             got = dev_out.reshape(chi, D, D, chi, order='F')[:rows]
