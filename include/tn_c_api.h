@@ -90,6 +90,15 @@ int32_t tn_expect_local(tn_mps* m, int32_t nops, const int32_t* sites, const tn_
 int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t trunc,
                      tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
 
+/* The split the MPS drivers use (replacesites!, moveleft!/moveright!: gmps.jl:60-82, 218-256): one orthonormal factor (the new
+ * site tensor) and the other factor multiplied by S.  side = 1: U (m x k) orthonormal and Vh <- S V^H; side = 2: Vh (k x n)
+ * orthonormal and U <- U S.  When the orthonormal factor sits on the long side of the matrix (always for square ones) the right
+ * rotations of the Jacobi sweeps are not accumulated ("W-only": half the rotation flops) and the weighted factor is the projection
+ * of the input on the orthonormal one.  repeat > 1 re-runs the factorisation on the resident matrix; ms_out (nullable) receives
+ * the device time of the last run (factorisation + both gathers, no PCIe). */
+int32_t tn_svd_trunc_split(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t trunc, int32_t side,
+                           tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out, int32_t repeat, double* ms_out);
+
 /* B truncated SVDs of same-shape matrices in one batched factorisation (the gate / gauge-move SVDs of B QJMC trajectories that
  * advance in lockstep: every kernel launch of the single-problem pipeline covers all B problems).  mats: B consecutive m x n
  * column-major matrices on the host.  Problem b writes U at U + b*m*kmax (m x k_b), S at S + b*kmax, Vh at Vh + b*kmax*n

@@ -233,6 +233,39 @@ int32_t tn_svd_trunc(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_t
   });
 }
 
+// The split the MPS drivers use (gmps.jl:60-82, 218-256): one orthonormal factor and the other one multiplied by S.
+// side = 1: U (m x k) orthonormal, Vh <- S V^H;  side = 2: Vh (k x n) orthonormal, U <- U S.  repeat > 1 re-runs the
+// factorisation on the resident matrix (timing without the PCIe copies); *ms_out (optional) = device time of the last run.
+int32_t tn_svd_trunc_split(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n, tn_trunc_t tr, int32_t side, tn_cplx* U, double* S,
+                           tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out, int32_t repeat, double* ms_out) {
+  return guard([&] { TN_CHECK(ctx, "tn_svd_trunc_split: null handle"); use_device(ctx);
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    TN_CHECK(m >= 1 && n >= 1 && (side == 1 || side == 2) && mat && U && S && Vh && k_out, "svd split: bad arguments");
+    cplx* dM = c->scratch[0].get((size_t)(m * n), s);
+    TN_CUDA(cudaMemcpyAsync(dM, mat, (size_t)(m * n) * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    const size_t kmax = (size_t)std::min(m, n);
+    cplx* dU = c->scratch[1].get((size_t)m * kmax, s);
+    cplx* dV = c->scratch[2].get(kmax * (size_t)n, s);
+    cudaEvent_t e0, e1; TN_CUDA(cudaEventCreate(&e0)); TN_CUDA(cudaEventCreate(&e1));
+    int k = 0;
+    for (int r = 0; r < std::max(1, (int)repeat); ++r) {
+      TN_CUDA(cudaEventRecord(e0, s));
+      k = svd_factor(c->svd, dM, (int)m, (int)n, m, T(tr), s, side); c->svds++;
+      svd_gather_U(c->svd, dU, m, side == 2, s);
+      svd_gather_Vh(c->svd, dV, k, side == 1, s);
+      TN_CUDA(cudaEventRecord(e1, s));
+    }
+    TN_CUDA(cudaMemcpyAsync(U, dU, (size_t)(m * k) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(Vh, dV, (size_t)(k * n) * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(S, c->svd.sig, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    c->sync();
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms_out) *ms_out = ms;
+    *k_out = k;
+    if (sweeps_out) *sweeps_out = c->svd.sweeps;
+  });
+}
+
 int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_t m, int64_t n, tn_trunc_t tr, tn_cplx* U, double* S,
                              tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out) {
   return guard([&] { TN_CHECK(ctx, "tn_svd_trunc_batched: null handle"); use_device(ctx);

@@ -188,6 +188,176 @@ __global__ void __launch_bounds__(EVD_THREADS, 1) jacobi_evd64_kernel(const cplx
   for (int e = tid; e < JP * JP; e += EVD_THREADS) jo[e] = J[(e % JP) * LDS_ + (e / JP)];
 }
 
+
+// ---- second-generation pair EVD ---------------------------------------------------------------------------------------
+// Same mathematics as jacobi_evd64_kernel (parallel-order two-sided Jacobi on the 64 x 64 Hermitian Gram block, rotations
+// accumulated in J), reorganised around the measured bottleneck: the old kernel spent 1.8 us per rotation step, 2n of which
+// are strictly sequential per outer sweep.  Here
+//   * the J accumulation is taken off the critical path: J' = J R_step is independent row by row, so a second group of warps
+//     owns 8 rows of J each and replays the rotation parameters from a shared ring (one entry per step, written by the G
+//     group) -- it never takes part in the per-step barriers, only waits for the step counter;
+//   * the G group is 288 threads (two 2x2 blocks of the upper block triangle per thread, independent instruction streams)
+//     synchronised with a named barrier that the J warps do not join;
+//   * all index tables of a step (pair -> columns) are built once per kernel, not per step.
+constexpr int EVD2_G = 288;                    // threads updating G (9 warps)
+constexpr int EVD2_J = 256;                    // threads accumulating J (8 warps x 8 rows)
+constexpr int EVD2_THREADS = EVD2_G + EVD2_J;
+constexpr int EVD2_RING = (JP - 1) * JB;       // rotation parameters of one inner sweep
+constexpr size_t EVD2_SMEM = 2 * (size_t)JP * LDS_ * sizeof(cplx) + (size_t)EVD2_RING * (sizeof(double) + sizeof(cplx)) + (size_t)(JP - 1) * JP;
+
+__global__ void __launch_bounds__(EVD2_THREADS, 1) jacobi_evd64v2_kernel(const cplx* __restrict__ Gpart, int nsplit, long long split_stride,
+                                                                         cplx* __restrict__ Jout, double tol, unsigned long long* offmax, int max_inner, int nact,
+                                                                         int* __restrict__ skip_out) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cplx* G = reinterpret_cast<cplx*>(sm_raw);     // G[row*LDS_ + col], upper triangle (row <= col) kept up to date
+  cplx* J = G + JP * LDS_;
+  double* ring_c = reinterpret_cast<double*>(J + JP * LDS_);            // [step][k] cosine
+  cplx* ring_s = reinterpret_cast<cplx*>(ring_c + EVD2_RING);           // [step][k] sine (complex)
+  unsigned char* pq = reinterpret_cast<unsigned char*>(ring_s + EVD2_RING);   // [step][2k], [step][2k+1]: the columns of pair k
+  __shared__ double red[EVD2_THREADS / 32];
+  __shared__ unsigned char blk_a[NBLK], blk_b[NBLK];
+  __shared__ volatile int ready;               // steps of the current inner sweep whose parameters are in the ring
+  __shared__ int rotated;
+  const int tid = threadIdx.x;
+  const int nsteps = nact - 1, npairs = nact / 2;
+  for (int e = tid; e < JB * JB; e += EVD2_THREADS) {
+    int a = e >> 5, b = e & 31;
+    if (a <= b) { int i = a * JB - a * (a - 1) / 2 + (b - a); blk_a[i] = (unsigned char)a; blk_b[i] = (unsigned char)b; }
+  }
+  for (int e = tid; e < nsteps * JB; e += EVD2_THREADS) {
+    int st = e / JB, k = e - st * JB, p = 0, q = 0;
+    if (k < npairs) rr_pair(nact, st, k, p, q);
+    pq[st * JP + 2 * k] = (unsigned char)p; pq[st * JP + 2 * k + 1] = (unsigned char)q;
+  }
+  if (tid == 0) { ready = 0; rotated = 0; }
+  const cplx* gp = Gpart + (long long)blockIdx.x * JP * JP;
+  for (int e = tid; e < JP * JP; e += EVD2_THREADS) {
+    int row = e % JP, col = e / JP;
+    double xr = 0, xi = 0;
+    for (int s = 0; s < nsplit; ++s) { cplx v = gp[s * split_stride + e]; xr += v.x; xi += v.y; }
+    G[row * LDS_ + col] = make_double2(xr, xi);
+    J[row * LDS_ + col] = make_double2(row == col ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  // symmetrise (the two triangles come from different DMMA accumulation orders) and measure the off-diagonals
+  double mx = 0;
+  for (int e = tid; e < JP * JP; e += EVD2_THREADS) {
+    int row = e % JP, col = e / JP;
+    if (row < col) {
+      cplx a = G[row * LDS_ + col], b = G[col * LDS_ + row];
+      cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+      G[row * LDS_ + col] = h;
+      double dd = G[row * LDS_ + row].x * G[col * LDS_ + col].x;
+      double off2 = h.x * h.x + h.y * h.y;
+      if (dd > 0) mx = fmax(mx, off2 / dd);
+      else if (off2 > 0) mx = fmax(mx, 1.0);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < EVD2_THREADS / 32; ++i) mx = fmax(mx, red[i]);
+  mx = sqrt(mx);
+  if (tid == 0) atomicMax(offmax, (unsigned long long)__double_as_longlong(mx));
+  cplx* jo = Jout + (long long)blockIdx.x * JP * JP;
+  if (tid == 0 && skip_out) skip_out[blockIdx.x] = (mx <= tol) ? 1 : 0;   // the rotation GEMM skips converged pairs
+  if (mx <= tol) {   // already orthogonal: identity rotation
+    for (int e = tid; e < JP * JP; e += EVD2_THREADS) jo[e] = make_double2((e % JP) == (e / JP) ? 1.0 : 0.0, 0.0);
+    return;
+  }
+  const double tol2 = tol * tol;
+  const bool ggroup = tid < EVD2_G;
+  const int jt = tid - EVD2_G, jwarp = jt >> 5, lane = tid & 31;
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
+    if (ggroup) {
+      for (int step = 0; step < nsteps; ++step) {
+        const unsigned char* pqs = pq + step * JP;
+        if (tid < JB) {
+          const int p = pqs[2 * tid], q = pqs[2 * tid + 1];
+          double a = G[p * LDS_ + p].x, b = G[q * LDS_ + q].x;
+          cplx c = G[p * LDS_ + q];
+          double absc2 = c.x * c.x + c.y * c.y;
+          double cs = 1.0; cplx s = make_double2(0, 0);
+          if (tid < npairs && absc2 > tol2 * fabs(a * b) && absc2 > 0) {
+            double dl = 0.5 * (b - a);
+            double h = fabs(dl) + sqrt(fma(dl, dl, absc2));
+            double qq = rsqrt(fma(h, h, absc2));
+            cs = h * qq;
+            double sg = dl >= 0 ? qq : -qq;
+            s = make_double2(sg * c.x, sg * c.y);
+            rotated = 1;
+          }
+          ring_c[step * JB + tid] = cs; ring_s[step * JB + tid] = s;
+          __syncwarp();
+          if (tid == 0) { __threadfence_block(); ready = step + 1; }
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(EVD2_G) : "memory");
+        const double* rc = ring_c + step * JB; const cplx* rs = ring_s + step * JB;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int blk = tid + it * EVD2_G;
+          if (blk < NBLK) {
+            // G block (pair a rows, pair b cols), a <= b only: G' = R_a^H (G R_b),  R = [[cs, s], [-conj(s), cs]]
+            const int a = blk_a[blk], b = blk_b[blk];
+            const double ca = rc[a], cb = rc[b]; const cplx sa = rs[a], sb = rs[b];
+            const bool ra = !(sa.x == 0.0 && sa.y == 0.0), rb = !(sb.x == 0.0 && sb.y == 0.0);
+            if ((ra || rb) && b < npairs) {
+              const int pa = pqs[2 * a], qa = pqs[2 * a + 1], pb = pqs[2 * b], qb = pqs[2 * b + 1];
+              cplx g00, g01, g10, g11;
+              if (a == b) {
+                g00 = make_double2(G[pa * LDS_ + pa].x, 0.0); g11 = make_double2(G[qa * LDS_ + qa].x, 0.0);
+                g01 = G[pa * LDS_ + qa]; g10 = make_double2(g01.x, -g01.y);
+              } else {
+                g00 = herm_get(G, pa, pb); g01 = herm_get(G, pa, qb); g10 = herm_get(G, qa, pb); g11 = herm_get(G, qa, qb);
+              }
+              cplx t00, t01, t10, t11;
+              { cplx y = cmulc(g01, sb), x = cmul(g00, sb); t00 = make_double2(cb * g00.x - y.x, cb * g00.y - y.y); t01 = make_double2(x.x + cb * g01.x, x.y + cb * g01.y); }
+              { cplx y = cmulc(g11, sb), x = cmul(g10, sb); t10 = make_double2(cb * g10.x - y.x, cb * g10.y - y.y); t11 = make_double2(x.x + cb * g11.x, x.y + cb * g11.y); }
+              cplx n00, n01, n10, n11;
+              { cplx y = cmul(sa, t10), x = cmulc(t00, sa); n00 = make_double2(ca * t00.x - y.x, ca * t00.y - y.y); n10 = make_double2(x.x + ca * t10.x, x.y + ca * t10.y); }
+              { cplx y = cmul(sa, t11), x = cmulc(t01, sa); n01 = make_double2(ca * t01.x - y.x, ca * t01.y - y.y); n11 = make_double2(x.x + ca * t11.x, x.y + ca * t11.y); }
+              if (a == b) {
+                G[pa * LDS_ + pa] = make_double2(n00.x, 0.0); G[qa * LDS_ + qa] = make_double2(n11.x, 0.0);
+                G[pa * LDS_ + qa] = n01;
+              } else {
+                herm_put(G, pa, pb, n00); herm_put(G, pa, qb, n01); herm_put(G, qa, pb, n10); herm_put(G, qa, qb, n11);
+              }
+            }
+          }
+        }
+        asm volatile("bar.sync 1, %0;" :: "n"(EVD2_G) : "memory");
+      }
+    } else {
+      // J warps: rows [8 jwarp, 8 jwarp + 8), lane = pair; they trail the G group by polling the step counter
+      for (int step = 0; step < nsteps; ++step) {
+        if (lane == 0) { while (ready <= step) { } }
+        __syncwarp();
+        const double cs = ring_c[step * JB + lane]; const cplx s = ring_s[step * JB + lane];
+        if (!(s.x == 0.0 && s.y == 0.0)) {
+          const int p = pq[step * JP + 2 * lane], q = pq[step * JP + 2 * lane + 1];
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int row = jwarp * 8 + r;
+            cplx x = J[row * LDS_ + p], y = J[row * LDS_ + q];
+            cplx ys = cmulc(y, s), xs = cmul(x, s);
+            J[row * LDS_ + p] = make_double2(cs * x.x - ys.x, cs * x.y - ys.y);
+            J[row * LDS_ + q] = make_double2(xs.x + cs * y.x, xs.y + cs * y.y);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();                 // both groups have finished this inner sweep: the ring can be reused
+    const int any = rotated;
+    __syncthreads();
+    if (tid == 0) { ready = 0; rotated = 0; }
+    __syncthreads();
+    if (!any) break;
+  }
+  for (int e = tid; e < JP * JP; e += EVD2_THREADS) jo[e] = J[(e % JP) * LDS_ + (e / JP)];
+}
+
 // ---- preparation / finalisation kernels -----------------------------------------------------
 __global__ void __launch_bounds__(256) svd_init_kernel(const cplx* __restrict__ M, long long ld, int m, int n, int transposed,
                                                         cplx* __restrict__ Z, int rows, int ncols, int ncols_pad, int ldz) {
@@ -271,7 +441,7 @@ __global__ void __launch_bounds__(1024) sort_trunc_kernel(const double* __restri
 
 // out[r, j] = src[r, perm[j]] * scale_j                (transpose_out = 0)
 // out[j, r] = conj(src[r, perm[j]]) * scale_j          (transpose_out = 1)
-// scale: 0 -> 1, 1 -> sigma_j, 2 -> 1/sigma_j (0 if sigma_j == 0)
+// scale: 0 -> 1, 1 -> sigma_j, 2 -> 1/sigma_j (0 if sigma_j == 0), 3 -> 1/sigma_j^2
 __global__ void __launch_bounds__(256) gather_kernel(const cplx* __restrict__ src, int lds, int rows, int k, const int* __restrict__ perm,
                                                       const double* __restrict__ sig, int scale_mode, int transpose_out,
                                                       cplx* __restrict__ out, long long ldo) {
@@ -284,6 +454,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const cplx* __restrict__ sr
     double sc = 1.0;
     if (scale_mode == 1) sc = sig[j];
     else if (scale_mode == 2) sc = sig[j] > 0 ? 1.0 / sig[j] : 0.0;
+    else if (scale_mode == 3) sc = sig[j] > 0 ? 1.0 / (sig[j] * sig[j]) : 0.0;
     if (!transpose_out) out[r + (long long)j * ldo] = make_double2(v.x * sc, v.y * sc);
     else out[j + (long long)r * ldo] = make_double2(v.x * sc, -v.y * sc);
   }
@@ -455,6 +626,25 @@ __global__ void __launch_bounds__(256) set_identity_kernel(cplx* __restrict__ ds
 }
 
 // ---- host driver ------------------------------------------------------------------------------
+
+// Launches the pair EVD over `npairs` Gram blocks (TN_SVD_EVD=1 selects the first-generation kernel).
+static void launch_evd(int npairs, const cplx* Gp, cplx* Jp, double tol, unsigned long long* offmax, int inner, int nact, int* skip, cudaStream_t s) {
+  static int ver = -1;
+  if (ver < 0) { const char* e = getenv("TN_SVD_EVD"); ver = (e && e[0] == '1') ? 1 : 2; }
+  if (ver == 1) {
+    static DeviceOnce cfg1;
+    const int smem = 2 * JP * LDS_ * (int)sizeof(cplx);
+    cfg1.run([&] { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+    jacobi_evd64_kernel<<<npairs, EVD_THREADS, smem, s>>>(Gp, 1, 0, Jp, tol, offmax, inner, nact, skip);
+  } else {
+    static DeviceOnce cfg2;
+    cfg2.run([&] { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EVD2_SMEM)); });
+    jacobi_evd64v2_kernel<<<npairs, EVD2_THREADS, EVD2_SMEM, s>>>(Gp, 1, 0, Jp, tol, offmax, inner, nact, skip);
+  }
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
+
 template <class T>
 static void ensure(T*& p, size_t& cap, size_t need, cudaStream_t s) {
   if (need <= cap) return;
@@ -501,6 +691,17 @@ static int max_split() {
   return v;
 }
 
+static double early_stop() {
+  static double v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_EARLY"); v = e ? atof(e) : 1e-9; }
+  return v;
+}
+static bool wonly_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_WONLY"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
 
 // Optional phase timing (TN_SVD_PROFILE=1): CUDA events at the phase boundaries, summed per factorisation and printed
@@ -543,9 +744,6 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   ensure(w.J, w.J_cap, (size_t)np * JP * JP, s);
   ensure(w.skip, w.skip_cap, (size_t)np, s);                // per-pair "already converged" flags
   const int* tab = pair_table(w, nb, s);
-  static DeviceOnce evd_cfg;
-  const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
-  evd_cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem)); });
   // Convergence threshold on |g_pq| / sqrt(g_pp g_qq).  The DMMA Gram blocks carry a rounding error of about sqrt(K) eps
   // (K = jrows accumulations, split-K partials summed in arbitrary order), so a threshold of exactly sqrt(K) eps makes
   // the last sweeps chase noise (9-11 sweeps run to run at n = 2048); 3 sqrt(K) eps sits just above that floor and is
@@ -586,12 +784,10 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         if (g.atomic_c) TN_CUDA(cudaMemsetAsync(Gg, 0, (size_t)npg * JP * JP * sizeof(cplx), gs));
         zgemm_auto(g, gs);
         if (marks) prof().mark(PH_GRAM, gs);
-        jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, gs>>>(Gg, 1, 0, Jg, tol, w.offmax, inner_sweeps, nact, w.skip + p0);
-        TN_CUDA(cudaGetLastError());
-        count_launch(1);
+        launch_evd(npg, Gg, Jg, tol, w.offmax, inner_sweeps, nact, w.skip + p0, gs);
         if (marks) prof().mark(PH_EVD, gs);
         GemmDesc a{};
-        a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;   // W rows + V rows (ldz may carry padding rows)
+        a.M = jrows + (w.wonly ? 0 : w.ncols_pad); a.N = JP; a.K = JP;   // W rows (+ V rows unless W-only; ldz may carry padding rows)
         a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
         a.B = Jg; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
         // in place (each CTA owns 128 rows x all 64 columns of its pair); pairs whose Gram block was already diagonal
@@ -613,7 +809,9 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
     double off; std::memcpy(&off, &bits, 8);
     w.last_off = off;
     w.sweeps = sweep + 1;
-    if (off <= tol) break;
+    // `off` was measured BEFORE this sweep's rotations; the sweeps converge quadratically, so a sweep that started below
+    // ~1e-9 ends below the threshold and the Gram-only verification sweep is not needed
+    if (off <= tol || off <= early_stop()) break;
   }
 }
 
@@ -707,12 +905,12 @@ static int pad_ld(int rows) {
 static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s);
 static thread_local SvdBatcher* tl_batcher = nullptr;
 
-int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso) {
   TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
   w.use_view = false;
   if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s);
   w.m = m; w.n = n;
-  w.transposed = m < n;
+  w.transposed = m < n || (m == n && iso == 2);       // a square matrix is factorised in the orientation whose long-side factor is the isometry
   w.rows = w.transposed ? n : m;
   w.ncols = w.transposed ? m : n;
   w.nsv = w.ncols;
@@ -720,6 +918,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
   const int npad = w.ncols_pad;
   w.precond = precond_enabled() && npad > JP;
+  w.wonly = w.precond && wonly_enabled() && ((iso == 1 && !w.transposed) || (iso == 2 && w.transposed));
   if (w.s_cap < (size_t)npad) {
     if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
     TN_CUDA(cudaMallocAsync((void**)&w.sig, npad * sizeof(double), s));
@@ -747,16 +946,20 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
     svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Q1, w.rows, w.ncols, npad, w.rows);   // ldz = rows: no identity part
     count_launch(1);
     bgs_qr(w, w.Q1, w.rows, w.rows, npad, s);                    // Ra = R1
+    if (w.wonly) {                                               // keep R1: S V_T^H = U'^H R1 (see tn_svd.cuh)
+      ensure(w.R1, w.R1_cap, (size_t)npad * npad, s);
+      TN_CUDA(cudaMemcpyAsync(w.R1, w.Ra, (size_t)npad * npad * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+    }
     ensure(w.Q2, w.Q2_cap, (size_t)npad * npad, s);
     launch_1d((long long)npad * npad, blocks);
     conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Q2, npad);   // Q2 <- R1^H
     count_launch(1);
     bgs_qr(w, w.Q2, npad, npad, npad, s);                        // Ra = R2
     w.jrows = npad;
-    w.ldz = pad_ld(2 * npad);
+    w.ldz = pad_ld(w.wonly ? npad : 2 * npad);
     ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
     conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, npad, npad, w.Z, w.ldz);   // W <- R2^H
-    set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
+    if (!w.wonly) set_identity_kernel<<<blocks, 256, 0, s>>>(w.Z + npad, w.ldz, npad);
     TN_CUDA(cudaGetLastError());
     count_launch(2);
     pf.mark(PH_QR, s);
@@ -807,6 +1010,16 @@ static void precond_right(SvdWork& w, int scale_mode, cplx* out, long long ldo, 
   else zgemm_auto(gd(k, w.ncols, npad, w.Tg, idx1(npad), idx1(1), 1, w.Q2, idx1(npad), idx1(1), 1, out, idx1(1), idx1(ldo)), s);
 }
 
+// W-only mode: the factor on the short side of the tall orientation T, [S] V_T^H = (W [/sigma^2 | /sigma])(:,perm)^H R1 (k x ncols),
+// or its conjugate transpose (ncols x k).  Without S the rows are divided by sigma_j (callers of the W-only mode ask for S).
+static void wonly_other(SvdWork& w, bool times_S, cplx* out, long long ldo, bool conj_transposed, cudaStream_t s) {
+  const int npad = w.ncols_pad, k = w.k;
+  ensure(w.Tg, w.Tg_cap, (size_t)npad * std::max(k, 1), s);
+  gather(w.Z, w.ldz, npad, k, w.perm, w.sig, times_S ? 2 : 3, 0, w.Tg, npad, s);
+  if (!conj_transposed) zgemm_auto(gd(k, w.ncols, npad, w.Tg, idx1(npad), idx1(1), 1, w.R1, idx1(1), idx1(npad), 0, out, idx1(1), idx1(ldo)), s);
+  else zgemm_auto(gd(w.ncols, k, npad, w.R1, idx1(npad), idx1(1), 1, w.Tg, idx1(1), idx1(npad), 0, out, idx1(1), idx1(ldo)), s);
+}
+
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
   if (w.use_view) {      // factors of a batching round: gather from this thread's slot, with this thread's scratch
     SvdWork& v = *w.bview; v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
@@ -816,6 +1029,7 @@ void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t
   }
   if (w.precond) {
     if (!w.transposed) precond_left(w, times_S ? 0 : 2, U, ldu, false, s);       // Q1 (W[/sigma])
+    else if (w.wonly) wonly_other(w, times_S, U, ldu, true, s);                  // ([S] V_T^H)^H
     else precond_right(w, times_S ? 1 : 0, U, ldu, false, s);                    // Q2 (V[*sigma])
     return;
   }
@@ -830,7 +1044,8 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
     return;
   }
   if (w.precond) {
-    if (!w.transposed) precond_right(w, times_S ? 1 : 0, Vh, ldv, true, s);      // (Q2 V[*sigma])^H
+    if (!w.transposed && w.wonly) wonly_other(w, times_S, Vh, ldv, false, s);    // [S] V_T^H = U'^H R1
+    else if (!w.transposed) precond_right(w, times_S ? 1 : 0, Vh, ldv, true, s); // (Q2 V[*sigma])^H
     else precond_left(w, times_S ? 0 : 2, Vh, ldv, true, s);                     // (Q1 W[/sigma])^H
     return;
   }
@@ -849,7 +1064,7 @@ void svd_free(SvdWork& w) {
   if (w.J) cudaFree(w.J);
   if (w.sig) { cudaFree(w.sig); cudaFree(w.sig2); cudaFree(w.perm); }
   if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); cudaFree(w.cflag); }
-  for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg}) if (p) cudaFree(p);
+  for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg, w.R1}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
   delete w.bview;
   w = SvdWork{};
@@ -876,6 +1091,7 @@ int svd_dist_begin(SvdWork& w, const cplx* M, int m, int n, long long ld, cudaSt
   TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
   const int npad = w.ncols_pad;
   w.precond = precond_enabled() && npad > JP;
+  w.wonly = false;
   if (w.s_cap < (size_t)npad) {
     if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
     TN_CUDA(cudaMallocAsync((void**)&w.sig, npad * sizeof(double), s));
@@ -932,8 +1148,6 @@ double svd_dist_step(SvdWork& w, const int* pairs_host, int npairs, cudaStream_t
   ensure(w.skip, w.skip_cap, (size_t)npairs, s);
   ensure(w.dtab, w.dtab_cap, (size_t)2 * npairs, s);
   TN_CUDA(cudaMemcpyAsync(w.dtab, pairs_host, (size_t)2 * npairs * sizeof(int), cudaMemcpyHostToDevice, s));
-  const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
-  TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem));
   const double tol = svd_dist_tol(w);
   const long long colblk = (long long)JB * w.ldz;
   TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
@@ -948,9 +1162,7 @@ double svd_dist_step(SvdWork& w, const int* pairs_host, int npairs, cudaStream_t
   g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
   if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)npairs * JP * JP * sizeof(cplx), s));
   zgemm_auto(g, s);
-  jacobi_evd64_kernel<<<npairs, EVD_THREADS, evd_smem, s>>>(w.Gpart, 1, 0, w.J, tol, w.offmax, 1, JP, w.skip);
-  TN_CUDA(cudaGetLastError());
-  count_launch(1);
+  launch_evd(npairs, w.Gpart, w.J, tol, w.offmax, 1, JP, w.skip, s);
   GemmDesc a{};
   a.M = jrows + w.ncols_pad; a.N = JP; a.K = JP;
   a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
@@ -1027,8 +1239,6 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
   ensure(w.J, w.J_cap, (size_t)npg * JP * JP, s);
   ensure(w.skip, w.skip_cap, (size_t)npg, s);
   const int* tab = pair_table_b(w, B, nb, s);
-  const int evd_smem = 2 * JP * LDS_ * (int)sizeof(cplx);
-  TN_CUDA(cudaFuncSetAttribute(jacobi_evd64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evd_smem));
   const double tol = 3.0 * std::sqrt((double)jrows) * 2.220446049250313e-16;
   const long long colblk = (long long)JB * w.ldz;
   const int inner_sweeps = (np == 1) ? 12 : 1;
@@ -1048,9 +1258,7 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)npg * JP * JP * sizeof(cplx), s));
       zgemm_auto(g, s);
-      jacobi_evd64_kernel<<<npg, EVD_THREADS, evd_smem, s>>>(w.Gpart, 1, 0, w.J, tol, w.offmax, inner_sweeps, nact, w.skip);
-      TN_CUDA(cudaGetLastError());
-      count_launch(1);
+      launch_evd(npg, w.Gpart, w.J, tol, w.offmax, inner_sweeps, nact, w.skip, s);
       GemmDesc a{};
       a.M = jrows + w.npad; a.N = JP; a.K = JP;
       a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
@@ -1067,7 +1275,7 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
     TN_CUDA(cudaStreamSynchronize(s));
     double off; std::memcpy(&off, &bits, 8);
     w.sweeps = sweep + 1;
-    if (off <= tol) break;
+    if (off <= tol || off <= early_stop()) break;
   }
 }
 

@@ -30,6 +30,12 @@ struct SvdWork {
   cplx* small = nullptr;                           // 3 x 64x64: Rinv, Rtot, scratch
   cplx* Tg = nullptr; size_t Tg_cap = 0;           // gathered / scaled singular-vector block (ncols_pad x k)
   bool precond = false; int jrows = 0;             // Jacobi ran on an jrows x ncols_pad matrix
+  // "W-only" factorisation (svd_factor with iso != 0): the caller needs ONE orthonormal factor (the isometry that becomes a site
+  // tensor) and the other one multiplied by S.  Then the right rotations V' are never accumulated (half of the rotation flops):
+  // with T = Q1 R1 (T = A or A^H, the tall orientation), R1^H = Q2 R2, X = R2^H and X V' = U' Sigma, the isometry is Q1 U' and
+  // the other factor is S V_T^H = (Q1 U')^H T = U'^H R1 -- one GEMM with the saved R1, no Q2, no V'.
+  bool wonly = false;
+  cplx* R1 = nullptr; size_t R1_cap = 0;           // R1 of the first QR step (W-only mode)
   // description of the last factorisation
   int m = 0, n = 0, rows = 0, ncols = 0, ncols_pad = 0, ldz = 0, nsv = 0, k = 0, sweeps = 0;
   bool transposed = false;
@@ -42,7 +48,9 @@ struct SvdWork {
 
 // Factorises the m x n column-major matrix M (leading dimension ld) and applies the reference's
 // truncation rule (src/tensors.jl:201-215).  Returns k; factors stay in `w` until gathered.
-int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s);
+// iso: 0 = both singular-vector sets are accumulated (any combination of gathers); 1 = the caller gathers U plain and S V^H;
+// 2 = V^H plain and U S (then the cheaper W-only factorisation is used when the isometry sits on the long side of M).
+int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso = 0);
 // U (m x k, leading dim ldu), optionally multiplied by S on the right.
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s);
 // V^H (k x n, leading dim ldv), optionally multiplied by S on the left.

@@ -6,6 +6,6 @@ The names follow the reference (``GMPS``, ``ProjMPS``, ``ProjMPSSum``, ``movecen
 are NumPy complex128 in Julia's column-major order.  Tensors live in HBM between
 calls; only scalars, observables and explicitly downloaded tensors cross PCIe."""
 from ._lib import TNError, load, LIB_PATH  # noqa: F401
-from .api import (Context, GMPS, ProjMPS, ProjMPSSum, GateList, applyMPO, svd, svd_batched, contract_strided, dmrg, vmps, vmps_sweeps, tebd,  # noqa: F401
+from .api import (Context, GMPS, ProjMPS, ProjMPSSum, GateList, applyMPO, svd, svd_split, svd_batched, contract_strided, dmrg, vmps, vmps_sweeps, tebd,  # noqa: F401
                   applygates, qjmc_simulation, qjmc_ensemble, inner, Trunc)
 from . import models, mpo, evolve, sharded  # noqa: F401

@@ -439,6 +439,24 @@ def svd(x, idx, cutoff=0.0, maxdim=0, mindim=1, ctx=None, return_sweeps=False):
     return out + (sw.value,) if return_sweeps else out
 
 
+def svd_split(y, side, cutoff=0.0, maxdim=0, mindim=1, ctx=None, repeat=1):
+    """The factorisation inside replacesites! / moveleft! / moveright! (gmps.jl:60-82, 218-256) of a matrix ``y`` (m x n):
+    side = 1 returns (U, S, S V^H) with U orthonormal, side = 2 returns (U S, S, V^H) with V^H orthonormal.  Also returns the
+    number of Jacobi sweeps and the device time in ms of the last of ``repeat`` runs (factorisation + gathers, no PCIe)."""
+    ctx = ctx or Context.default()
+    y = _f(np.asarray(y, dtype=np.complex128))
+    m, n = y.shape
+    kmax = min(m, n)
+    U = np.zeros(m * kmax, dtype=np.complex128)
+    Vh = np.zeros(kmax * n, dtype=np.complex128)
+    S = np.zeros(kmax)
+    k, sw, ms = C.c_int64(), C.c_int32(), C.c_double()
+    check(ctx.lib.tn_svd_trunc_split(ctx.h, _ptr(y), m, n, Trunc(cutoff, maxdim, mindim), int(side), _ptr(U), S.ctypes.data_as(C.POINTER(C.c_double)),
+                                     _ptr(Vh), C.byref(k), C.byref(sw), int(repeat), C.byref(ms)))
+    k = k.value
+    return (np.reshape(U[:m * k], (m, k), order='F'), S[:k].copy(), np.reshape(Vh[:k * n], (k, n), order='F'), sw.value, ms.value)
+
+
 def svd_batched(mats, cutoff=0.0, maxdim=0, mindim=1, ctx=None):
     """Truncated SVDs (tensors.jl:168-227 on matrices, idx = last) of a stack ``mats[b]`` (B, m, n) of same-shape matrices in one
     batched factorisation (tn_svd_trunc_batched).  Returns a list of (U (m x k_b), S (k_b,), Vh (k_b x n))."""

@@ -101,3 +101,33 @@ def test_preconditioned_shapes(m, n):
         assert np.linalg.norm(V @ V.conj().T - np.eye(k)) < 1e-10
         if not kw:
             assert np.linalg.norm(U @ S @ V - x) <= 1e-12 * np.linalg.norm(x)
+
+
+@pytest.mark.parametrize("m,n", [(96, 96), (130, 130), (200, 80), (80, 200), (256, 256), (512, 256), (256, 512), (512, 512)])
+@pytest.mark.parametrize("side", [1, 2])
+def test_split_factorisation_matches_lapack(m, n, side):
+    """The isometry + weighted-factor split of replacesites! / moveleft! / moveright! (gmps.jl:60-82, 218-256); when the isometry sits
+    on the long side the W-only factorisation runs (no accumulated right rotations, weighted factor = U'^H R1).  Graded spectrum
+    as on an MPS bond, with and without truncation."""
+    import tnb200
+    rng = np.random.default_rng(7 * m + n + side)
+    r = min(m, n)
+    u, _ = np.linalg.qr(crandn(rng, m, r))
+    v, _ = np.linalg.qr(crandn(rng, n, r))
+    sv = np.exp(-np.arange(r) * 24.0 / r)
+    x = (u * sv) @ v.conj().T
+    for kw in (dict(cutoff=0.0), dict(cutoff=1e-12), dict(cutoff=0.0, maxdim=r // 2)):
+        A, S, B, sweeps, ms = tnb200.svd_split(x, side, **kw)
+        Uo, So, Vo = oracle.svd(x, 2, **kw)
+        so = np.real(np.diag(So))
+        k = len(S)
+        assert k == len(so), (kw, k, len(so))
+        assert np.max(np.abs(S - so)) <= 1e-12 * so[0]
+        iso = A if side == 1 else B.conj().T
+        kk = int(np.sum(so > 1e-10 * so[0]))                  # singular vectors of sigma ~ eps sigma_max are not determined
+        assert np.linalg.norm(iso[:, :kk].conj().T @ iso[:, :kk] - np.eye(kk)) < 1e-11 * np.sqrt(kk)
+        want = (Uo @ So) @ Vo
+        assert np.linalg.norm(A @ B - want) <= 1e-12 * so[0] * np.sqrt(k)
+        # the weighted factor carries the singular values: its Gram matrix is diag(S^2)
+        wf = B if side == 1 else A.conj().T
+        assert np.linalg.norm(wf @ wf.conj().T - np.diag(S ** 2)) <= 1e-11 * so[0] ** 2 * np.sqrt(k)
