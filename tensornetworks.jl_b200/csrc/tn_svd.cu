@@ -358,6 +358,16 @@ __global__ void __launch_bounds__(EVD2_THREADS, 1) jacobi_evd64v2_kernel(const c
   for (int e = tid; e < JP * JP; e += EVD2_THREADS) jo[e] = J[(e % JP) * LDS_ + (e / JP)];
 }
 
+
+// ---- what did NOT pay (measured on a B200, profiles/r02_evd_experiments.md) --------------------------------------------------
+// A third kernel moved the critical path to a leader warp (the 32 elements the next step needs are updated in registers and the
+// next parameters derived at once, FP32-seeded and re-normalised in FP64, while bulk warps update the other blocks) and kept J in
+// registers (one lane shuffle per value and step instead of 128 KB of shared-memory traffic).  Bit-for-bit parity, but no gain:
+// 105 us per 63-step launch against 111 us -- the step is bound by instruction issue (~6800 warp instructions per step over four
+// schedulers; the select / move overhead of the shuffled J costs what its shared-memory traffic did), ~20 us of every launch are
+// fixed cost (load, symmetrise, tables, store), and polling J warps slowed the launch 4.5x until they joined the step barrier.
+// The kernel was removed again; the numbers are in the profile note.
+
 // ---- preparation / finalisation kernels -----------------------------------------------------
 __global__ void __launch_bounds__(256) svd_init_kernel(const cplx* __restrict__ M, long long ld, int m, int n, int transposed,
                                                         cplx* __restrict__ Z, int rows, int ncols, int ncols_pad, int ldz) {
