@@ -247,6 +247,58 @@ def qjmc_wave(device, N=64, chi=256, traj=32, workers=32, steps=1):
     return {"seconds": sec, "traj_steps": traj * steps, "jumps": int(nj.sum()), "mean_sum_z": float(np.real(obs[:, -1, :]).sum() / traj)}
 
 
+def _qjmc_cpu_worker(arg):
+    """One trajectory x one step of the oracle's qjmc_simulation (restates qjmc.jl:28-167) at the C4 shapes, `threads` BLAS threads."""
+    seed, N, chi, threads = arg
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=threads)
+    except Exception:
+        pass
+    import oracle
+    from oracle.gmps import GMPS as OG
+    sh = oracle.spinhalf()
+    H = oracle.OpList(N)
+    J = oracle.OpList(N)
+    for i in range(1, N + 1):
+        H.add("x", i, 1.0)
+        H.add("z", i, 20.0)
+        J.add("s-", i, np.sqrt(0.1))
+    for i in range(1, N):
+        H.add(["z", "z"], [i, i + 1], 10.0)
+    rng = np.random.default_rng(1)           # same seeded right-canonical start as the GPU wave (tnb200.models.random_canonical_mps)
+    dims = [min(D ** i, D ** (N - i), chi) for i in range(N + 1)]
+    tens = []
+    for i in range(N):
+        l, r = dims[i], dims[i + 1]
+        a = rng.standard_normal((l, D * r)) + 1j * rng.standard_normal((l, D * r))
+        q, _ = np.linalg.qr(a.T.conj())
+        tens.append(np.asfortranarray(np.ascontiguousarray(q.conj().T).reshape(l, D, r, order='F')))
+    tens[0] = tens[0] / np.linalg.norm(tens[0])
+    psi = OG(1, D, tens, 1)
+    dt = 5e-3
+    t0 = time.perf_counter()
+    oracle.qjmc_simulation(sh, psi, H, J, dt, dt, uniforms=np.random.default_rng(seed).random, cutoff=0.0, maxdim=chi)
+    return time.perf_counter() - t0
+
+
+def qjmc_cpu_sample(N=64, chi=256, traj=8):
+    """CPU baseline of the QJMC leg: `traj` trajectories x 1 step of the oracle port, one process per trajectory, the host's cores
+    split evenly between their BLAS pools (the reference itself is single-process: qjmc.jl:28 runs ONE trajectory per call)."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    traj = max(1, min(traj, cores))
+    threads = max(1, cores // traj)
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(traj) as pool:
+        per = pool.map(_qjmc_cpu_worker, [(100 + i, N, chi, threads) for i in range(traj)])
+    wall = time.perf_counter() - t0
+    busy = max(per)
+    return {"value": traj / busy, "unit": "trajectory-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{traj} trajectories x 1 step at the C4 shapes (N={N}, chi={chi}, cutoff=0), one process each with {threads} BLAS thread(s); "
+                      f"slowest trajectory-step {busy:.1f} s, wall incl. process start {wall:.1f} s"}
+
+
 class ClockSampler:
     def __init__(self, device):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -530,12 +582,14 @@ def main():
             barrier()
             q = qjmc_wave(local)
             sec = max_over_ranks(q["seconds"])
-            tot = max_over_ranks(0.0) if False else q["traj_steps"] * world
+            tot = q["traj_steps"] * world
             extras["qjmc_scaling"] = {"config": "C4 shapes: N=64, chi=256, cutoff=0; one wave of 32 trajectories x 1 step per GPU (the 8192-trajectory job is "
                                                 f"8192/(32*{world}) such waves per GPU), SVD batching rounds across the wave",
                                       "n_gpus": world, "seconds_slowest_rank": sec, "traj_steps_per_s": tot / sec, "traj_per_s_at_20_steps": tot / sec / 20.0,
                                       "collective": "none during the evolution (final gather of jump records only)", "jumps_rank0": q["jumps"],
                                       "mean_sum_z_rank0": q["mean_sum_z"]}
+            if world == 1 and not args.no_cpu_baseline:
+                extras["qjmc_scaling"]["cpu_baseline"] = qjmc_cpu_sample()
         except Exception as e:
             extras["qjmc_scaling"] = {"error": repr(e)[:200]}
     if rank == 0:

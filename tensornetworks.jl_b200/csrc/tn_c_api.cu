@@ -61,7 +61,7 @@ static inline void use_device_idx(int dev) {
 static inline void use_device(tn_ctx* h) { use_device_idx(h->c.device); }
 static inline void use_device(tn_mps* h) { use_device_idx(h->m->ctx->device); }
 static inline void use_device(tn_env* h) { use_device_idx(h->e->ctx->device); }
-static inline void use_device(tn_gates* h) { use_device_idx(h->g->ctx->device); }
+[[maybe_unused]] static inline void use_device(tn_gates* h) { use_device_idx(h->g->ctx->device); }
 static inline void use_device(tn_envsum* h) { use_device_idx(h->s->ctx->device); }
 static inline void use_device(tn_imps* h) { use_device_idx(h->m->ctx->device); }
 

@@ -114,7 +114,7 @@ static void moveright(Mps* m, int i, Trunc tr, bool s_stays = false) {
   Ctx* c = m->ctx; cudaStream_t s = c->stream;
   Tensor& A = m->sites[i - 1]; Tensor& Bn = m->sites[i];
   long long rows = A.size() / A.dims.back(), cols = A.dims.back();
-  int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s, s_stays ? 2 : 1); c->svds++;   // the factor gathered without S is the isometry
+  int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s, s_stays ? 2 : 1, s_stays); c->svds++;   // the factor gathered without S is the isometry; a plain gauge move needs no singular values
   Tensor U; std::vector<long long> du = A.dims; du.back() = k;
   c->alloc(U, du);
   svd_gather_U(c->svd, U.p, rows, s_stays, s);
@@ -134,7 +134,7 @@ static void moveleft(Mps* m, int i, Trunc tr, bool s_stays = false) {
   Ctx* c = m->ctx; cudaStream_t s = c->stream;
   Tensor& A = m->sites[i - 1]; Tensor& Pv = m->sites[i - 2];
   long long rows = A.dims.front(), cols = A.size() / rows;
-  int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s, s_stays ? 1 : 2); c->svds++;
+  int k = svd_factor(c->svd, A.p, (int)rows, (int)cols, rows, tr, s, s_stays ? 1 : 2, s_stays); c->svds++;
   Tensor V; std::vector<long long> dv = A.dims; dv.front() = k;
   c->alloc(V, dv);
   svd_gather_Vh(c->svd, V.p, k, s_stays, s);

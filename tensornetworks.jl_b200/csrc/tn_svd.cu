@@ -915,9 +915,41 @@ static int pad_ld(int rows) {
 static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s);
 static thread_local SvdBatcher* tl_batcher = nullptr;
 
-int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso) {
+static bool gauge_qr_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_GAUGE_QR"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
+int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso, bool need_values) {
   TN_CHECK(m >= 1 && n >= 1, "svd: empty matrix");
   w.use_view = false;
+  w.qr_mode = 0;
+  {
+    // the reference's rule (tensors.jl:201-215) keeps all min(m, n) values when cutoff == 0 and maxdim is 0 or >= min(m, n)
+    const long long nsv = std::min(m, n);
+    if (!need_values && iso != 0 && gauge_qr_enabled() && tr.cutoff == 0.0 && (tr.maxdim == 0 || tr.maxdim >= nsv)) {
+      w.m = m; w.n = n; w.k = (int)nsv; w.nsv = (int)nsv; w.sweeps = 0; w.wonly = false; w.precond = false;
+      const bool iso_long = (iso == 1 && m >= n) || (iso == 2 && n >= m);
+      if (!iso_long) { w.qr_mode = 2; w.M0 = M; w.ld0 = ld; w.transposed = false; return w.k; }
+      w.qr_mode = 1;
+      w.transposed = iso == 2;
+      w.rows = w.transposed ? n : m;
+      w.ncols = w.transposed ? m : n;
+      w.ncols_pad = ((w.ncols + JP - 1) / JP) * JP;
+      TN_CHECK(w.ncols_pad <= 8192, "svd: more than 8192 columns is not supported yet");
+      const int npad = w.ncols_pad;
+      if (!w.offmax) { TN_CUDA(cudaMalloc((void**)&w.offmax, 8)); TN_CUDA(cudaMalloc((void**)&w.kout, 4)); TN_CUDA(cudaMalloc((void**)&w.cflag, 4)); TN_CUDA(cudaMalloc((void**)&w.small, 3 * JP * JP * sizeof(cplx))); }
+      ensure(w.Q1, w.Q1_cap, (size_t)w.rows * npad, s);
+      int blocks;
+      launch_1d((long long)w.rows * npad, blocks);
+      svd_init_kernel<<<blocks, 256, 0, s>>>(M, ld, m, n, w.transposed ? 1 : 0, w.Q1, w.rows, w.ncols, npad, w.rows);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      bgs_qr(w, w.Q1, w.rows, w.rows, npad, s);                  // T = Q1 Ra
+      return w.k;
+    }
+  }
   if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s);
   w.m = m; w.n = n;
   w.transposed = m < n || (m == n && iso == 2);       // a square matrix is factorised in the orientation whose long-side factor is the isometry
@@ -1030,6 +1062,42 @@ static void wonly_other(SvdWork& w, bool times_S, cplx* out, long long ldo, bool
   else zgemm_auto(gd(w.ncols, k, npad, w.R1, idx1(npad), idx1(1), 1, w.Tg, idx1(1), idx1(npad), 0, out, idx1(1), idx1(ldo)), s);
 }
 
+// Factors of a gauge move that was not an SVD (SvdWork::qr_mode).  want_U: the m x k factor, else the k x n factor; which of
+// the two is the isometry was fixed by the `iso` argument of svd_factor.
+static void qr_gather(SvdWork& w, bool want_U, cplx* out, long long ldo, cudaStream_t s) {
+  const int k = w.k, m = w.m, n = w.n;
+  int blocks;
+  if (w.qr_mode == 2) {
+    // isometry on the short side: identity there, the matrix itself on the other side (k = min(m, n))
+    const bool u_is_identity = m <= n;
+    if (want_U == u_is_identity) {
+      TN_CHECK(ldo == k, "gauge move: unexpected leading dimension");
+      launch_1d((long long)k * k, blocks);
+      set_identity_kernel<<<blocks, 256, 0, s>>>(out, ldo, k);
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+    } else {
+      TN_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(cplx), w.M0, (size_t)w.ld0 * sizeof(cplx), (size_t)m * sizeof(cplx), n, cudaMemcpyDeviceToDevice, s));
+    }
+    return;
+  }
+  const int npad = w.ncols_pad;
+  if (!w.transposed) {          // A = Q1 R: U = Q1(:, :k), [S V^H] = R(:k, :n)
+    if (want_U) TN_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(cplx), w.Q1, (size_t)w.rows * sizeof(cplx), (size_t)m * sizeof(cplx), k, cudaMemcpyDeviceToDevice, s));
+    else TN_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(cplx), w.Ra, (size_t)npad * sizeof(cplx), (size_t)k * sizeof(cplx), n, cudaMemcpyDeviceToDevice, s));
+  } else {                      // A^H = Q1 R: [U S] = R^H (m x k), V^H = Q1^H (k x n)
+    if (want_U) {
+      launch_1d((long long)k * m, blocks);
+      conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra, npad, k, m, out, ldo);
+    } else {
+      launch_1d((long long)n * k, blocks);
+      conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Q1, w.rows, n, k, out, ldo);
+    }
+    TN_CUDA(cudaGetLastError());
+    count_launch(1);
+  }
+}
+
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
   if (w.use_view) {      // factors of a batching round: gather from this thread's slot, with this thread's scratch
     SvdWork& v = *w.bview; v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
@@ -1037,6 +1105,7 @@ void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t
     w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
     return;
   }
+  if (w.qr_mode != 0) { qr_gather(w, true, U, ldu, s); return; }
   if (w.precond) {
     if (!w.transposed) precond_left(w, times_S ? 0 : 2, U, ldu, false, s);       // Q1 (W[/sigma])
     else if (w.wonly) wonly_other(w, times_S, U, ldu, true, s);                  // ([S] V_T^H)^H
@@ -1053,6 +1122,7 @@ void svd_gather_Vh(SvdWork& w, cplx* Vh, long long ldv, bool times_S, cudaStream
     w.Tg = v.Tg; w.Tg_cap = v.Tg_cap;
     return;
   }
+  if (w.qr_mode != 0) { qr_gather(w, false, Vh, ldv, s); return; }
   if (w.precond) {
     if (!w.transposed && w.wonly) wonly_other(w, times_S, Vh, ldv, false, s);    // [S] V_T^H = U'^H R1
     else if (!w.transposed) precond_right(w, times_S ? 1 : 0, Vh, ldv, true, s); // (Q2 V[*sigma])^H

@@ -36,6 +36,11 @@ struct SvdWork {
   // the other factor is S V_T^H = (Q1 U')^H T = U'^H R1 -- one GEMM with the saved R1, no Q2, no V'.
   bool wonly = false;
   cplx* R1 = nullptr; size_t R1_cap = 0;           // R1 of the first QR step (W-only mode)
+  // Gauge moves that cannot truncate (svd_factor with need_values = false, cutoff = 0 and maxdim >= min(m, n)): any orthogonal
+  // factorisation yields the same state, so the SVD is replaced by  1 = one QR step of the tall orientation (isometry Q, other
+  // factor R)  or  2 = nothing at all when the isometry sits on the short side (identity, other factor = the matrix itself).
+  int qr_mode = 0;
+  const cplx* M0 = nullptr; long long ld0 = 0;     // the caller's matrix (qr_mode 2; valid until the gathers)
   // description of the last factorisation
   int m = 0, n = 0, rows = 0, ncols = 0, ncols_pad = 0, ldz = 0, nsv = 0, k = 0, sweeps = 0;
   bool transposed = false;
@@ -50,7 +55,9 @@ struct SvdWork {
 // truncation rule (src/tensors.jl:201-215).  Returns k; factors stay in `w` until gathered.
 // iso: 0 = both singular-vector sets are accumulated (any combination of gathers); 1 = the caller gathers U plain and S V^H;
 // 2 = V^H plain and U S (then the cheaper W-only factorisation is used when the isometry sits on the long side of M).
-int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso = 0);
+// need_values = false: the caller uses neither the singular values nor the canonical choice of the singular vectors (moveleft! /
+// moveright! inside movecenter!, gmps.jl:60-112) -- see SvdWork::qr_mode.
+int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso = 0, bool need_values = true);
 // U (m x k, leading dim ldu), optionally multiplied by S on the right.
 void svd_gather_U(SvdWork& w, cplx* U, long long ldu, bool times_S, cudaStream_t s);
 // V^H (k x n, leading dim ldv), optionally multiplied by S on the left.

@@ -88,3 +88,39 @@ def test_movecenter_norm_replacesites():
         assert relerr(np.tensordot(g[3], g[4], axes=([2], [0])), np.tensordot(psi[3], psi[4], axes=([2], [0]))) < 1e-11
         g.normalize()
         assert abs(g.norm() - 1.0) < 1e-13
+
+
+def test_gauge_moves_that_cannot_truncate_keep_the_state():
+    """movecenter! without truncation (cutoff = 0, maxdim >= bond): the library replaces the SVD of moveleft!/moveright!
+    (gmps.jl:60-82) by one QR step (or by nothing when the isometry sits on the short side).  Gauge-invariant parity with
+    the oracle's SVD-based moves: same state, same bond dimensions, orthonormal sites, same norm; bonds > 64 take two QR panels."""
+    import tnb200
+    rng = np.random.default_rng(11)
+    N, chi = 14, 80
+    psi = random_complex_mps(rng, N, 2, chi, center=1)
+    g = tnb200.GMPS.from_host(psi)
+
+    def dense(p):
+        v = p[1]
+        for i in range(2, N + 1):
+            v = np.tensordot(v, p[i], axes=([v.ndim - 1], [0]))
+        return v.reshape(-1)
+    want = dense(psi)
+    for c, kw in ((N, {}), (3, {}), (9, dict(maxdim=chi)), (1, dict(maxdim=200)), (7, {})):
+        g.movecenter(c, **kw)
+        psi.movecenter(c, **kw)
+        assert g.center == c
+        assert [g.bonddim(i) for i in range(1, N)] == [psi.bonddim(i) for i in range(1, N)]
+        assert relerr(dense(g), want) < 1e-12
+        assert abs(g.norm() - psi.norm()) < 1e-12
+        for i in range(1, c):
+            m = g[i].reshape(-1, g[i].shape[2], order='F')
+            assert np.linalg.norm(m.conj().T @ m - np.eye(m.shape[1])) < 1e-11
+        for i in range(c + 1, N + 1):
+            m = g[i].reshape(g[i].shape[0], -1, order='F')
+            assert np.linalg.norm(m @ m.conj().T - np.eye(m.shape[0])) < 1e-11
+    # a truncating move still goes through the SVD and matches the oracle's spectrum
+    g.movecenter(2, maxdim=20)
+    psi.movecenter(2, maxdim=20)
+    assert [g.bonddim(i) for i in range(1, N)] == [psi.bonddim(i) for i in range(1, N)]
+    assert np.max(np.abs(g.spectrum(5) - psi.spectrum(5))) < 1e-10

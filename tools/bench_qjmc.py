@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--workers", type=int, default=16)
     ap.add_argument("--warm", type=int, default=1, help="warm-up steps per worker")
+    ap.add_argument("--profile", default="", help="write a per-kernel time summary of the timed region (torch.profiler / CUPTI) to this file")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -44,7 +45,15 @@ def main():
         dist.barrier()
     l0 = tnb200.Context(local).counters()["launches"]
     t0 = time.perf_counter()
-    nj, jumps, times, obs = tnb200.qjmc_ensemble(*args, a.steps, dt, mine, save_every=a.steps, **kw)
+    if a.profile:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            nj, jumps, times, obs = tnb200.qjmc_ensemble(*args, a.steps, dt, mine, save_every=a.steps, **kw)
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
+    else:
+        nj, jumps, times, obs = tnb200.qjmc_ensemble(*args, a.steps, dt, mine, save_every=a.steps, **kw)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     launches = tnb200.Context(local).counters()["launches"] - l0
