@@ -912,7 +912,7 @@ static int pad_ld(int rows) {
   return (rows % 64 == 0) ? rows + pad : rows;
 }
 
-static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s);
+static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso, bool qr);
 static thread_local SvdBatcher* tl_batcher = nullptr;
 
 static bool gauge_qr_enabled() {
@@ -932,6 +932,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
       w.m = m; w.n = n; w.k = (int)nsv; w.nsv = (int)nsv; w.sweeps = 0; w.wonly = false; w.precond = false;
       const bool iso_long = (iso == 1 && m >= n) || (iso == 2 && n >= m);
       if (!iso_long) { w.qr_mode = 2; w.M0 = M; w.ld0 = ld; w.transposed = false; return w.k; }
+      if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s, iso, true);    // the QR steps of all trajectories in one batched launch sequence
       w.qr_mode = 1;
       w.transposed = iso == 2;
       w.rows = w.transposed ? n : m;
@@ -950,7 +951,7 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
       return w.k;
     }
   }
-  if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s);
+  if (tl_batcher != nullptr) return batcher_submit(w, M, m, n, ld, tr, s, iso, false);
   w.m = m; w.n = n;
   w.transposed = m < n || (m == n && iso == 2);       // a square matrix is factorised in the orientation whose long-side factor is the isometry
   w.rows = w.transposed ? n : m;
@@ -1340,7 +1341,7 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
       zgemm_auto(g, s);
       launch_evd(npg, w.Gpart, w.J, tol, w.offmax, inner_sweeps, nact, w.skip, s);
       GemmDesc a{};
-      a.M = jrows + w.npad; a.N = JP; a.K = JP;
+      a.M = jrows + (w.wonly ? 0 : w.npad); a.N = JP; a.K = JP;
       a.A = w.Z; a.am = idx1(1); a.ak = cols; a.conjA = 0;
       a.B = w.J; a.bk = idx1(1); a.bn = idx1(JP); a.conjB = 0;
       a.C = w.Z; a.cm = idx1(1); a.cn = cols;
@@ -1427,16 +1428,36 @@ static void bgs_qr_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, cu
   zgemm_auto(g, s);
 }
 
-void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso, bool qr_only) {
   TN_CHECK(B >= 1 && B <= 1024 && m >= 1 && n >= 1, "batched svd: bad batch / shape");
   w.B = B; w.m = m; w.n = n;
-  w.transposed = m < n;
+  w.transposed = m < n || (m == n && iso == 2);
   w.rows = w.transposed ? n : m;
   w.ncols = w.transposed ? m : n;
   w.npad = ((w.ncols + JP - 1) / JP) * JP;
   const int npad = w.npad, rows = w.rows;
   TN_CHECK(npad <= 8192 && (long long)B * (npad / JB) < (1 << 24), "batched svd: problem too large");
+  w.qr_mode = 0;
+  if (qr_only) {
+    // gauge moves that cannot truncate: T_b = Q1_b R_b for every problem, nothing else (see SvdWork::qr_mode)
+    TN_CHECK((iso == 1 && !w.transposed) || (iso == 2 && w.transposed), "batched QR: the isometry must sit on the long side");
+    w.qr_mode = 1; w.precond = false; w.wonly = false; w.sweeps = 0;
+    ensure(w.cflag, w.cflag_cap, (size_t)B, s);
+    ensure(w.small, w.small_cap, (size_t)2 * B * JP * JP, s);
+    ensure(w.Q1, w.Q1_cap, (size_t)rows * B * npad, s);
+    int blocks;
+    launch_1d((long long)rows * npad, blocks);
+    for (int b = 0; b < B; ++b)
+      svd_init_kernel<<<blocks, 256, 0, s>>>(Ms[b], ld, m, n, w.transposed ? 1 : 0, w.Q1 + (size_t)b * npad * rows, rows, w.ncols, npad, rows);
+    TN_CUDA(cudaGetLastError());
+    count_launch(B);
+    bgs_qr_b(w, w.Q1, rows, rows, npad, s);
+    w.k.assign(B, std::min(m, n));
+    TN_CUDA(cudaStreamSynchronize(s));
+    return;
+  }
   w.precond = precond_enabled() && npad > JP;
+  w.wonly = w.precond && wonly_enabled() && ((iso == 1 && !w.transposed) || (iso == 2 && w.transposed));
   const size_t tot = (size_t)B * npad;
   if (w.s_cap < tot) {
     if (w.sig) { TN_CUDA(cudaFreeAsync(w.sig, s)); TN_CUDA(cudaFreeAsync(w.perm, s)); TN_CUDA(cudaFreeAsync(w.sig2, s)); }
@@ -1467,6 +1488,10 @@ void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n,
       svd_init_kernel<<<blocks, 256, 0, s>>>(Ms[b], ld, m, n, w.transposed ? 1 : 0, w.Q1 + (size_t)b * npad * rows, rows, w.ncols, npad, rows);
     count_launch(B);
     bgs_qr_b(w, w.Q1, rows, rows, npad, s);                       // Ra_b = R1 of problem b
+    if (w.wonly) {
+      ensure(w.R1, w.R1_cap, (size_t)npad * tot, s);
+      TN_CUDA(cudaMemcpyAsync(w.R1, w.Ra, (size_t)npad * tot * sizeof(cplx), cudaMemcpyDeviceToDevice, s));
+    }
     ensure(w.Q2, w.Q2_cap, (size_t)npad * tot, s);
     launch_1d((long long)npad * npad, blocks);
     for (int b = 0; b < B; ++b)
@@ -1474,12 +1499,12 @@ void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n,
     count_launch(B);
     bgs_qr_b(w, w.Q2, npad, npad, npad, s);                       // Ra_b = R2
     w.jrows = npad;
-    w.ldz = pad_ld(2 * npad);
+    w.ldz = pad_ld(w.wonly ? npad : 2 * npad);
     ensure(w.Z, w.Z_cap, (size_t)w.ldz * tot, s);
     for (int b = 0; b < B; ++b) {
       cplx* Zb = w.Z + (size_t)b * npad * w.ldz;
       conj_transpose_kernel<<<blocks, 256, 0, s>>>(w.Ra + (size_t)b * npad * npad, npad, npad, npad, Zb, w.ldz);   // W <- R2^H
-      set_identity_kernel<<<blocks, 256, 0, s>>>(Zb + npad, w.ldz, npad);
+      if (!w.wonly) set_identity_kernel<<<blocks, 256, 0, s>>>(Zb + npad, w.ldz, npad);
     }
     TN_CUDA(cudaGetLastError());
     count_launch(2 * B);
@@ -1501,14 +1526,17 @@ static SvdWork batch_view(SvdBatch& w, int b) {
   TN_CHECK(b >= 0 && b < w.B, "batched svd: problem index out of range");
   SvdWork v;
   const size_t npad = (size_t)w.npad;
-  v.Z = w.Z + (size_t)b * npad * w.ldz;
-  v.sig = w.sig + b * npad; v.perm = w.perm + b * npad;
+  v.Z = w.Z ? w.Z + (size_t)b * npad * w.ldz : nullptr;
+  v.sig = w.sig ? w.sig + b * npad : nullptr; v.perm = w.perm ? w.perm + b * npad : nullptr;
   v.Q1 = w.Q1 ? w.Q1 + (size_t)b * npad * w.rows : nullptr;
   v.Q2 = w.Q2 ? w.Q2 + (size_t)b * npad * npad : nullptr;
   v.Tg = w.Tg; v.Tg_cap = w.Tg_cap;
   v.precond = w.precond; v.jrows = w.jrows;
   v.m = w.m; v.n = w.n; v.rows = w.rows; v.ncols = w.ncols; v.ncols_pad = w.npad; v.ldz = w.ldz; v.nsv = w.ncols; v.k = w.k[b];
   v.transposed = w.transposed;
+  v.wonly = w.wonly; v.qr_mode = w.qr_mode;
+  v.R1 = (w.wonly && w.R1) ? w.R1 + (size_t)b * npad * npad : nullptr;
+  v.Ra = w.Ra ? w.Ra + (size_t)b * npad * npad : nullptr;
   return v;
 }
 void svd_batched_gather_U(SvdBatch& w, int b, cplx* U, long long ldu, bool times_S, cudaStream_t s) {
@@ -1525,7 +1553,7 @@ void svd_batched_copy_S(SvdBatch& w, int b, double* S, cudaStream_t s) {
   TN_CUDA(cudaMemcpyAsync(S, w.sig + (size_t)b * w.npad, (size_t)w.k[b] * sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 void svd_batched_free(SvdBatch& w) {
-  for (cplx* p : {w.Z, w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Gpart, w.J, w.small, w.Tg}) if (p) cudaFree(p);
+  for (cplx* p : {w.Z, w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Gpart, w.J, w.small, w.Tg, w.R1}) if (p) cudaFree(p);
   if (w.skip) cudaFree(w.skip);
   if (w.cflag) cudaFree(w.cflag);
   if (w.kout) cudaFree(w.kout);
@@ -1538,10 +1566,10 @@ void svd_batched_free(SvdBatch& w) {
 // ================================================================================================
 // Batching rounds across worker threads (see tn_svd.cuh)
 // ================================================================================================
-struct BatchReq { SvdWork* w; const cplx* M; int m, n; long long ld; Trunc tr; int k; };
+struct BatchReq { SvdWork* w; const cplx* M; int m, n; long long ld; Trunc tr; int k; int iso; bool qr; };
 struct SvdBatcher {
   Rounds<BatchReq> rounds;
-  typedef std::tuple<int, int, long long, double, long long, long long> Key;   // m, n, ld, cutoff, maxdim, mindim
+  typedef std::tuple<int, int, long long, double, long long, long long, int> Key;   // m, n, ld, cutoff, maxdim, mindim, iso + 4 * qr
   std::map<Key, SvdBatch> work;                                               // one stacked workspace per shape group
   explicit SvdBatcher(int n) : rounds(n) {}
 };
@@ -1561,30 +1589,30 @@ static void batcher_run_round(SvdBatcher& bt, std::vector<BatchReq*>& pending, c
   // every worker synchronised its stream before parking, so nobody still reads the previous round's factors)
   if (bt.work.size() > 48) { for (auto& kv : bt.work) svd_batched_free(kv.second); bt.work.clear(); }
   std::map<SvdBatcher::Key, std::vector<BatchReq*>> groups;
-  for (BatchReq* r : pending) groups[SvdBatcher::Key(r->m, r->n, r->ld, r->tr.cutoff, r->tr.maxdim, r->tr.mindim)].push_back(r);
+  for (BatchReq* r : pending) groups[SvdBatcher::Key(r->m, r->n, r->ld, r->tr.cutoff, r->tr.maxdim, r->tr.mindim, r->iso + (r->qr ? 4 : 0))].push_back(r);
   for (auto& kv : groups) {
     std::vector<BatchReq*>& g = kv.second;
     SvdBatch& wb = bt.work[kv.first];
     std::vector<const cplx*> ptrs;
     for (BatchReq* r : g) ptrs.push_back(r->M);
-    svd_batched_factor(wb, (int)g.size(), ptrs.data(), g[0]->m, g[0]->n, g[0]->ld, g[0]->tr, s);   // ends with a stream synchronise
+    svd_batched_factor(wb, (int)g.size(), ptrs.data(), g[0]->m, g[0]->n, g[0]->ld, g[0]->tr, s, g[0]->iso, g[0]->qr);   // ends with a stream synchronise
     for (size_t b = 0; b < g.size(); ++b) {
       SvdWork& w = *g[b]->w;
       if (!w.bview) w.bview = new SvdWork();
       *w.bview = batch_view(wb, (int)b);
       w.use_view = true;
-      w.k = wb.k[b]; w.m = wb.m; w.n = wb.n; w.sweeps = wb.sweeps;
+      w.k = wb.k[b]; w.m = wb.m; w.n = wb.n; w.sweeps = wb.sweeps; w.qr_mode = 0;      // (the view carries the mode of the batch)
       g[b]->k = wb.k[b];
     }
   }
 }
 
-static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s) {
+static int batcher_submit(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso, bool qr) {
   SvdBatcher& bt = *tl_batcher;
   // the input matrix is complete, and every gather this thread enqueued from the previous round's workspace has finished,
   // before the workspace can be overwritten by the next round
   TN_CUDA(cudaStreamSynchronize(s));
-  BatchReq rq{&w, M, m, n, ld, tr, 0};
+  BatchReq rq{&w, M, m, n, ld, tr, 0, iso, qr};
   try { bt.rounds.submit(&rq, [&](std::vector<BatchReq*>& pending) { batcher_run_round(bt, pending, s); }); }
   catch (const std::runtime_error& e) { throw tn::Error(-3, std::string("svd batching round: ") + e.what()); }
   return rq.k;

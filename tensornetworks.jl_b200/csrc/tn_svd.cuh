@@ -75,6 +75,9 @@ int svd_dist_finish(SvdWork& w, Trunc tr, int sweeps, cudaStream_t s);
 struct SvdBatch {
   int B = 0, m = 0, n = 0, rows = 0, ncols = 0, npad = 0, ldz = 0, jrows = 0, sweeps = 0;
   bool transposed = false, precond = false;
+  bool wonly = false;                                // W-only factorisation (see SvdWork::wonly); R1 of every problem kept
+  int qr_mode = 0;                                   // 1: only the first QR step was run (gauge moves that cannot truncate)
+  cplx* R1 = nullptr; size_t R1_cap = 0;
   cplx* Z = nullptr; size_t Z_cap = 0;
   cplx* Q1 = nullptr; size_t Q1_cap = 0;
   cplx* Q2 = nullptr; size_t Q2_cap = 0;
@@ -95,7 +98,8 @@ struct SvdBatch {
 };
 // Factorises B matrices Ms[b] (device pointers, each m x n column-major with leading dimension ld) and applies the
 // reference's truncation rule to each; the ranks are left in w.k.
-void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s);
+// iso / qr_only: as the iso / need_values = false arguments of svd_factor (qr_only requires iso on the long side).
+void svd_batched_factor(SvdBatch& w, int B, const cplx* const* Ms, int m, int n, long long ld, Trunc tr, cudaStream_t s, int iso = 0, bool qr_only = false);
 void svd_batched_gather_U(SvdBatch& w, int b, cplx* U, long long ldu, bool times_S, cudaStream_t s);
 void svd_batched_gather_Vh(SvdBatch& w, int b, cplx* Vh, long long ldv, bool times_S, cudaStream_t s);
 void svd_batched_copy_S(SvdBatch& w, int b, double* S, cudaStream_t s);
