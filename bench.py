@@ -282,7 +282,7 @@ def _qjmc_cpu_worker(arg):
     return time.perf_counter() - t0
 
 
-def qjmc_cpu_sample(N=64, chi=256, traj=8):
+def qjmc_cpu_sample(N=64, chi=256, traj=4):
     """CPU baseline of the QJMC leg: `traj` trajectories x 1 step of the oracle port, one process per trajectory, the host's cores
     split evenly between their BLAS pools (the reference itself is single-process: qjmc.jl:28 runs ONE trajectory per call)."""
     import multiprocessing as mp

@@ -206,7 +206,7 @@ def inner(st, psi, oplist, phi):
                 if (site - 1 + i) in sites:
                     O = st.op(oplist.ops[idx][sites.index(site - 1 + i)])
                     B = np.einsum('st,ltr->lsr', O, B)
-                left = np.einsum('ab,asc,bsd->cd', left, A, B)
+                left = np.tensordot(A, np.tensordot(left, B, axes=([1], [0])), axes=([0, 1], [0, 1]))      # sum_{a,b,s} left(a,b) A(a,s,c) B(b,s,d)
             out[idx] = oplist.coeffs[idx] * np.einsum('ab,ab->', left, right)
     return out
 

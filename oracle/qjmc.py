@@ -44,7 +44,8 @@ def qjmc_emission_rates(st, psi, jumpops):
                     O = st.op("id")
                 # <A| O^dag O |A> sandwiched between the blocks (qjmc.jl:206-209)
                 OA = np.einsum('st,btc->bsc', O, A)
-                prod = np.einsum('ab,asc,bsd->cd', prod, np.conj(OA), OA)
+                # prod(c,d) = sum_{a,b,s} prod(a,b) conj(OA)(a,s,c) OA(b,s,d): two pairwise contractions like the reference's contract()
+                prod = np.tensordot(np.conj(OA), np.tensordot(prod, OA, axes=([1], [0])), axes=([0, 1], [0, 1]))
             rates[idx] = coeff * np.einsum('ab,ab->', prod, right)
     return np.abs(rates)
 

@@ -27,7 +27,7 @@ def overlap(phi, psi):
     """inner(phi, psi) (mpo.jl:181-217 for two MPS): <phi|psi>."""
     prod = np.ones((1, 1), dtype=np.complex128)
     for i in range(1, len(psi) + 1):
-        prod = np.einsum('ab,asc,bsd->cd', prod, np.conj(phi[i]), psi[i])
+        prod = np.tensordot(np.conj(phi[i]), np.tensordot(prod, psi[i], axes=([1], [0])), axes=([0, 1], [0, 1]))
     return prod[0, 0]
 
 

@@ -54,3 +54,26 @@ def test_qjmc_ensemble_threads_match_sequential():
     par = run_ensemble(make_runner(None), 6, workers=3)
     assert seq == par
     assert len({tuple(v[0]) for v in seq.values()}) > 1     # different trajectories really differ
+
+
+def test_sharded_dmrg_two_gpus_nccl_matches_single_gpu():
+    """World size 2 over NCCL (one process per GPU, torchrun): the MPO-bond-sharded environments + sweep of the J1-J2 cylinder give
+    the single-GPU energies to 1e-10 relative (north_star tolerance); also with the Jacobi sweeps of the SVD distributed over the ranks.
+    Needs two visible GPUs (first run on 2 x B200: profiles/r02_sharded_dmrg_2gpu.jsonl)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for extra in ([], ["--dist-svd"]):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+               os.path.join(root, "tools", "bench_multigpu.py"), "--what", "dmrg", "--lx", "4", "--ly", "4", "--chi", "64", "--sweeps", "2", "--check"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        rec = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+        assert rec["n_gpus"] == 2 and rec["single_gpu_energies"] is not None
+        for a, b in zip(rec["energies"], rec["single_gpu_energies"]):
+            assert abs(a - b) <= 1e-10 * abs(b), rec
