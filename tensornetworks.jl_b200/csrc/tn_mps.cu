@@ -210,7 +210,12 @@ void mps_replacesites2(Mps* m, const cplx* theta, int site, bool direction, bool
   svd_gather_U(c->svd, A.p, rows, direction, s);
   svd_gather_Vh(c->svd, B.p, k, !direction, s);
   m->center = direction ? site : site + 1;
-  if (normalize) mps_normalize(m);
+  if (normalize) {          // normalize! (gmps.jl:46-51) without a host round trip: <A,A> of the centre is real, A <- A / sqrt(<A,A>)
+    Tensor& Cn = m->sites[m->center - 1];
+    const cplx* xs[1] = {Cn.p};
+    zdots(Cn.size(), 1, xs, Cn.p, c->dscal + 50, c->partials, s);
+    zscale_invnorm(Cn.size(), Cn.p, c->dscal + 50, Cn.p, s);
+  }
 }
 
 // The part of mps_replacesites2 after the factorisation, for factors that are already in the context's SvdWork (a caller that
@@ -669,6 +674,12 @@ void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, doub
   TN_CHECK(e->ket == psi && e->bra == psi, "dmrg: the environment must be built on psi");
   int N = psi->N, d = psi->d;
   double cost = 0;
+  // small bonds: Theta0 and the eigsolve run in one single-CTA launch (tn_small.cu) that leaves the energy and the number of H_eff
+  // applications in device memory (dscal slots 48 / 49) -- read back once, at the end of the half sweep
+  double* energy_dev = reinterpret_cast<double*>(c->dscal + 48);
+  int* numops_dev = reinterpret_cast<int*>(c->dscal + 49);
+  TN_CUDA(cudaMemsetAsync(numops_dev, 0, sizeof(int), s));
+  bool last_small = false, any_small = false;
   for (int j = 1; j <= N - 1; ++j) {
     int site = direction ? N + 1 - j : j;
     int site1 = direction ? site - 1 : site;
@@ -676,13 +687,23 @@ void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, doub
     Tensor& A = psi->sites[site1 - 1]; Tensor& B = psi->sites[site1];
     int cl = (int)A.dims[0], cm = (int)A.dims[2], cr = (int)B.dims[2];
     long long n = (long long)cl * d * d * cr;
-    cplx* th0 = c->scratch[13].get((size_t)n, s);
     cplx* th1 = c->scratch[14].get((size_t)n, s);
-    zgemm_auto(mk(cl * d, d * cr, cm, A.p, idx1(1), idx1((long long)cl * d), 0, B.p, idx1(1), idx1(cm), 0, th0, idx1(1), idx1((long long)cl * d)), s);
-    cost = lanczos_lowest(e, site1, th0, th1, n, lz, nullptr);
+    last_small = lanczos_small(e, site1, energy_dev, numops_dev, th1, lz);
+    if (last_small) any_small = true;
+    else {
+      cplx* th0 = c->scratch[13].get((size_t)n, s);
+      zgemm_auto(mk(cl * d, d * cr, cm, A.p, idx1(1), idx1((long long)cl * d), 0, B.p, idx1(1), idx1(cm), 0, th0, idx1(1), idx1((long long)cl * d)), s);
+      cost = lanczos_lowest(e, site1, th0, th1, n, lz, nullptr);
+    }
     mps_replacesites2(psi, th1, site1, direction, true, tr);
   }
   env_movecenter(e, direction ? 1 : N);
+  if (any_small) {
+    TN_CUDA(cudaMemcpyAsync(c->hscal + 48, c->dscal + 48, 2 * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+    if (last_small) cost = *reinterpret_cast<double*>(c->hscal + 48);
+    c->matvecs += *reinterpret_cast<int*>(c->hscal + 49);
+  }
   if (energy) *energy = cost;
   if (maxbond) *maxbond = psi->maxbonddim();
 }

@@ -67,6 +67,10 @@ struct Gate { int site, nsites; cplx* dev; };
 struct Gates { Ctx* ctx; int d; std::vector<std::vector<Gate>> rows; };
 
 struct Lanczos { int krylovdim, maxiter; double tol; };
+struct Env;
+// tn_small.cu: Theta0 + the whole Lanczos eigsolve of one bond in a single-CTA launch when everything fits in shared memory (small
+// bond dimensions); energy and the count of H_eff applications stay on the device.  false = does not fit, use the general path.
+bool lanczos_small(Env* e, int site, double* energy_dev, int* numops_dev, cplx* theta_out, Lanczos lz);
 
 // GEMM descriptor for one (unbatched, unsplit) strided contraction
 inline GemmDesc mk(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int conjA, const cplx* B, Idx2 bk, Idx2 bn, int conjB,

@@ -368,6 +368,156 @@ __global__ void __launch_bounds__(EVD2_THREADS, 1) jacobi_evd64v2_kernel(const c
 // fixed cost (load, symmetrise, tables, store), and polling J warps slowed the launch 4.5x until they joined the step barrier.
 // The kernel was removed again; the numbers are in the profile note.
 
+// ---- small matrices: the whole factorisation in one CTA -------------------------------------------------------------------
+// rotation R = [[cs, s], [-conj(s), cs]] that annihilates the off-diagonal c between the diagonal entries a, b: the angle is seeded
+// in FP32 (scale-free ratio |dl| / |c| after the even part of the exponent of |c|^2 is removed) and cs^2 + |s|^2 = 1 is restored in
+// FP64 by one Newton step.  Unitary to double precision; the angle is accurate to ~1e-7 relative, which leaves Jacobi's quadratic
+// convergence intact down to 1e-7 * off.  ~10 dependent FP64 instructions instead of ~21 plus two MUFU expansions.
+__device__ __forceinline__ void jacobi_params(double a, double b, cplx c, double absc2, double& cs, cplx& s) {
+  const double dl = 0.5 * (b - a);
+  const int ex = ((__double2hiint(absc2) >> 20) & 0x7ff) - 1023;
+  const int h = ex >> 1;
+  const double sc = __hiloint2double((1023 - h) << 20, 0);
+  const float cx = (float)(c.x * sc), cy = (float)(c.y * sc);
+  const float cn2 = fmaf(cx, cx, cy * cy);
+  const float rc = rsqrtf(cn2);                                  // 1 / |cn|
+  const float z = fminf(fabsf((float)(dl * sc)) * rc, 1e30f);    // |zeta| = |dl| / |c|
+  const float t = z < 1e4f ? __fdividef(1.0f, z + sqrtf(fmaf(z, z, 1.0f))) : __fdividef(0.5f, z);
+  const float c0 = rsqrtf(fmaf(t, t, 1.0f));
+  const float m0 = (dl >= 0 ? t : -t) * c0 * rc;                 // s0 = m0 * cn
+  const double csd = (double)c0, sx = (double)(m0 * cx), sy = (double)(m0 * cy);
+  const double e = fma(csd, csd, fma(sx, sx, sy * sy)) - 1.0;    // |e| ~ 1e-7
+  const double f = fma(e, fma(e, 0.375, -0.5), 1.0);             // (1 + e)^(-1/2) up to O(e^3)
+  cs = csd * f; s = make_double2(sx * f, sy * f);
+}
+
+// One-sided (Hestenes) Jacobi on a matrix with at most 64 columns and 128 rows, entirely in shared memory: one warp per column
+// pair of the round-robin step (lane = row), three dot products by warp shuffles, the rotation applied to the two columns of W
+// and of V, one block barrier per step.  Then sigma_j = ||W_j||, the sort and the reference's truncation rule (tensors.jl:201-215),
+// and W / V go back to the ordinary workspace layout Z = [W ; V] so that the gathers do not change.  Replaces ~15 launches
+// (init, 3 x (memset, Gram GEMM, pair EVD, rotation GEMM), column norms, sort) of the general path: the bond of the reference's own
+// example (examples/dmrg.jl, 22 x 22) spent 450 of its 920 us there.
+constexpr int SMALL_MAX_ROWS = 128;
+__global__ void __launch_bounds__(1024, 1) small_svd_kernel(const cplx* __restrict__ M, long long ld, int transposed, int rows, int ncols,
+                                                            cplx* __restrict__ Z, int ldz, double* __restrict__ sig, int* __restrict__ perm,
+                                                            int nsv, double cutoff, long long maxdim, long long mindim, int* __restrict__ kout,
+                                                            int* __restrict__ sweeps_out, double tol) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int nact = (ncols + 1) & ~1, npairs = nact / 2;
+  cplx* W = reinterpret_cast<cplx*>(sm_raw);                  // rows x nact, column-major, leading dimension rows
+  cplx* V = W + (size_t)rows * nact;                          // nact x nact
+  __shared__ double s2[JP];
+  __shared__ unsigned long long offbits;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < rows * nact; e += blockDim.x) {
+    const int r = e % rows, c = e / rows;
+    cplx v = make_double2(0, 0);
+    if (c < ncols) {
+      if (!transposed) v = M[r + (long long)c * ld];
+      else { const cplx t = M[c + (long long)r * ld]; v = make_double2(t.x, -t.y); }
+    }
+    W[e] = v;
+  }
+  for (int e = tid; e < nact * nact; e += blockDim.x) V[e] = make_double2((e % nact) == (e / nact) ? 1.0 : 0.0, 0.0);
+  if (tid == 0) offbits = 0ull;
+  __syncthreads();
+  const double tol2 = tol * tol;
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    for (int step = 0; step < nact - 1; ++step) {
+      if (warp < npairs) {
+        int p, q;
+        rr_pair(nact, step, warp, p, q);
+        cplx* wp = W + (size_t)p * rows; cplx* wq = W + (size_t)q * rows;
+        cplx xp[4], xq[4];
+        double a = 0, b = 0, cr = 0, ci = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = lane + 32 * i;
+          if (r < rows) {
+            xp[i] = wp[r]; xq[i] = wq[r];
+            a = fma(xp[i].x, xp[i].x, fma(xp[i].y, xp[i].y, a));
+            b = fma(xq[i].x, xq[i].x, fma(xq[i].y, xq[i].y, b));
+            cr = fma(xp[i].x, xq[i].x, fma(xp[i].y, xq[i].y, cr));       // conj(xp) * xq
+            ci = fma(xp[i].x, xq[i].y, fma(-xp[i].y, xq[i].x, ci));
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+          cr += __shfl_xor_sync(0xffffffffu, cr, o); ci += __shfl_xor_sync(0xffffffffu, ci, o);
+        }
+        const double absc2 = fma(cr, cr, ci * ci);
+        if (absc2 > tol2 * a * b && absc2 > 1e-280) {
+          if (lane == 0) atomicMax(&offbits, (unsigned long long)__double_as_longlong(absc2 / (a * b)));
+          double cs; cplx s;
+          jacobi_params(a, b, make_double2(cr, ci), absc2, cs, s);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = lane + 32 * i;
+            if (r < rows) {
+              const cplx ys = cmulc(xq[i], s), xs = cmul(xp[i], s);
+              wp[r] = make_double2(cs * xp[i].x - ys.x, cs * xp[i].y - ys.y);
+              wq[r] = make_double2(xs.x + cs * xq[i].x, xs.y + cs * xq[i].y);
+            }
+          }
+          cplx* vp = V + (size_t)p * nact; cplx* vq = V + (size_t)q * nact;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = lane + 32 * i;
+            if (r < nact) {
+              const cplx x = vp[r], y = vq[r];
+              const cplx ys = cmulc(y, s), xs = cmul(x, s);
+              vp[r] = make_double2(cs * x.x - ys.x, cs * x.y - ys.y);
+              vq[r] = make_double2(xs.x + cs * y.x, xs.y + cs * y.y);
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    const unsigned long long ob = offbits;
+    __syncthreads();
+    if (tid == 0) offbits = 0ull;
+    __syncthreads();
+    if (ob == 0ull) { ++sweep; break; }             // no pair was above the threshold in this sweep
+  }
+  // squared column norms, descending order (ties by index; padding columns last), truncation rank
+  if (tid < JP) {
+    double v = -1.0;
+    if (tid < ncols) { v = 0; const cplx* wc = W + (size_t)tid * rows; for (int r = 0; r < rows; ++r) v = fma(wc[r].x, wc[r].x, fma(wc[r].y, wc[r].y, v)); }
+    s2[tid] = v;
+  }
+  __syncthreads();
+  if (tid < JP) {
+    const double v = s2[tid];
+    int rank = 0;
+    for (int i = 0; i < JP; ++i) { const double u = s2[i]; rank += (u > v || (u == v && i < tid)) ? 1 : 0; }
+    sig[rank] = sqrt(fmax(v, 0.0)); perm[rank] = tid;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // reference rule, src/tensors.jl:201-215 (the S==0 test at :205 is a no-op)
+    const long long n = nsv;
+    const long long mind = mindim < n ? mindim : n;
+    long long maxd = (maxdim == 0 || maxdim > n) ? n : maxdim;
+    if (maxd == 0) maxd = 1;
+    if (cutoff != 0.0) {
+      double tot = 0;
+      for (long long i = 0; i < n; ++i) tot += sig[i] * sig[i];
+      double run = 0; long long keep = 0;
+      for (long long i = n - 1; i >= 0; --i) { run += sig[i] * sig[i]; if (run / tot > cutoff) { keep = i + 1; break; } }
+      if (keep == 0) keep = 1;
+      if (keep < maxd) maxd = keep;
+    }
+    kout[0] = (int)(maxd > mind ? maxd : mind);
+    sweeps_out[0] = sweep;
+  }
+  // back to the workspace layout: Z(0:rows, j) = W(:, j), Z(rows + i, j) = V(i, j)
+  for (int e = tid; e < rows * nact; e += blockDim.x) { const int r = e % rows, c = e / rows; Z[r + (long long)c * ldz] = W[e]; }
+  for (int e = tid; e < nact * nact; e += blockDim.x) { const int r = e % nact, c = e / nact; Z[rows + r + (long long)c * ldz] = V[e]; }
+}
+
 // ---- preparation / finalisation kernels -----------------------------------------------------
 __global__ void __launch_bounds__(256) svd_init_kernel(const cplx* __restrict__ M, long long ld, int m, int n, int transposed,
                                                         cplx* __restrict__ Z, int rows, int ncols, int ncols_pad, int ldz) {
@@ -706,6 +856,11 @@ static double early_stop() {
   if (v < 0) { const char* e = getenv("TN_SVD_EARLY"); v = e ? atof(e) : 1e-9; }
   return v;
 }
+static bool small_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_SMALL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 static bool wonly_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("TN_SVD_WONLY"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -973,6 +1128,28 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   int blocks;
   SvdProf& pf = prof();
   if (pf.on) { for (double& m : pf.ms) m = 0; pf.used = 0; pf.mark(PH_START, s); }
+  if (!w.precond && npad == JP && w.rows <= SMALL_MAX_ROWS && small_enabled()) {
+    // at most 64 columns and 128 rows: the whole factorisation (init, sweeps, norms, sort, truncation rank) in one single-CTA launch
+    w.jrows = w.rows;
+    w.ldz = pad_ld(w.rows + npad);
+    ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
+    const int nact = (w.ncols + 1) & ~1;
+    const size_t smem = ((size_t)w.rows * nact + (size_t)nact * nact) * sizeof(cplx);
+    static DeviceOnce small_cfg;
+    small_cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(small_svd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)SMALL_MAX_ROWS * JP + (size_t)JP * JP) * sizeof(cplx)))); });
+    const double tol = 3.0 * std::sqrt((double)w.rows) * 2.220446049250313e-16;
+    small_svd_kernel<<<1, 32 * std::max(2, nact / 2), smem, s>>>(M, ld, w.transposed ? 1 : 0, w.rows, w.ncols, w.Z, w.ldz, w.sig, w.perm, w.nsv,
+                                                              tr.cutoff, tr.maxdim, tr.mindim, w.kout, w.cflag, tol);
+    TN_CUDA(cudaGetLastError());
+    count_launch(1);
+    int ks[2] = {0, 0};
+    TN_CUDA(cudaMemcpyAsync(&ks[0], w.kout, 4, cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(&ks[1], w.cflag, 4, cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaStreamSynchronize(s));
+    w.k = ks[0]; w.sweeps = ks[1];
+    if (pf.on) { pf.mark(PH_FIN, s); pf.flush(s); }
+    return w.k;
+  }
   if (!w.precond) {
     w.jrows = w.rows;
     w.ldz = pad_ld(w.rows + npad);
