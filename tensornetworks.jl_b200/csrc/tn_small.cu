@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(SL_THREADS, 1) lanczos_small_kernel(SmallBond 
     __syncthreads();
     for (int e = tid; e < n; e += SL_THREADS) {         // out[(a,s1,s2),a'] = coeff sum_{(w2,b')} T2[(a,s1,s2),(w2,b')] R[a',(w2,b')]
       const int m = e % (ca * d2), ap = e / (ca * d2);
+      const cplx* t2 = T2 + (m % ca) + ca * (m / ca);   // + ca d2 iw2 + ca NW b'
+      const cplx* rr = Rs + ap;                         // + ca2 (iw2 + w2 b')
       double xr = 0, xi = 0;
-      for (int kk = 0; kk < w2 * ca2; ++kk) {
-        const int iw2 = kk % w2, bp = kk / w2;
-        const cplx t = T2[m % ca + ca * ((m / ca) + d2 * iw2) + ca * NW * bp], r = Rs[ap + ca2 * kk];
-        xr += t.x * r.x - t.y * r.y; xi += t.x * r.y + t.y * r.x;
-      }
+      for (int bp = 0; bp < ca2; ++bp)
+        for (int iw2 = 0; iw2 < w2; ++iw2) {
+          const cplx t = t2[ca * d2 * iw2 + ca * NW * bp], r = rr[ca2 * (iw2 + w2 * bp)];
+          xr += t.x * r.x - t.y * r.y; xi += t.x * r.y + t.y * r.x;
+        }
       out[e] = cmul_(p.coeff, make_double2(xr, xi));
     }
     __syncthreads();

@@ -861,6 +861,11 @@ static bool small_enabled() {
   if (v < 0) { const char* e = getenv("TN_SVD_SMALL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
+static int small_max_cols() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_SMALL_MAXCOLS"); v = e ? std::max(2, std::min(JP, atoi(e))) : 32; }
+  return v;
+}
 static bool wonly_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("TN_SVD_WONLY"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1128,8 +1133,11 @@ int svd_factor(SvdWork& w, const cplx* M, int m, int n, long long ld, Trunc tr, 
   int blocks;
   SvdProf& pf = prof();
   if (pf.on) { for (double& m : pf.ms) m = 0; pf.used = 0; pf.mark(PH_START, s); }
-  if (!w.precond && npad == JP && w.rows <= SMALL_MAX_ROWS && small_enabled()) {
-    // at most 64 columns and 128 rows: the whole factorisation (init, sweeps, norms, sort, truncation rank) in one single-CTA launch
+  if (!w.precond && w.ncols <= small_max_cols() && w.rows <= SMALL_MAX_ROWS && small_enabled()) {
+    // small matrices (default: at most 32 columns, 128 rows): the whole factorisation (init, sweeps, norms, sort, truncation rank) in one
+    // single-CTA launch.  Measured on a B200: 22 x 22 inside the C1 sweep 146 us against ~410 us for the general path; plain one-sided
+    // Jacobi needs 17-28 sweeps on a graded spectrum without the QR preconditioner (22: 0.45 ms, 64: 4.2 ms), so 64 columns stay
+    // on the general path (a de Rijk column swap made it worse in the parallel ordering: 23-43 sweeps)
     w.jrows = w.rows;
     w.ldz = pad_ld(w.rows + npad);
     ensure(w.Z, w.Z_cap, (size_t)w.ldz * npad, s);
