@@ -105,6 +105,26 @@ def oracle_mpo_pair():
     return np.asfortranarray(H[SITE]), np.asfortranarray(H[SITE + 1])
 
 
+def julia_reference_sample(chi, w, M1, M2, steps, warmup, rows):
+    """The reference itself, when it can run: `julia` on the PATH and TN_REFERENCE_JL = a checkout of lcauser/TensorNetworks.jl with its
+    dependencies instantiated (neither exists in the build image or on the GPU boxes of this pool).  Returns the parsed JSON line of
+    baseline/run_reference.jl or None."""
+    import shutil
+    proj = os.environ.get("TN_REFERENCE_JL", "")
+    if not shutil.which("julia") or not os.path.isdir(proj):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            f1, f2 = os.path.join(td, "M1.bin"), os.path.join(td, "M2.bin")
+            open(f1, "wb").write(np.asfortranarray(M1).tobytes(order="F"))
+            open(f2, "wb").write(np.asfortranarray(M2).tobytes(order="F"))
+            r = subprocess.run(["julia", "-t1", f"--project={proj}", os.path.join(ROOT, "baseline", "run_reference.jl"), str(chi), str(w), str(rows),
+                                str(steps), str(warmup), f1, f2], capture_output=True, text=True, timeout=1800)
+        return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    except Exception:
+        return None
+
+
 def cpu_reference_sample(chi, w, M1, M2, steps, warmup, rows=REF_ROWS, budget_s=None):
     """The reference's CPU path on the bounded sample: oracle ProjMPS.product (reference contraction order, projmps.jl:119-134)
     with the left block restricted to ``rows`` bra-bond rows.  Returns (tflops, timed steps, seconds, cores, out[:rows])."""
@@ -341,14 +361,21 @@ def run_reference(args):
     assert M1.shape == (w, D, D, w) and M2.shape == (w, D, D, w), (M1.shape, M2.shape)
     W_eff = max(3, args.warmup)
     rows = min(REF_ROWS, chi)
-    tf, calls, secs, cores, _ = cpu_reference_sample(chi, w, M1, M2, args.steps, W_eff, rows=rows)
+    kind = "port"
+    jl = julia_reference_sample(chi, w, M1, M2, args.steps, W_eff, rows)
+    if jl is not None:
+        tf, calls, secs, cores, kind = jl["tflops"], args.steps, jl["seconds_per_step"] * args.steps, jl["threads"], "julia"
+        how = f"the reference itself under Julia {jl['julia']} (baseline/run_reference.jl), {cores} BLAS threads"
+    else:
+        tf, calls, secs, cores, _ = cpu_reference_sample(chi, w, M1, M2, args.steps, W_eff, rows=rows)
+        how = f"NumPy/OpenBLAS port of the reference's product(), {cores} threads"
     sample = (f"each step = rows a in [0,{rows}) of one H_eff*Theta at chi={chi}, w={w} ({rows}/{chi} of a full application, normalised by the same "
-              f"fraction of F_mv), reference contraction order (L.M1.M2 first), NumPy/OpenBLAS, {cores} threads")
+              f"fraction of F_mv), reference contraction order (L.M1.M2 first), {how}")
     line = {
         "impl": "reference", "metric": METRIC, "value": tf, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": calls, "warmup": W_eff,
         "ms_per_step": secs / calls * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c128 (complex f64)",
         "data": "synthetic", "config": config(chi, w),
-        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": tf, "unit": "TFLOP/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": tf, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
