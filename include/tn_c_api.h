@@ -283,6 +283,19 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
                          const tn_cplx* obs_op, int32_t save_every, tn_cplx* obs_out, int32_t* njumps_out,
                          int32_t* jumps_out, double* jumptimes_out, int32_t jump_cap, int32_t classical);
 
+/* ---- MPO-bond-sharded H_eff application on several GPUs of ONE process (the library owns the NCCL
+ * communicators) -----------------------------------------------------------------------------------------------------------
+ * Replaces product(projV, A, ...) (structures/mps/projmps.jl:103-145) when the environment blocks of a large-chi bond are spread over
+ * the box.  L (chi, w, chi), R (chi2, w2, chi2), M1 (w, d, d, w1), M2 (w1, d, d, w2): host buffers, borrowed for the call; device g
+ * keeps rows [m0, m1) of the fused (a, w) index of L and an equal chunk of the fused (b', w2) index of R.  apply: theta (chi, d, d,
+ * chi2) and out are host buffers; per call one local chi^3 stage, the small MPO stage, ncclReduceScatter, the second local chi^3
+ * stage and ncclAllReduce run on one stream per device.  NCCL (libnccl.so.2) is loaded at run time; ngpus = 1 needs none. */
+typedef struct tn_shard tn_shard;
+int32_t tn_heff_sharded_create(int32_t ngpus, const int32_t* device_ids, int64_t chi, int64_t chi2, int32_t d, int64_t w, int64_t w1, int64_t w2,
+                               const tn_cplx* L, const tn_cplx* R, const tn_cplx* M1, const tn_cplx* M2, tn_cplx coeff, tn_shard** out);
+int32_t tn_heff_sharded_apply(tn_shard* h, const tn_cplx* theta, tn_cplx* out);
+int32_t tn_heff_sharded_free(tn_shard* h);
+
 #ifdef __cplusplus
 }
 #endif

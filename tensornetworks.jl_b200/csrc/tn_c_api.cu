@@ -12,6 +12,14 @@ int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cpl
              const cplx* obs_op, int save_every, cplx* obs_out, int* jumps_out, double* jumptimes_out, int jump_cap, bool classical);
 }
 
+namespace tn {
+struct Shard;
+Shard* shard_create(int G, const int* devices, long long ca, long long ca2, int d, long long w, long long w1, long long w2,
+                    const cplx* L, const cplx* R, const cplx* M1, const cplx* M2, cplx coeff);
+void shard_apply(Shard* sh, const cplx* theta_host, cplx* out_host);
+void shard_free(Shard* s);
+}
+
 using namespace tn;
 
 // One context = one GPU + one stream + its workspaces (also used by the worker threads of tn_qjmc_ensemble).
@@ -50,6 +58,7 @@ struct tn_env { Env* e; };
 struct tn_gates { Gates* g; };
 struct tn_envsum { EnvSum* s; };
 struct tn_imps { IMps* m; };
+struct tn_shard { Shard* s; };
 
 
 // Every handle remembers the device of its context; an entry point makes that device current for the calling thread before it
@@ -697,6 +706,21 @@ int32_t tn_itebd_apply_gate(tn_imps* p, const tn_cplx* gate_host, int32_t nsteps
     c->sync();
   });
 }
+
+// ---- MPO-bond-sharded H_eff application over several GPUs of this process (tn_shard.cu) ------------------------------------
+int32_t tn_heff_sharded_create(int32_t ngpus, const int32_t* device_ids, int64_t chi, int64_t chi2, int32_t d, int64_t w, int64_t w1, int64_t w2,
+                               const tn_cplx* L, const tn_cplx* R, const tn_cplx* M1, const tn_cplx* M2, tn_cplx coeff, tn_shard** out) {
+  return guard([&] {
+    TN_CHECK(out && device_ids, "tn_heff_sharded_create: null pointer");
+    std::vector<int> dev(device_ids, device_ids + std::max(0, (int)ngpus));
+    Shard* s = shard_create(ngpus, dev.data(), chi, chi2, d, w, w1, w2, C(L), C(R), C(M1), C(M2), cplx{coeff.re, coeff.im});
+    *out = new tn_shard{s};
+  });
+}
+int32_t tn_heff_sharded_apply(tn_shard* h, const tn_cplx* theta, tn_cplx* out) {
+  return guard([&] { TN_CHECK(h && theta && out, "tn_heff_sharded_apply: null handle"); shard_apply(h->s, C(theta), C(out)); });
+}
+int32_t tn_heff_sharded_free(tn_shard* h) { return guard([&] { if (h) { shard_free(h->s); delete h; } }); }
 
 int32_t tn_inner_oplist(tn_mps* psi, tn_mps* phi, int32_t nterms, const int32_t* nops, const int32_t* op_sites, const tn_cplx* ops_host,
                         const tn_cplx* coeffs, tn_cplx* out) {

@@ -767,6 +767,175 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_inv64_kernel(const cplx*
   }
 }
 
+// ---- blocked variant of chol_inv64_kernel ------------------------------------------------------------------------------------------
+// Same inputs, outputs and null-column / failed-pivot semantics, but the 64 pivots are processed in four 16-wide blocks: the diagonal
+// block is factorised and inverted by ONE warp (warp-level synchronisation only), the block row R12 = R11^-H G12 and the trailing update
+// G22 -= R12^H R12 are small GEMMs over the whole CTA -- 3 block barriers per 16 pivots instead of one per pivot -- and the inverse
+// is assembled block column by block column.  ncu on the one-barrier-per-column kernel (profiles/r02_ncu_full_summary.json): 108 us
+// per call, stalled on barriers / shared-memory latency at 25 % FP64 utilisation; it is half of the QR phase at n = 2048 and 70 % of it
+// at n = 512 (64 calls per 512 x 512 factorisation).
+constexpr int CB = 16;                       // pivot block
+constexpr int CHOL2_THREADS = 512;
+__global__ void __launch_bounds__(CHOL2_THREADS, 1) chol_inv64b_kernel(const cplx* __restrict__ Gpart, cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot,
+                                                                       int pass, int last_pass, double shift_factor, int* __restrict__ done_flag) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);                                    // G, then R in its upper triangle
+  cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1
+  cplx (*Ro)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + 2 * sizeof(cplx) * JP * (JP + 1)); // old Rtot
+  __shared__ double red[CHOL2_THREADS / 32];
+  __shared__ int nullcol[JP];
+  __shared__ double rrow[JP];       // 1 / R(j,j) per row (0 = null / failed pivot)
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  Gpart += (long long)blockIdx.x * JP * JP; Rinv_out += (long long)blockIdx.x * JP * JP; Rtot += (long long)blockIdx.x * JP * JP;
+  if (done_flag != nullptr) done_flag += blockIdx.x;
+  if (done_flag != nullptr) {
+    if (pass == 0) { if (tid == 0) *done_flag = 0; }
+    else if (pass == 2 && *done_flag != 0) return;
+  }
+  double fro = 0;
+  for (int e = tid; e < JP * JP; e += CHOL2_THREADS) {
+    const int row = e % JP, col = e / JP;
+    const cplx v = Gpart[e];
+    G[row][col] = v;
+    fro += v.x * v.x + v.y * v.y;
+    Ri[row][col] = make_double2(0, 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
+  if (lane == 0) red[wrp] = fro;
+  __syncthreads();
+  fro = 0; for (int i = 0; i < CHOL2_THREADS / 32; ++i) fro += red[i];
+  const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
+  if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
+  __syncthreads();
+  double dev = 0;                                        // max |G - I| over the non-null part (second pass only)
+  for (int e = tid; e < JP * JP; e += CHOL2_THREADS) {   // symmetrise + shift
+    const int row = e % JP, col = e / JP;
+    if (row < col) {
+      const cplx a = G[row][col], b = G[col][row];
+      const cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+      G[row][col] = h; G[col][row] = make_double2(h.x, -h.y);
+      dev = fmax(dev, fmax(fabs(h.x), fabs(h.y)));
+    } else if (row == col) {
+      if (!nullcol[row]) dev = fmax(dev, fabs(G[row][col].x - 1.0));
+      G[row][col].x += shift; G[row][col].y = 0;
+    }
+  }
+  if (done_flag != nullptr && pass == 1) {
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    __syncthreads();                                     // red[] was read above
+    if (lane == 0) red[wrp] = dev;
+    __syncthreads();
+    dev = 0; for (int i = 0; i < CHOL2_THREADS / 32; ++i) dev = fmax(dev, red[i]);
+    if (dev < 1e-3) { last_pass = 1; if (tid == 0) *done_flag = 1; }
+  }
+  __syncthreads();
+  for (int kb = 0; kb < JP / CB; ++kb) {
+    const int b0 = kb * CB, b1 = b0 + CB;
+    if (wrp == 0) {
+      // (1) right-looking Cholesky of the diagonal block by one warp: pivot j reads row j (final), updates the trailing upper triangle
+      for (int j = b0; j < b1; ++j) {
+        const double dd = G[j][j].x;
+        const bool bad = nullcol[j] || !(dd > 0.0) || !isfinite(dd);
+        const double ri = bad ? 0.0 : rsqrt(dd);
+        const double sc = ri * ri;
+        if (lane == 0) rrow[j] = ri;
+        if (!bad) {
+          const int nt = b1 - 1 - j;                     // trailing rows / columns inside the block
+          for (int e = lane; e < nt * nt; e += 32) {
+            const int i = j + 1 + e / nt, c = j + 1 + e % nt;
+            if (i <= c) {
+              const cplx gji = G[j][i], gjc = G[j][c];
+              const double ar = gji.x * gjc.x + gji.y * gjc.y, ai = gji.x * gjc.y - gji.y * gjc.x;   // conj(G(j,i)) G(j,c)
+              cplx v = G[i][c];
+              v.x = fma(-sc, ar, v.x); v.y = fma(-sc, ai, v.y);
+              G[i][c] = v;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      // rows of the diagonal block scaled to R11 (null / failed pivot: unit row)
+      for (int e = lane; e < CB * CB; e += 32) {
+        const int row = b0 + e / CB, col = b0 + e % CB;
+        if (col < row) continue;
+        const double ri = rrow[row];
+        if (ri == 0.0) G[row][col] = make_double2(col == row ? 1.0 : 0.0, 0.0);
+        else { const cplx v = G[row][col]; G[row][col] = (col == row) ? make_double2(v.x * ri, 0.0) : make_double2(v.x * ri, v.y * ri); }
+      }
+      __syncwarp();
+      // (2) inverse of the 16 x 16 upper-triangular R11 by back substitution: lane = column (lanes 16..31 idle)
+      if (lane < CB) {
+        const int cc = b0 + lane;
+        for (int i = cc; i >= b0; --i) {
+          double ar = 0, ai = 0;
+          for (int k = i + 1; k <= cc; ++k) { const cplx a = G[i][k], b = Ri[k][cc]; ar += a.x * b.x - a.y * b.y; ai += a.x * b.y + a.y * b.x; }
+          const double dinv = rrow[i] == 0.0 ? 1.0 : rrow[i];
+          Ri[i][cc] = make_double2(((i == cc ? 1.0 : 0.0) - ar) * dinv, -ai * dinv);
+        }
+      }
+    }
+    __syncthreads();
+    // (3) R12 = R11^-H G12 (rows b0..b1, columns >= b1); rows of null / failed pivots are zero
+    const int nc = JP - b1;
+    for (int e = tid; e < CB * nc; e += CHOL2_THREADS) {
+      const int r = b0 + e % CB, c = b1 + e / CB;
+      double xr = 0, xi = 0;
+      if (rrow[r] != 0.0)
+        for (int k = b0; k <= r; ++k) { const cplx a = Ri[k][r], g = G[k][c]; xr += a.x * g.x + a.y * g.y; xi += a.x * g.y - a.y * g.x; }   // conj(Rinv(k,r)) G(k,c)
+      Ro[r][c] = make_double2(xr, xi);                  // scratch: another thread still needs the old G(r, c) for a row below r
+    }
+    __syncthreads();
+    for (int e = tid; e < CB * nc; e += CHOL2_THREADS) { const int r = b0 + e % CB, c = b1 + e / CB; G[r][c] = Ro[r][c]; }
+    __syncthreads();
+    // (4) trailing update G22 -= R12^H R12 (upper triangle)
+    for (int e = tid; e < nc * nc; e += CHOL2_THREADS) {
+      const int i = b1 + e % nc, c = b1 + e / nc;
+      if (i > c) continue;
+      double xr = 0, xi = 0;
+#pragma unroll 4
+      for (int k = b0; k < b1; ++k) { const cplx a = G[k][i], b = G[k][c]; xr += a.x * b.x + a.y * b.y; xi += a.x * b.y - a.y * b.x; }
+      cplx v = G[i][c]; v.x -= xr; v.y -= xi; G[i][c] = v;
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < JP * JP; e += CHOL2_THREADS) { const int row = e / JP, col = e % JP; if (col < row) G[row][col] = make_double2(0, 0); }
+  __syncthreads();
+  // (5) off-diagonal blocks of R^-1, block column by block column: Rinv_ij = -Rinv_ii sum_{i < l <= j} R_il Rinv_lj  (i = j-1 .. 0)
+  for (int step = 1; step < JP / CB; ++step) {
+    // all block columns j >= step handle their block row i = j - step at once (they only need rows > i of their own column)
+    for (int e = tid; e < (JP / CB - step) * CB * CB; e += CHOL2_THREADS) {
+      const int jb = step + e / (CB * CB), ib = jb - step, r = ib * CB + (e % (CB * CB)) % CB, c = jb * CB + (e % (CB * CB)) / CB;
+      double xr = 0, xi = 0;
+      for (int k = (ib + 1) * CB; k <= c; ++k) { const cplx a = G[r][k], b = Ri[k][c]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+      Ro[c][r] = make_double2(xr, xi);                  // T = R_i,(i+1..j) Rinv_(i+1..j),j  (scratch, stored transposed)
+    }
+    __syncthreads();
+    for (int e = tid; e < (JP / CB - step) * CB * CB; e += CHOL2_THREADS) {
+      const int jb = step + e / (CB * CB), ib = jb - step, r = ib * CB + (e % (CB * CB)) % CB, c = jb * CB + (e % (CB * CB)) / CB;
+      double xr = 0, xi = 0;
+      for (int k = r; k < (ib + 1) * CB; ++k) { const cplx a = Ri[r][k], t = Ro[c][k]; xr += a.x * t.x - a.y * t.y; xi += a.x * t.y + a.y * t.x; }
+      Ri[r][c] = make_double2(-xr, -xi);
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < JP * JP; e += CHOL2_THREADS) { const int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
+  // (6) Rtot <- R * Rtot_old  (pass 0: Rtot = R)
+  if (pass != 0) {
+    for (int e = tid; e < JP * JP; e += CHOL2_THREADS) Ro[e % JP][e / JP] = Rtot[e];     // the accumulated R of the earlier passes
+    __syncthreads();
+  }
+  for (int e = tid; e < JP * JP; e += CHOL2_THREADS) {
+    const int row = e % JP, col = e / JP;
+    double xr = 0, xi = 0;
+    if (pass == 0) { if (col >= row) { xr = G[row][col].x; xi = G[row][col].y; } }
+    else {
+      for (int k = row; k < JP; ++k) { const cplx a = G[row][k], b = Ro[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+    }
+    if (last_pass && nullcol[row]) { xr = 0; xi = 0; }
+    Rtot[e] = make_double2(xr, xi);
+  }
+}
+
 // dst(c, r) = conj(src(r, c)): dst is cols x rows (ldd), src rows x cols (lds); optional zero fill beyond (rows_valid, cols_valid)
 __global__ void __launch_bounds__(256) conj_transpose_kernel(const cplx* __restrict__ src, long long lds, int rows, int cols,
                                                               cplx* __restrict__ dst, long long ldd) {
@@ -786,6 +955,25 @@ __global__ void __launch_bounds__(256) set_identity_kernel(cplx* __restrict__ ds
 }
 
 // ---- host driver ------------------------------------------------------------------------------
+
+// Panel Cholesky + inverse over `nb` Gram blocks (TN_SVD_CHOL=1 selects the one-barrier-per-column kernel).
+static void launch_chol(int nb, const cplx* Gp, cplx* Rinv, cplx* Rtot, int pass, int last, double shift_factor, int* flag, cudaStream_t s) {
+  static int ver = -1;
+  if (ver < 0) { const char* e = getenv("TN_SVD_CHOL"); ver = (e && e[0] == '1') ? 1 : 2; }
+  if (ver == 1) {
+    static DeviceOnce cfg1;
+    const int smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
+    cfg1.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+    chol_inv64_kernel<<<nb, CHOL_THREADS, smem, s>>>(Gp, 1, (long long)JP * JP, Rinv, Rtot, pass, last, shift_factor, flag);
+  } else {
+    static DeviceOnce cfg2;
+    const int smem = 3 * JP * (JP + 1) * (int)sizeof(cplx);
+    cfg2.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+    chol_inv64b_kernel<<<nb, CHOL2_THREADS, smem, s>>>(Gp, Rinv, Rtot, pass, last, shift_factor, flag);
+  }
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
 
 // Launches the pair EVD over `npairs` Gram blocks (TN_SVD_EVD=1 selects the first-generation kernel).
 static void launch_evd(int npairs, const cplx* Gp, cplx* Jp, double tol, unsigned long long* offmax, int inner, int nact, int* skip, cudaStream_t s) {
@@ -998,9 +1186,6 @@ static GemmDesc gd(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int con
 //   Q (rows x npad, ld = ldq) is overwritten by the orthonormal factor, R (npad x npad, ld = npad) receives the
 //   upper-triangular factor.  Everything is GEMM-shaped (tn_zgemm.cu) plus the 64x64 Cholesky kernel.
 static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, int chol_passes, cudaStream_t s) {
-  static DeviceOnce cfg;
-  const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
-  cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem)); });
   TN_CUDA(cudaMemsetAsync(R, 0, (size_t)npad * npad * sizeof(cplx), s));
   ensure(w.Gpart, w.G_cap, (size_t)32 * JP * JP, s);
   int ksplit = std::max(1, std::min(std::min(32, max_split()), rows / 64));   // one 64 x 64 tile per panel: spread its K range over many SMs
@@ -1019,10 +1204,7 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       g.skip = skip3;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)JP * JP * sizeof(cplx), s));
       zgemm_auto(g, s);
-      chol_inv64_kernel<<<1, CHOL_THREADS, chol_smem, s>>>(w.Gpart, 1, (long long)JP * JP, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
-                                                  chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr);
-      TN_CUDA(cudaGetLastError());
-      count_launch(1);
+      launch_chol(1, w.Gpart, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0, chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr, s);
       // P <- P * Rinv (in place: each CTA owns 128 rows x all 64 columns)
       GemmDesc ap = gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq));
       ap.skip = skip3;
@@ -1550,8 +1732,6 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
 static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, cplx* R, int chol_passes, cudaStream_t s) {
   const int B = w.B;
   const long long qs = (long long)npad * ldq, rs = (long long)npad * npad, gs = (long long)JP * JP;
-  const int chol_smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
-  TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chol_smem));
   TN_CUDA(cudaMemsetAsync(R, 0, (size_t)B * rs * sizeof(cplx), s));
   ensure(w.Gpart, w.G_cap, (size_t)B * gs, s);
   // B tiles of 64 x 64 per panel: split their K range until about one wave of CTAs is in flight
@@ -1571,10 +1751,7 @@ static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, 
       g.skip = skip3;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)B * gs * sizeof(cplx), s));
       zgemm_auto(g, s);
-      chol_inv64_kernel<<<B, CHOL_THREADS, chol_smem, s>>>(w.Gpart, 1, gs, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0,
-                                                          chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr);
-      TN_CUDA(cudaGetLastError());
-      count_launch(1);
+      launch_chol(B, w.Gpart, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0, chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr, s);
       GemmDesc ap = gd(rows, JP, JP, P, idx1(1), idx1(ldq), 0, Rinv, idx1(1), idx1(JP), 0, P, idx1(1), idx1(ldq));
       ap.batch = B; ap.bsA = qs; ap.bsB = gs; ap.bsC = qs;
       ap.skip = skip3;

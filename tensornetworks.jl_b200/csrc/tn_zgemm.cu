@@ -432,7 +432,12 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
         if (dur < best - 1e-9) { best = dur; pl.nseg = ns; }
       }
       pl.unit_ctas = 0;
-      if (pl.dp_tiles == 0) {   // small problem: contiguous unit runs, at least 16 k-tiles per CTA
+      // Under two waves with operands that fit in L2: contiguous unit runs.  With operands beyond L2 (e.g. the a'-slices of the
+      // pipelined host-buffer matvec: M = 8192, N = 256, K = 40960, A = 5.4 GB) the unit runs read A once PER N-TILE -- ncu measured
+      // 44 GB of DRAM reads for such a launch -- whereas the lockstep segments above keep the CTAs of neighbouring tiles on the
+      // same k range (profiles/r02_ncu_full_summary.json).
+      const double operand_bytes = 16.0 * ((double)d.M * d.K + (double)d.K * d.N);
+      if (pl.dp_tiles == 0 && operand_bytes <= 64.0 * 1024 * 1024) {   // small problem: contiguous unit runs, at least 16 k-tiles per CTA
         pl.unit_ctas = (int)std::max<long long>(1, std::min<long long>(slots, (long long)pl.rem_tiles * KT / 16));
         pl.nseg = 2;            // (marks the launch as split)
       }

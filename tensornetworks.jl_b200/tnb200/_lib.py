@@ -60,6 +60,9 @@ PROTOTYPES = {
     "tn_mps_scale": [P, tn_cplx],
     "tn_expect_local": [P, I32, pI32, P, P],
     "tn_svd_trunc": [P, P, I64, I64, tn_trunc_t, P, pF64, P, pI64, pI32],
+    "tn_heff_sharded_create": [I32, pI32, I64, I64, I32, I64, I64, I64, P, P, P, P, tn_cplx, PP],
+    "tn_heff_sharded_apply": [P, P, P],
+    "tn_heff_sharded_free": [P],
     "tn_svd_trunc_split": [P, P, I64, I64, tn_trunc_t, I32, P, pF64, P, pI64, pI32, I32, pF64],
     "tn_svd_trunc_batched": [P, I32, P, I64, I64, tn_trunc_t, P, pF64, P, pI64, pI32],
     "tn_svd_set_precond": [I32],

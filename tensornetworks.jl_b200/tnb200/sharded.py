@@ -34,6 +34,43 @@ def dense_w(M1, M2):
     return np.reshape(W, (w * d * d, d * d * M2.shape[3]), order='F')
 
 
+class HeffSharded:
+    """MPO-bond-sharded H_eff application over several GPUs of THIS process, entirely behind the C ABI (tn_heff_sharded_*: one stream
+    per device, NCCL communicators owned by the library) -- what a ccall caller uses.  L (chi, w, chi), R (chi2, w2, chi2),
+    M1 (w, d, d, w1), M2 (w1, d, d, w2) are host arrays; apply(theta) takes and returns host arrays (projmps.jl:103-145)."""
+
+    def __init__(self, L, R, M1, M2, devices, coeff=1.0):
+        self.lib = _lib.load()
+        L, R, M1, M2 = (np.asfortranarray(np.asarray(x, dtype=np.complex128)) for x in (L, R, M1, M2))
+        chi, w, _ = L.shape
+        chi2, w2, _ = R.shape
+        d, w1 = M1.shape[1], M1.shape[3]
+        self.shape_in = (chi, d, d, chi2)
+        dev = np.asarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        cf = complex(coeff)
+        check(self.lib.tn_heff_sharded_create(len(dev), dev.ctypes.data_as(C.POINTER(C.c_int32)), chi, chi2, d, w, w1, w2,
+                                              C.c_void_p(L.ctypes.data), C.c_void_p(R.ctypes.data), C.c_void_p(M1.ctypes.data), C.c_void_p(M2.ctypes.data),
+                                              tn_cplx(cf.real, cf.imag), C.byref(h)))
+        self.h = h
+
+    def apply(self, theta, out=None):
+        theta = np.asfortranarray(np.asarray(theta, dtype=np.complex128))
+        assert theta.shape == self.shape_in
+        if out is None:
+            out = np.empty(self.shape_in, dtype=np.complex128, order='F')
+        check(self.lib.tn_heff_sharded_apply(self.h, C.c_void_p(theta.ctypes.data), C.c_void_p(out.ctypes.data)))
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.tn_heff_sharded_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
 class GpuContractor:
     """C = alpha * A B + beta * C on device buffers through the C ABI (tn_contract_strided_dev)."""
 

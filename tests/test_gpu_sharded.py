@@ -77,3 +77,23 @@ def test_sharded_dmrg_two_gpus_nccl_matches_single_gpu():
         assert rec["n_gpus"] == 2 and rec["single_gpu_energies"] is not None
         for a, b in zip(rec["energies"], rec["single_gpu_energies"]):
             assert abs(a - b) <= 1e-10 * abs(b), rec
+
+
+@pytest.mark.parametrize("ngpus", [1, 2])
+def test_cabi_sharded_heff_matches_einsum(ngpus):
+    """tn_heff_sharded_* (one process, ngpus devices, NCCL inside the library): the MPO-bond-sharded matvec a ccall caller reaches,
+    against the five-tensor contraction of projmps.jl:107-134; bond dimensions that do not divide evenly over the devices."""
+    import torch
+    from tnb200.sharded import HeffSharded
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(3)
+    chi, chi2, d, w, w1, w2 = 48, 40, 2, 7, 6, 5
+    L, R = crandn(rng, chi, w, chi), crandn(rng, chi2, w2, chi2)
+    M1, M2 = crandn(rng, w, d, d, w1), crandn(rng, w1, d, d, w2)
+    theta = crandn(rng, chi, d, d, chi2)
+    want = (0.5 - 0.25j) * np.einsum('awb,wstx,xuvy,btvc,eyc->asue', L, M1, M2, theta, R)
+    sh = HeffSharded(L, R, M1, M2, list(range(ngpus)), coeff=0.5 - 0.25j)
+    for _ in range(2):
+        out = sh.apply(theta)
+        assert relerr(out, want) < 1e-13

@@ -18,10 +18,28 @@ d, dt = 2, 5e-3
 for item in spec.split(","):
     N, chi = (int(v) for v in item.split(":"))
     ss, gg = models.trotter_gates(N, -1.0 * models.X, -1.0 * np.kron(models.Z, models.Z), dt, evol="imag", order=2)
-    tens = models.random_canonical_mps(N, d, chi, seed=3)
-    psi = tnb200.GMPS(1, d, tens, 1, ctx=ctx)
+    if chi <= 512:
+        tens = models.random_canonical_mps(N, d, chi, seed=3)
+        psi = tnb200.GMPS(1, d, tens, 1, ctx=ctx)
+    else:
+        # large bonds: seeded random (non-canonical) tensors, a handful of distinct ones per shape, brought to canonical form on the
+        # device (untruncated gauge moves = one QR step each); a host QR per site would take minutes at chi = 2048
+        rng = np.random.default_rng(3)
+        dims = [min(d ** i, d ** (N - i), chi) for i in range(N + 1)]
+        pool = {}
+        tens = []
+        for i in range(N):
+            key = (dims[i], dims[i + 1], i % 4)
+            if key not in pool:
+                pool[key] = np.asfortranarray((rng.standard_normal((dims[i], d, dims[i + 1])) + 1j * rng.standard_normal((dims[i], d, dims[i + 1]))) / np.sqrt(dims[i] * d))
+            tens.append(pool[key])
+        psi = tnb200.GMPS(1, d, tens, 0, ctx=ctx)
+        del tens, pool
+        psi.movecenter(1)
+        psi.normalize()
     gl = tnb200.GateList(d, ss, gg, ctx=ctx)
-    tnb200.tebd(psi, gl, 1, cutoff=0.0, maxdim=chi)            # warm-up step (workspaces, bond dimensions settle)
+    if "--no-warmup" not in sys.argv:
+        tnb200.tebd(psi, gl, 1, cutoff=0.0, maxdim=chi)            # warm-up step (workspaces, bond dimensions settle)
     c0 = ctx.counters()
     t0 = time.perf_counter()
     psi, _, normal = tnb200.tebd(psi, gl, 1, cutoff=0.0, maxdim=chi)
@@ -30,7 +48,7 @@ for item in spec.split(","):
     c1 = ctx.counters()
     line = {"what": "tebd_step", "sites": N, "chi": chi, "maxbond": psi.maxbonddim(), "gates": sum(len(r) for r in ss), "seconds_per_step": sec,
             "svds": c1["svds"] - c0["svds"], "gpu_launches": c1["launches"] - c0["launches"], "lognorm": normal}
-    if chi <= omax:
+    if chi <= omax and chi <= 512:
         import oracle
         from oracle.gmps import GMPS as OG
         po = OG(1, d, [t.copy() for t in tens], 1)
