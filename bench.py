@@ -596,7 +596,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * n,
                     "api": api, "matches_resident_path_rel": same, "ms_per_step_events": e2e_ms / K, "ms_per_step_wall": e2e_wall / K},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": zgemm_peak, "unit": "TFLOP/s", "frac": achieved / zgemm_peak,
-                         "traffic": None, "kernel": "tn::zgemm_sk_kernel<4,1,4,4,true> (persistent stream-K, 128x32 tile, 2 CTAs/SM, DMMA.8x8x4), 2 launches per matvec",
+                         "traffic": None, "kernel": "tn::zgemm_kernel<4,1,4,4,1> (128x32 CTA tile, 2 CTAs/SM, DMMA.8x8x4, 4-stage cp.async; its persistent stream-K twin zgemm_sk_kernel runs when the tile count leaves a partial last wave), 2 launches per matvec",
                          "flops_per_launch": big_flops, "ms_per_launch": ms_launch,
                          "peak_source": "cuBLAS ZGEMM 4096^3 via torch.matmul measured in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "DMMA issue peak measured 37.17 TFLOP/s, profiles/r01_probe_fp64.jsonl)",
