@@ -753,8 +753,23 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     // trajectory-steps/s and 11x fewer launches, profiles/r02_first_run_qjmc_batching_and_sharded1.jsonl); TN_QJMC_BATCH=0
     // restores the independent multi-stream workers.
     const char* benv = getenv("TN_QJMC_BATCH");
-    SvdBatcher* batcher = (!(benv && benv[0] == '0') && nw > 1) ? svd_batcher_create(nw) : nullptr;
+    // The workers are split into groups with one batcher each (default 2 groups from 16 workers on, TN_QJMC_GROUPS): while one group's
+    // round sits in its latency-bound phases (pair EVD, panel Cholesky) the other group's GEMMs fill the SMs -- the only overlap
+    // available to a Jacobi step, whose own phases depend on each other.
+    int ngroups = 1;
+    if (!(benv && benv[0] == '0') && nw > 1) {
+      const char* genv = getenv("TN_QJMC_GROUPS");
+      ngroups = genv ? std::max(1, atoi(genv)) : (nw >= 16 ? 2 : 1);
+      ngroups = std::min(ngroups, nw / 2);
+      ngroups = std::max(ngroups, 1);
+    }
+    std::vector<SvdBatcher*> batchers;
+    if (!(benv && benv[0] == '0') && nw > 1)
+      for (int g = 0; g < ngroups; ++g) batchers.push_back(svd_batcher_create(nw / ngroups + (g < nw % ngroups ? 1 : 0)));
+    std::atomic<int> next_worker{0};
     auto worker = [&]() {
+      const int widx = next_worker.fetch_add(1);
+      SvdBatcher* batcher = batchers.empty() ? nullptr : batchers[widx % ngroups];
       Ctx c;
       Gates* g = nullptr; Mps* psi = nullptr;
       bool attached = false;
@@ -791,9 +806,9 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     std::vector<std::thread> pool;
     for (int k = 0; k < nw; ++k) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
-    if (batcher) {
+    for (SvdBatcher* batcher : batchers) {
       long long probs = 0; const long long rounds = svd_batcher_rounds(batcher, &probs);
-      if (getenv("TN_QJMC_BATCH_STATS")) fprintf(stderr, "{\"qjmc_batching\": {\"workers\": %d, \"rounds\": %lld, \"svds\": %lld}}\n", nw, rounds, probs);
+      if (getenv("TN_QJMC_BATCH_STATS")) fprintf(stderr, "{\"qjmc_batching\": {\"workers\": %d, \"groups\": %d, \"rounds\": %lld, \"svds\": %lld}}\n", nw, ngroups, rounds, probs);
       cudaSetDevice(device);
       svd_batcher_destroy(batcher);
     }

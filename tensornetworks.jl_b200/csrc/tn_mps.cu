@@ -711,20 +711,26 @@ void dmrg_halfsweep(Mps* psi, Env* e, bool direction, Lanczos lz, Trunc tr, doub
 // ================================================================================================
 // Gates (gatelist.jl)
 // ================================================================================================
+void gates_free(Gates* g);
 Gates* gates_create(Ctx* c, int d, int nrows, const int* counts, const int* sites, const int* nsites, const cplx* const* host_gates) {
   auto g = std::make_unique<Gates>();
   g->ctx = c; g->d = d; g->rows.resize(nrows);
   int idx = 0;
-  for (int r = 0; r < nrows; ++r)
-    for (int k = 0; k < counts[r]; ++k, ++idx) {
-      TN_CHECK(nsites[idx] == 1 || nsites[idx] == 2, "only one- and two-site gates are supported");
-      size_t ne = 1; for (int q = 0; q < 2 * nsites[idx]; ++q) ne *= d;
-      Gate gt{sites[idx], nsites[idx], nullptr};
-      TN_CUDA(cudaMalloc((void**)&gt.dev, ne * sizeof(cplx)));
-      TN_CUDA(cudaMemcpyAsync(gt.dev, host_gates[idx], ne * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
-      g->rows[r].push_back(gt);
-    }
-  c->sync();
+  try {
+    for (int r = 0; r < nrows; ++r)
+      for (int k = 0; k < counts[r]; ++k, ++idx) {
+        TN_CHECK(nsites[idx] == 1 || nsites[idx] == 2, "only one- and two-site gates are supported");
+        size_t ne = 1; for (int q = 0; q < 2 * nsites[idx]; ++q) ne *= d;
+        Gate gt{sites[idx], nsites[idx], nullptr};
+        TN_CUDA(cudaMalloc((void**)&gt.dev, ne * sizeof(cplx)));
+        g->rows[r].push_back(gt);                       // owned by the list from here on (freed below if a later gate fails)
+        TN_CUDA(cudaMemcpyAsync(gt.dev, host_gates[idx], ne * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+      }
+    c->sync();
+  } catch (...) {
+    gates_free(g.release());
+    throw;
+  }
   return g.release();
 }
 void gates_free(Gates* g) {

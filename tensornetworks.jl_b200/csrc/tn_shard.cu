@@ -6,7 +6,8 @@
 // Split (even for any MPO bond dimension, as tnb200.sharded.BalancedShardedHeff):
 //   stage 1  device g owns rows [m0, m1) of the fused (a, w) index of L:  T1_g = L_g . Theta          (chi^3 d^2 w / G)
 //   stage 2  T2p(a,s1,s2,[b',w2]) = sum_{w in g,s1',s2'} T1_g W_g   -- partial sums for ALL (b', w2)     (small)
-//   exchange ncclReduceScatter over the fused contraction index k = (b', w2) in equal chunks
+//   exchange ncclReduceScatter over the fused contraction index k = (b', w2) in equal chunks -- Theta's right bond is cut into slices
+//            and the exchange of slice j runs on a communication stream under stage 1 + 2 of slice j + 1 (events, no host sync)
 //   stage 3  out_p = T2_g . R_g[k in chunk g, a']                                                        (chi^3 d^2 w2 / G)
 //   exchange ncclAllReduce(out_p)
 // NCCL is resolved at run time (dlopen "libnccl.so.2"): the library has no link-time dependency on it and reports a clear error
@@ -60,20 +61,24 @@ Nccl& nccl() {
     if (r_ != 0) throw tn::Error(-2, std::string("NCCL error: ") + nccl().GetErrorString(r_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
   } while (0)
 
+struct SlicePart {                       // one slice [b0, b0 + nb) of Theta's right bond on one device
+  cplx *Rg = nullptr, *T2p = nullptr, *T2g = nullptr;
+  cudaEvent_t ev12 = nullptr, evx = nullptr;
+};
 struct DevPart {
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t stream = nullptr, comm = nullptr;   // contractions / collectives
   int mloc = 0, nw = 0, r0 = 0;
-  cplx *Lg = nullptr, *Wg = nullptr, *Rg = nullptr, *theta = nullptr, *T1 = nullptr, *T2p = nullptr, *T2g = nullptr, *out = nullptr;
+  cplx *Lg = nullptr, *Wg = nullptr, *theta = nullptr, *T1 = nullptr, *out = nullptr;
+  std::vector<SlicePart> sl;
 };
 }  // namespace
 
 struct Shard {
   int G = 0;
   int ca, cb, ca2, cb2, d, w, w1, w2;
-  long long c = 0;                     // rows of the fused (b', w2) index per device (reduce_scatter chunk)
   cplx coeff;
+  std::vector<long long> cut, c;       // slices of Theta's right bond: [cut[j], cut[j+1]); c[j] = rows of the fused (b', w2) index of slice j per device
   std::vector<DevPart> parts;
   std::vector<nccl_comm_t> comms;
   ~Shard() {
@@ -81,8 +86,14 @@ struct Shard {
     for (auto& p : parts) {
       cudaSetDevice(p.device);
       if (p.stream) cudaStreamSynchronize(p.stream);
-      for (cplx* q : {p.Lg, p.Wg, p.Rg, p.theta, p.T1, p.T2p, p.T2g, p.out}) if (q) cudaFree(q);
-      if (p.done) cudaEventDestroy(p.done);
+      if (p.comm) cudaStreamSynchronize(p.comm);
+      for (cplx* q : {p.Lg, p.Wg, p.theta, p.T1, p.out}) if (q) cudaFree(q);
+      for (auto& q : p.sl) {
+        for (cplx* b : {q.Rg, q.T2p, q.T2g}) if (b) cudaFree(b);
+        if (q.ev12) cudaEventDestroy(q.ev12);
+        if (q.evx) cudaEventDestroy(q.evx);
+      }
+      if (p.comm) cudaStreamDestroy(p.comm);
       if (p.stream) cudaStreamDestroy(p.stream);
     }
   }
@@ -114,8 +125,14 @@ Shard* shard_create(int G, const int* devices, long long ca, long long ca2, int 
   auto sh = std::make_unique<Shard>();
   sh->G = G; sh->ca = (int)ca; sh->cb = (int)ca; sh->ca2 = (int)ca2; sh->cb2 = (int)ca2; sh->d = d; sh->w = (int)w; sh->w1 = (int)w1; sh->w2 = (int)w2;
   sh->coeff = coeff;
-  const long long d2 = (long long)d * d, mtot = ca * w, ktot = ca2 * w2, cb = ca, cb2 = ca2;
-  sh->c = (ktot + G - 1) / G;
+  const long long d2 = (long long)d * d, mtot = ca * w, cb = ca, cb2 = ca2;
+  // slices of Theta's right bond: the reduce_scatter of slice j runs on the communication stream under stage 1 + 2 of slice j + 1
+  int S = 1;
+  if (G > 1) { const char* e = getenv("TN_SHARD_SLICES"); S = e ? std::max(1, atoi(e)) : std::max(4, G); }
+  S = (int)std::min<long long>(S, cb2);
+  sh->cut.resize(S + 1); sh->c.resize(S);
+  for (int j = 0; j <= S; ++j) sh->cut[j] = cb2 * j / S;
+  for (int j = 0; j < S; ++j) sh->c[j] = ((sh->cut[j + 1] - sh->cut[j]) * w2 + G - 1) / G;
   // W[(w,s1',s2'),(s1,s2,w2)] = sum_{w1} M1(w,s1,s1',w1) M2(w1,s2,s2',w2)  (host, tiny)
   const long long KW = w * d2, NW = d2 * w2;
   std::vector<cplx> Wfull((size_t)(KW * NW));
@@ -139,29 +156,38 @@ Shard* shard_create(int G, const int* devices, long long ca, long long ca2, int 
     cudaDeviceProp prop; TN_CUDA(cudaGetDeviceProperties(&prop, p.device));
     if (prop.major != 10) throw tn::Error(TN_ERR_CUDA, std::string("libtnb200 is built for sm_100a (B200) only; found ") + prop.name);
     TN_CUDA(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
-    TN_CUDA(cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+    TN_CUDA(cudaStreamCreateWithFlags(&p.comm, cudaStreamNonBlocking));
     const long long m0 = mtot * g / G, m1 = mtot * (g + 1) / G;
     p.mloc = (int)(m1 - m0);
     const long long w_first = p.mloc > 0 ? m0 / ca : 0, w_last = p.mloc > 0 ? (m1 - 1) / ca : 0;
     p.nw = (int)(w_last - w_first + 1);
     p.r0 = (int)(m0 - ca * w_first);
-    std::vector<cplx> Lg((size_t)p.mloc * cb), Wg((size_t)p.nw * d2 * NW), Rg((size_t)(sh->c * ca2), cplx{0, 0});
+    std::vector<cplx> Lg((size_t)p.mloc * cb), Wg((size_t)p.nw * d2 * NW);
     for (long long b = 0; b < cb; ++b) for (long long m = 0; m < p.mloc; ++m) Lg[(size_t)(m + p.mloc * b)] = L[(m0 + m) + mtot * b];
     for (long long nn = 0; nn < NW; ++nn)
       for (long long sp = 0; sp < d2; ++sp)
         for (long long wl = 0; wl < p.nw; ++wl) Wg[(size_t)(wl + p.nw * sp + p.nw * d2 * nn)] = Wfull[(size_t)((w_first + wl) + w * sp + KW * nn)];
-    const long long k0 = std::min<long long>(g * sh->c, ktot), k1 = std::min<long long>((g + 1) * sh->c, ktot);
-    for (long long ap = 0; ap < ca2; ++ap)
-      for (long long k = k0; k < k1; ++k) {
-        const long long bp = k % cb2, iw2 = k / cb2;                       // k = b' + cb2 * w2
-        Rg[(size_t)((k - k0) + sh->c * ap)] = R[ap + ca2 * (iw2 + w2 * bp)];
-      }
-    p.Lg = dev_copy(Lg); p.Wg = dev_copy(Wg); p.Rg = dev_copy(Rg);
+    p.Lg = dev_copy(Lg); p.Wg = dev_copy(Wg);
     p.theta = dev_zeros((size_t)(cb * d2 * cb2));
     p.T1 = dev_zeros((size_t)(ca * p.nw * d2 * cb2));                     // rows outside [r0, r0 + mloc) stay zero
-    p.T2p = dev_zeros((size_t)(ca * d2 * sh->c * G));                     // the padding beyond k = ktot stays zero
-    p.T2g = dev_zeros((size_t)(ca * d2 * sh->c));
     p.out = dev_zeros((size_t)(ca * d2 * ca2));
+    p.sl.resize(S);
+    for (int j = 0; j < S; ++j) {
+      SlicePart& q = p.sl[j];
+      const long long b0 = sh->cut[j], nb = sh->cut[j + 1] - b0, ktot = nb * w2, c = sh->c[j];
+      const long long k0 = std::min<long long>(g * c, ktot), k1 = std::min<long long>((g + 1) * c, ktot);
+      std::vector<cplx> Rg((size_t)(c * ca2), cplx{0, 0});
+      for (long long ap = 0; ap < ca2; ++ap)
+        for (long long k = k0; k < k1; ++k) {
+          const long long bl = k % nb, iw2 = k / nb;                        // k = b'_local + nb * w2
+          Rg[(size_t)((k - k0) + c * ap)] = R[ap + ca2 * (iw2 + w2 * (b0 + bl))];
+        }
+      q.Rg = dev_copy(Rg);
+      q.T2p = dev_zeros((size_t)(ca * d2 * c * G));                       // the padding beyond k = ktot stays zero
+      q.T2g = dev_zeros((size_t)(ca * d2 * c));
+      TN_CUDA(cudaEventCreateWithFlags(&q.ev12, cudaEventDisableTiming));
+      TN_CUDA(cudaEventCreateWithFlags(&q.evx, cudaEventDisableTiming));
+    }
   }
   if (G > 1) {
     sh->comms.assign(G, nullptr);
@@ -172,41 +198,61 @@ Shard* shard_create(int G, const int* devices, long long ca, long long ca2, int 
 
 void shard_free(Shard* s) { delete s; }
 
-// theta_host (cb, d, d, cb2) -> out_host (ca, d, d, ca2); both borrowed for the call
+// theta_host (cb, d, d, cb2) -> out_host (ca, d, d, ca2); both borrowed for the call.  Everything is enqueued by this one host thread:
+// per device a contraction stream and a communication stream, ordered by events (no host synchronisation before the end).
 void shard_apply(Shard* sh, const cplx* theta_host, cplx* out_host) {
-  const int G = sh->G;
-  const long long ca = sh->ca, cb = sh->cb, ca2 = sh->ca2, cb2 = sh->cb2, d2 = (long long)sh->d * sh->d, w2 = sh->w2, c = sh->c;
+  const int G = sh->G, S = (int)sh->c.size();
+  const long long ca = sh->ca, cb = sh->cb, ca2 = sh->ca2, cb2 = sh->cb2, d2 = (long long)sh->d * sh->d, w2 = sh->w2;
   const long long n_in = cb * d2 * cb2, n_out = ca * d2 * ca2;
+  auto stage3 = [&](int j) {            // out (+)= coeff sum_k T2g_j[(a,s1,s2), k] Rg_j[k, a']
+    for (int g = 0; g < G; ++g) {
+      DevPart& p = sh->parts[g];
+      TN_CUDA(cudaSetDevice(p.device));
+      if (G > 1) TN_CUDA(cudaStreamWaitEvent(p.stream, p.sl[j].evx, 0));
+      const cplx* T2 = G > 1 ? p.sl[j].T2g : p.sl[j].T2p;
+      zgemm_auto(mk((int)(ca * d2), (int)ca2, (int)sh->c[j], T2, idx1(1), idx1(ca * d2), 0, p.sl[j].Rg, idx1(1), idx1(sh->c[j]), 0,
+                    p.out, idx1(1), idx1(ca * d2), sh->coeff, j == 0 ? cplx{0.0, 0.0} : cplx{1.0, 0.0}), p.stream);
+    }
+  };
   for (int g = 0; g < G; ++g) {
     DevPart& p = sh->parts[g];
     TN_CUDA(cudaSetDevice(p.device));
     TN_CUDA(cudaMemcpyAsync(p.theta, theta_host, (size_t)n_in * sizeof(cplx), cudaMemcpyHostToDevice, p.stream));
-    if (p.mloc > 0) {
-      const long long ld1 = ca * p.nw;
-      // T1[r0 + m, (s1',s2',b')] = L_g[m, b] Theta[b, (s1',s2',b')]
-      zgemm_auto(mk(p.mloc, (int)(d2 * cb2), (int)cb, p.Lg, idx1(1), idx1(p.mloc), 0, p.theta, idx1(1), idx1(cb), 0, p.T1 + p.r0, idx1(1), idx1(ld1)), p.stream);
-      // T2p(a,s1,s2,[b',w2]) = sum_{(w,s1',s2')} T1(a,(w,s1',s2'),b') W_g[(w,s1',s2'),(s1,s2,w2)]
-      zgemm_auto(mk((int)(ca * cb2), (int)(d2 * w2), (int)(p.nw * d2), p.T1, idx2((int)ca, 1, ld1 * d2), idx1(ca), 0, p.Wg, idx1(1), idx1(p.nw * d2), 0,
-                    p.T2p, idx2((int)ca, 1, ca * d2), idx2((int)d2, ca, ca * d2 * cb2)), p.stream);
-    } else {
-      TN_CUDA(cudaMemsetAsync(p.T2p, 0, (size_t)(ca * d2 * c * G) * sizeof(cplx), p.stream));
-    }
   }
-  if (G > 1) {
-    TN_NCCL(nccl().GroupStart());
+  for (int j = 0; j < S; ++j) {
+    const long long b0 = sh->cut[j], nb = sh->cut[j + 1] - b0;
     for (int g = 0; g < G; ++g) {
       DevPart& p = sh->parts[g];
-      TN_NCCL(nccl().ReduceScatter(p.T2p, p.T2g, (size_t)(2 * ca * d2 * c), NCCL_DOUBLE, NCCL_SUM, sh->comms[g], p.stream));
+      SlicePart& q = p.sl[j];
+      TN_CUDA(cudaSetDevice(p.device));
+      if (p.mloc > 0) {
+        const long long ld1 = ca * p.nw;
+        cplx* T1j = p.T1 + ld1 * d2 * b0;
+        // T1[r0 + m, (s1',s2',b')] = L_g[m, b] Theta[b, (s1',s2',b')]   for b' in the slice
+        zgemm_auto(mk(p.mloc, (int)(d2 * nb), (int)cb, p.Lg, idx1(1), idx1(p.mloc), 0, p.theta + cb * d2 * b0, idx1(1), idx1(cb), 0, T1j + p.r0, idx1(1), idx1(ld1)), p.stream);
+        // T2p_j(a,s1,s2,[b',w2]) = sum_{(w,s1',s2')} T1(a,(w,s1',s2'),b') W_g[(w,s1',s2'),(s1,s2,w2)]
+        zgemm_auto(mk((int)(ca * nb), (int)(d2 * w2), (int)(p.nw * d2), T1j, idx2((int)ca, 1, ld1 * d2), idx1(ca), 0, p.Wg, idx1(1), idx1(p.nw * d2), 0,
+                      q.T2p, idx2((int)ca, 1, ca * d2), idx2((int)d2, ca, ca * d2 * nb)), p.stream);
+      } else {
+        TN_CUDA(cudaMemsetAsync(q.T2p, 0, (size_t)(ca * d2 * sh->c[j] * G) * sizeof(cplx), p.stream));
+      }
+      if (G > 1) {
+        TN_CUDA(cudaEventRecord(q.ev12, p.stream));
+        TN_CUDA(cudaStreamWaitEvent(p.comm, q.ev12, 0));
+      }
     }
-    TN_NCCL(nccl().GroupEnd());
+    if (G > 1) {
+      TN_NCCL(nccl().GroupStart());
+      for (int g = 0; g < G; ++g) {
+        DevPart& p = sh->parts[g];
+        TN_NCCL(nccl().ReduceScatter(p.sl[j].T2p, p.sl[j].T2g, (size_t)(2 * ca * d2 * sh->c[j]), NCCL_DOUBLE, NCCL_SUM, sh->comms[g], p.comm));
+      }
+      TN_NCCL(nccl().GroupEnd());
+      for (int g = 0; g < G; ++g) { DevPart& p = sh->parts[g]; TN_CUDA(cudaSetDevice(p.device)); TN_CUDA(cudaEventRecord(p.sl[j].evx, p.comm)); }
+    }
+    if (j >= 1) stage3(j - 1);           // its exchange overlapped stage 1 + 2 of slice j
   }
-  for (int g = 0; g < G; ++g) {
-    DevPart& p = sh->parts[g];
-    TN_CUDA(cudaSetDevice(p.device));
-    const cplx* T2 = G > 1 ? p.T2g : p.T2p;
-    // out[(a,s1,s2), a'] = coeff sum_k T2g[(a,s1,s2), k] R_g[k, a']
-    zgemm_auto(mk((int)(ca * d2), (int)ca2, (int)c, T2, idx1(1), idx1(ca * d2), 0, p.Rg, idx1(1), idx1(c), 0, p.out, idx1(1), idx1(ca * d2), sh->coeff), p.stream);
-  }
+  stage3(S - 1);
   if (G > 1) {
     TN_NCCL(nccl().GroupStart());
     for (int g = 0; g < G; ++g) {
@@ -219,7 +265,7 @@ void shard_apply(Shard* sh, const cplx* theta_host, cplx* out_host) {
   DevPart& p0 = sh->parts[0];
   TN_CUDA(cudaSetDevice(p0.device));
   TN_CUDA(cudaMemcpyAsync(out_host, p0.out, (size_t)n_out * sizeof(cplx), cudaMemcpyDeviceToHost, p0.stream));
-  for (int g = 0; g < G; ++g) { TN_CUDA(cudaSetDevice(sh->parts[g].device)); TN_CUDA(cudaStreamSynchronize(sh->parts[g].stream)); }
+  for (int g = 0; g < G; ++g) { TN_CUDA(cudaSetDevice(sh->parts[g].device)); TN_CUDA(cudaStreamSynchronize(sh->parts[g].stream)); TN_CUDA(cudaStreamSynchronize(sh->parts[g].comm)); }
 }
 
 }  // namespace tn

@@ -57,9 +57,14 @@ def test_null_handles_are_errors_not_crashes():
     calls = [lambda: lib.tn_mps_norm(None, C.byref(v)), lambda: lib.tn_mps_normalize(None), lambda: lib.tn_mps_movecenter(None, 1, tr),
              lambda: lib.tn_env_movecenter(None, 1), lambda: lib.tn_env_calculate(None, C.byref(v)), lambda: lib.tn_envsum_movecenter(None, 1),
              lambda: lib.tn_apply_gates(None, None, tr), lambda: lib.tn_mps_maxbonddim(None, C.byref(k)), lambda: lib.tn_sync(None),
-             lambda: lib.tn_mpo_compress(None, tr)]
+             lambda: lib.tn_mpo_compress(None, tr), lambda: lib.tn_heff_sharded_apply(None, None, None),
+             lambda: lib.tn_svd_trunc_split(None, None, 4, 4, tr, 1, None, None, None, C.byref(k), None, 1, None)]
     for f in calls:
         assert f() == -1
         assert b"null" in lib.tn_last_error()
     # the free functions accept NULL like free()
     assert lib.tn_mps_free(None) == 0 and lib.tn_env_free(None) == 0 and lib.tn_gates_free(None) == 0 and lib.tn_envsum_free(None) == 0
+    assert lib.tn_heff_sharded_free(None) == 0
+    # the sharded matvec validates its device list before touching CUDA
+    h = C.c_void_p()
+    assert lib.tn_heff_sharded_create(0, None, 4, 4, 2, 3, 3, 3, None, None, None, None, _lib.tn_cplx(1.0, 0.0), C.byref(h)) != 0
