@@ -68,6 +68,7 @@ struct GemmDesc {
   int kchunk;
   long long ssC;           // C stride between k-splits (partials are summed by the consumer)
   int swap_raster;         // set by the launcher
+  int panel;               // set by the launcher: width (in tiles) of the raster panels along the fast tile direction, 0 = one panel
   int a_kfast, b_kfast;    // global-load thread mapping: 1 = consecutive threads walk k (k is the unit-stride index)
   const int* skip;         // optional per-batch flags (device): CTAs of a batch with skip[batch] != 0 exit immediately
   int atomic_c;            // split-K contributions are added to C with red.global.add.f64 (ssC = 0, caller zeroes C, beta ignored)

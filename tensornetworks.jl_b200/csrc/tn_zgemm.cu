@@ -15,6 +15,7 @@
 // bank groups on fragment loads.
 #include "tn_common.cuh"
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdlib>
 
@@ -320,6 +321,28 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
   }
 }
 
+// Raster order of the tiles.  Tiles are visited fast-index first; with `panel` > 0 the fast direction is cut into panels of that many
+// tiles and a panel is walked down the whole slow direction before the next one starts.  Why: a wave of ~296 concurrent tiles then
+// covers (296 / panel) x panel tiles, so it touches 296 / panel blocks of the slow-side operand and `panel` blocks of the fast-side
+// operand instead of ~1 and ALL of them -- at the bench shape (M = 40960, N = 8192, K = 2048) the single-panel order streamed the whole
+// 268 MB Theta from DRAM in every one of its 277 waves: ncu measured 83.6 GB of DRAM reads against 1.6 GB of operands
+// (profiles/r02_matvec_stage_metrics.csv).  The launcher picks panel = sqrt(slots * BM / BN) (or BN / BM), the width that minimises
+// the bytes a wave touches, whenever the operands exceed what L2 can hold.
+__device__ __forceinline__ void raster_tile(long long lin, int nfast, int nslow, int panel, int& fast, int& slow) {
+  if (panel <= 0 || panel >= nfast) { fast = (int)(lin % nfast); slow = (int)(lin / nfast); return; }
+  const int full = nfast / panel;
+  const long long span = (long long)panel * nslow;
+  if (lin < (long long)full * span) {
+    const int pnl = (int)(lin / span);
+    const long long rem = lin - (long long)pnl * span;
+    slow = (int)(rem / panel); fast = pnl * panel + (int)(rem % panel);
+  } else {
+    const long long rem = lin - (long long)full * span;
+    const int pl = nfast - full * panel;
+    slow = (int)(rem / pl); fast = full * panel + (int)(rem % pl);
+  }
+}
+
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_kernel(const GemmDesc d) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -330,7 +353,9 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   const int batch = z / d.ksplit, split = z - batch * d.ksplit;
   if (d.skip != nullptr && d.skip[batch] != 0) return;   // e.g. identity rotation of an already converged Jacobi pair
   // raster: consecutive CTAs walk m (default) or n (swap_raster) so that the LARGER operand is streamed from DRAM once
-  const int m_blk = (d.swap_raster ? blockIdx.y : blockIdx.x) * Cfg::BM, n_blk = (d.swap_raster ? blockIdx.x : blockIdx.y) * Cfg::BN;
+  int fast = blockIdx.x, slow = blockIdx.y;
+  if (d.panel > 0) raster_tile((long long)blockIdx.x + (long long)gridDim.x * blockIdx.y, (int)gridDim.x, (int)gridDim.y, d.panel, fast, slow);
+  const int m_blk = (d.swap_raster ? slow : fast) * Cfg::BM, n_blk = (d.swap_raster ? fast : slow) * Cfg::BN;
   const int k_begin = split * d.kchunk;
   const int k_end = min(d.K, k_begin + d.kchunk);
   gemm_tile<WARPS_M, WARPS_N, TM, TN, KMODE>(d, As, Bs, m_blk, n_blk, batch, split, k_begin, k_end, d.atomic_c != 0);
@@ -345,7 +370,7 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
 // nseg > 1 are accumulated with red.global.add.f64.
 // Problems of less than two waves of tiles (operands fit in L2 anyway) instead use one contiguous run of k-tile
 // units per CTA (unit_ctas > 0): fewer, longer runs amortise the pipeline ramp and the atomic epilogue better.
-struct SkPlan { int tiles_fast, dp_tiles, rem_tiles, nseg, kt, unit_ctas; };
+struct SkPlan { int tiles_fast, tiles_slow, dp_tiles, rem_tiles, nseg, kt, unit_ctas; };
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WARPS_N, TM, TN>::value) zgemm_sk_kernel(const GemmDesc d, const SkPlan pl) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -353,7 +378,8 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   cplx* As = reinterpret_cast<cplx*>(smem_raw);
   cplx* Bs = As + Cfg::STAGES * Cfg::A_STAGE;
   auto origin = [&](int tile, int& m_blk, int& n_blk) {
-    int fast = tile % pl.tiles_fast, slow = tile / pl.tiles_fast;
+    int fast, slow;
+    raster_tile(tile, pl.tiles_fast, pl.tiles_slow, d.panel, fast, slow);
     m_blk = (d.swap_raster ? slow : fast) * Cfg::BM;
     n_blk = (d.swap_raster ? fast : slow) * Cfg::BN;
   };
@@ -400,6 +426,16 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
   // Within a wave the CTAs share the operand indexed by the slow raster direction through L2; across waves the other
   // operand is re-read from DRAM.  Stream the operand with more bytes (A: M*K, B: K*N) only once.
   dd.swap_raster = (d.batch * d.ksplit == 1 && (long long)d.M > (long long)d.N && tm <= 65535 && tn_ > 1) ? 1 : 0;
+  dd.panel = 0;
+  if (d.batch * d.ksplit == 1 && 16.0 * ((double)d.M * d.K + (double)d.K * d.N) > 96.0 * 1024 * 1024) {
+    // operands beyond L2: panels along the fast direction (see raster_tile); ~296 CTA slots on a B200
+    const double ratio = dd.swap_raster ? (double)Cfg::BM / Cfg::BN : (double)Cfg::BN / Cfg::BM;
+    const int nfast = dd.swap_raster ? (int)tn_ : (int)tm;
+    static double scale = -1;
+    if (scale < 0) { const char* e = getenv("TN_GEMM_PANEL_SCALE"); scale = e ? atof(e) : 1.0; }
+    const int pw = std::max(1, (int)std::lround(scale * std::sqrt(296.0 * ratio)));
+    if (pw < nfast) dd.panel = pw;
+  }
   if (d.streamk) {
     // stream-K: only when the plain launch would leave a partial last wave (or less than one wave) of CTAs
     static int slots = 0;          // identical B200s: the value of the first device holds for all
@@ -420,6 +456,7 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
     if (eff < 0.94 && KT >= 16 && T < (1ll << 30)) {
       SkPlan pl;
       pl.tiles_fast = dd.swap_raster ? (int)tn_ : (int)tm;
+      pl.tiles_slow = dd.swap_raster ? (int)tm : (int)tn_;
       pl.dp_tiles = (T < 2 * (long long)slots) ? 0 : (int)((T / slots) * slots);   // under two waves: one unit run per CTA
       pl.rem_tiles = (int)(T - pl.dp_tiles);
       pl.kt = KT;
