@@ -106,6 +106,14 @@ int32_t tn_svd_trunc_split(tn_ctx* ctx, const tn_cplx* mat, int64_t m, int64_t n
 int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_t m, int64_t n, tn_trunc_t trunc,
                              tn_cplx* U, double* S, tn_cplx* Vh, int64_t* k_out, int32_t* sweeps_out);
 
+/* One Gram + rotation pass of the blocked Jacobi step on caller data (the two kernels of csrc/tn_jacobi.cu, which the factorisations
+ * above run between the pair eigen-decompositions; exposed so that they can be checked on their own).  Z: rows x ncols column-major
+ * on the host (leading dimension rows), ncols a multiple of 32; pairs: npairs x 2 indices of 32-column blocks (disjoint);
+ * J: npairs column-major 64 x 64 matrices; skip: npairs flags or NULL.  G_out[p] = P_p^H P_p (64 x 64, P_p = the 64 columns of pair p,
+ * evaluated BEFORE the update), Z_out = Z with the columns of every pair p (skip[p] == 0) replaced by P_p J_p. */
+int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
+                            const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out);
+
 /* tuning switch (process-wide): 1 = QR-preconditioned Jacobi (default), 0 = plain Jacobi */
 int32_t tn_svd_set_precond(int32_t mode);
 

@@ -304,6 +304,35 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 
 int32_t tn_svd_set_precond(int32_t mode) { return guard([&] { svd_set_precond(mode); }); }
 
+int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
+                            const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out) {
+  return guard([&] { TN_CHECK(ctx && Z && pairs && J && G_out && Z_out, "tn_jacobi_pair_pass: null pointer"); use_device(ctx);
+    TN_CHECK(rows >= 1 && rows < (1ll << 30) && ncols >= 64 && ncols % 32 == 0 && ncols < (1ll << 24) && npairs >= 1, "tn_jacobi_pair_pass: bad shape");
+    const int nb = (int)(ncols / 32);
+    std::vector<char> seen((size_t)nb, 0);
+    for (int i = 0; i < 2 * npairs; ++i) {
+      TN_CHECK(pairs[i] >= 0 && pairs[i] < nb && !seen[pairs[i]], "tn_jacobi_pair_pass: column blocks must be in range and disjoint");
+      seen[pairs[i]] = 1;
+    }
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    const size_t ze = (size_t)rows * ncols, je = (size_t)npairs * 64 * 64;
+    cplx* dZ = c->scratch[0].get(ze, s);
+    cplx* dJ = c->scratch[1].get(je, s);
+    cplx* dG = c->scratch[2].get(je, s);
+    int* dI = reinterpret_cast<int*>(c->scratch[3].get((size_t)npairs, s));      // 16 B per entry: room for 2 + 1 ints per pair
+    int* dskip = dI + 2 * npairs;
+    TN_CUDA(cudaMemcpyAsync(dZ, Z, ze * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemcpyAsync(dJ, J, je * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemcpyAsync(dI, pairs, (size_t)2 * npairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (skip) TN_CUDA(cudaMemcpyAsync(dskip, skip, (size_t)npairs * sizeof(int), cudaMemcpyHostToDevice, s));
+    jacobi_gram64(dZ, rows, (int)rows, dI, npairs, dG, 32, s);
+    jacobi_rot64(dZ, rows, (int)rows, dI, npairs, dJ, skip ? dskip : nullptr, s);
+    TN_CUDA(cudaMemcpyAsync(G_out, dG, je * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(Z_out, dZ, ze * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+  });
+}
+
 static Idx2 I2(tn_idx2_t i) { return Idx2{(int)std::min<int64_t>(i.n0, 0x7fffffff), (long long)i.s0, (long long)i.s1, nullptr, 0}; }
 
 int32_t tn_contract_strided(tn_ctx* ctx, int64_t M, int64_t N, int64_t K, const tn_cplx* A, int64_t ae, tn_idx2_t am, tn_idx2_t ak, int32_t conjA,

@@ -936,6 +936,209 @@ __global__ void __launch_bounds__(CHOL2_THREADS, 1) chol_inv64b_kernel(const cpl
   }
 }
 
+// ---- register-blocked variant (default) ---------------------------------------------------------------------------------------------
+// Same inputs, outputs and null-column / failed-pivot semantics.  The blocked kernel above still spends ~72 us per call (ncu launch
+// list of a 2048^2 factorisation: 256 calls = 18 of the 52 ms of the QR phase, and half of the QR phase at n = 512): its 16 x 16 diagonal
+// blocks are factorised and inverted by one warp through shared memory, a chain of ~20 k cycles per block.  Here 256 threads own one
+// 4 x 4 block of G each IN REGISTERS (thread (ti, tj): rows 4 ti.., columns 4 tj..).  Per 4 pivots: the diagonal thread factorises its
+// block and inverts the 4 x 4 triangle with fully unrolled register arithmetic (the only sequential part: four rsqrt chains), the
+// threads of the block row form R12 = R11^-H G12 in registers and publish it, every trailing thread applies the rank-4 update to its
+// own registers -- two block barriers per 4 pivots and no shared-memory round trip on the pivot chain.  R^-1 is then assembled by
+// recursive doubling ([A B; 0 C]^-1 = [A^-1, -A^-1 B C^-1; 0, C^-1], block sizes 4, 8, 16, 32) with the whole CTA.
+constexpr int CHOL3_THREADS = 256;
+__global__ void __launch_bounds__(CHOL3_THREADS, 1) chol_inv64c_kernel(const cplx* __restrict__ Gpart, cplx* __restrict__ Rinv_out, cplx* __restrict__ Rtot,
+                                                                       int pass, int last_pass, double shift_factor, int* __restrict__ done_flag) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  cplx (*G)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw);                                    // G, then R in its upper triangle
+  cplx (*Ri)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + sizeof(cplx) * JP * (JP + 1));    // R^-1
+  cplx (*Ro)[JP + 1] = reinterpret_cast<cplx (*)[JP + 1]>(sm_raw + 2 * sizeof(cplx) * JP * (JP + 1)); // scratch / old Rtot
+  __shared__ double red[CHOL3_THREADS / 32];
+  __shared__ int nullcol[JP];
+  __shared__ int rowbad[JP];                          // null column or failed pivot: R(j, :) = e_j
+  __shared__ cplx Pn[4][JP];                          // R12 of the current pivot block, column 4 tj + b stored at tj + 16 b
+  __shared__ cplx X11[4][4];                          // inverse of the current diagonal block
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  Gpart += (long long)blockIdx.x * JP * JP; Rinv_out += (long long)blockIdx.x * JP * JP; Rtot += (long long)blockIdx.x * JP * JP;
+  if (done_flag != nullptr) done_flag += blockIdx.x;
+  if (done_flag != nullptr) {
+    if (pass == 0) { if (tid == 0) *done_flag = 0; }
+    else if (pass == 2 && *done_flag != 0) return;
+  }
+  double fro = 0;
+  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) {
+    const int row = e % JP, col = e / JP;
+    const cplx v = Gpart[e];
+    G[row][col] = v;
+    fro += v.x * v.x + v.y * v.y;
+    Ri[row][col] = make_double2(0, 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) fro += __shfl_xor_sync(0xffffffffu, fro, o);
+  if (lane == 0) red[wrp] = fro;
+  __syncthreads();
+  fro = 0; for (int i = 0; i < CHOL3_THREADS / 32; ++i) fro += red[i];
+  const double shift = pass == 0 ? shift_factor * sqrt(fro) : 0.0;
+  if (tid < JP) nullcol[tid] = (G[tid][tid].x <= 0.0) ? 1 : 0;
+  __syncthreads();
+  double dev = 0;                                        // max |G - I| over the non-null part (second pass only)
+  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) {   // symmetrise + shift
+    const int row = e % JP, col = e / JP;
+    if (row < col) {
+      const cplx a = G[row][col], b = G[col][row];
+      const cplx h = make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+      G[row][col] = h; G[col][row] = make_double2(h.x, -h.y);
+      dev = fmax(dev, fmax(fabs(h.x), fabs(h.y)));
+    } else if (row == col) {
+      if (!nullcol[row]) dev = fmax(dev, fabs(G[row][col].x - 1.0));
+      G[row][col].x += shift; G[row][col].y = 0;
+    }
+  }
+  if (done_flag != nullptr && pass == 1) {
+    for (int o = 16; o > 0; o >>= 1) dev = fmax(dev, __shfl_xor_sync(0xffffffffu, dev, o));
+    __syncthreads();                                     // red[] was read above
+    if (lane == 0) red[wrp] = dev;
+    __syncthreads();
+    dev = 0; for (int i = 0; i < CHOL3_THREADS / 32; ++i) dev = fmax(dev, red[i]);
+    if (dev < 1e-3) { last_pass = 1; if (tid == 0) *done_flag = 1; }
+  }
+  __syncthreads();
+
+  // ---- factorisation: thread (ti, tj) keeps G(4 ti + a, 4 tj + b) in registers (only tj >= ti matters) ----
+  const int ti = tid >> 4, tj = tid & 15;
+  cplx B[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) B[a][b] = G[4 * ti + a][4 * tj + b];
+  __syncthreads();                                       // G is rewritten below (R) while other threads may still be loading
+  for (int kb = 0; kb < JP / 4; ++kb) {
+    if (ti == kb && tj == kb) {
+      // (1) diagonal block: R11 (rows of null / failed pivots become unit rows) and X = R11^-1, all in registers
+      double dinv[4]; bool bad[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const double dd = B[a][a].x;
+        bad[a] = nullcol[4 * kb + a] || !(dd > 0.0) || !isfinite(dd);
+        const double ri = bad[a] ? 0.0 : rsqrt(dd);
+        dinv[a] = bad[a] ? 1.0 : ri;
+        B[a][a] = make_double2(bad[a] ? 1.0 : dd * ri, 0.0);
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) B[a][b] = bad[a] ? make_double2(0, 0) : make_double2(B[a][b].x * ri, B[a][b].y * ri);
+#pragma unroll
+        for (int a2 = a + 1; a2 < 4; ++a2)
+#pragma unroll
+          for (int b2 = a2; b2 < 4; ++b2) {              // G(a2, b2) -= conj(R(a, a2)) R(a, b2)
+            const cplx u = B[a][a2], v = B[a][b2];
+            B[a2][b2].x -= u.x * v.x + u.y * v.y; B[a2][b2].y -= u.x * v.y - u.y * v.x;
+          }
+      }
+      cplx X[4][4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+#pragma unroll
+        for (int a = 3; a >= 0; --a) {
+          if (a > b) { X[a][b] = make_double2(0, 0); continue; }
+          if (a == b) { X[a][b] = make_double2(dinv[a], 0.0); continue; }
+          double xr = 0, xi = 0;
+#pragma unroll
+          for (int k = a + 1; k <= b; ++k) { xr += B[a][k].x * X[k][b].x - B[a][k].y * X[k][b].y; xi += B[a][k].x * X[k][b].y + B[a][k].y * X[k][b].x; }
+          X[a][b] = make_double2(-xr * dinv[a], -xi * dinv[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        rowbad[4 * kb + a] = bad[a] ? 1 : 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          G[4 * kb + a][4 * kb + b] = (b >= a) ? B[a][b] : make_double2(0, 0);
+          Ri[4 * kb + a][4 * kb + b] = X[a][b];
+          X11[a][b] = X[a][b];
+        }
+      }
+    }
+    __syncthreads();
+    if (ti == kb && tj > kb) {
+      // (2) R12 = R11^-H G12: row r = sum_{k <= r} conj(X(k, r)) G12(k, :); rows of null / failed pivots are zero
+      cplx Nw[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool zr = rowbad[4 * kb + r] != 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double xr = 0, xi = 0;
+#pragma unroll
+          for (int k = 0; k <= r; ++k) { const cplx x = X11[k][r]; xr += x.x * B[k][c].x + x.y * B[k][c].y; xi += x.x * B[k][c].y - x.y * B[k][c].x; }
+          Nw[r][c] = zr ? make_double2(0, 0) : make_double2(xr, xi);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { B[r][c] = Nw[r][c]; G[4 * kb + r][4 * tj + c] = Nw[r][c]; Pn[r][tj + 16 * c] = Nw[r][c]; }
+    }
+    __syncthreads();
+    if (ti > kb && tj >= ti) {
+      // (3) trailing update G22 -= R12^H R12 on the thread's own block
+      cplx L[4][4], Rr[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { L[k][a] = Pn[k][ti + 16 * a]; Rr[k][a] = Pn[k][tj + 16 * a]; }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          double xr = 0, xi = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { xr += L[k][a].x * Rr[k][b].x + L[k][a].y * Rr[k][b].y; xi += L[k][a].x * Rr[k][b].y - L[k][a].y * Rr[k][b].x; }
+          B[a][b].x -= xr; B[a][b].y -= xi;
+        }
+    }
+    // no barrier here: step kb + 1 starts in the registers of thread (kb + 1, kb + 1); Pn / X11 are rewritten only after the next barrier
+    // ... except X11 and rowbad, written in (1) of the next step while (2)/(3) of this step never read them after the barrier above
+  }
+  __syncthreads();
+  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) { const int row = e / JP, col = e % JP; if (col < row) G[row][col] = make_double2(0, 0); }
+  __syncthreads();
+  // ---- R^-1 by recursive doubling: the diagonal 4 x 4 blocks are in Ri; merge blocks of size h into 2h ----
+  for (int h = 4; h < JP; h *= 2) {
+    const int nprob = JP / (2 * h);
+    // T = B C^-1 (B = R(rows, cols), C^-1 = Ri(cols, cols) upper triangular)
+    for (int e = tid; e < nprob * h * h; e += CHOL3_THREADS) {
+      const int pb = e / (h * h), r = (e % (h * h)) / h, c = e % h;
+      const int r0 = pb * 2 * h, c0 = r0 + h;
+      double xr = 0, xi = 0;
+      for (int k = 0; k <= c; ++k) { const cplx a = G[r0 + r][c0 + k], b = Ri[c0 + k][c0 + c]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+      Ro[r0 + r][c0 + c] = make_double2(xr, xi);
+    }
+    __syncthreads();
+    // Ri(rows, cols) = -A^-1 T (A^-1 = Ri(rows, rows) upper triangular)
+    for (int e = tid; e < nprob * h * h; e += CHOL3_THREADS) {
+      const int pb = e / (h * h), r = (e % (h * h)) / h, c = e % h;
+      const int r0 = pb * 2 * h, c0 = r0 + h;
+      double xr = 0, xi = 0;
+      for (int k = r; k < h; ++k) { const cplx a = Ri[r0 + r][r0 + k], t = Ro[r0 + k][c0 + c]; xr += a.x * t.x - a.y * t.y; xi += a.x * t.y + a.y * t.x; }
+      Ri[r0 + r][c0 + c] = make_double2(-xr, -xi);
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) { const int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
+  // ---- Rtot <- R * Rtot_old  (pass 0: Rtot = R) ----
+  if (pass != 0) {
+    for (int e = tid; e < JP * JP; e += CHOL3_THREADS) Ro[e % JP][e / JP] = Rtot[e];
+    __syncthreads();
+  }
+  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) {
+    const int col = e % JP, row = e / JP;                // a warp shares the row: uniform loop length, R(row, k) is a broadcast
+    double xr = 0, xi = 0;
+    if (pass == 0) { if (col >= row) { xr = G[row][col].x; xi = G[row][col].y; } }
+    else {
+      for (int k = row; k < JP; ++k) { const cplx a = G[row][k], b = Ro[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+    }
+    if (last_pass && nullcol[row]) { xr = 0; xi = 0; }
+    Rtot[row + (long long)JP * col] = make_double2(xr, xi);
+  }
+}
+
 // dst(c, r) = conj(src(r, c)): dst is cols x rows (ldd), src rows x cols (lds); optional zero fill beyond (rows_valid, cols_valid)
 __global__ void __launch_bounds__(256) conj_transpose_kernel(const cplx* __restrict__ src, long long lds, int rows, int cols,
                                                               cplx* __restrict__ dst, long long ldd) {
@@ -956,11 +1159,16 @@ __global__ void __launch_bounds__(256) set_identity_kernel(cplx* __restrict__ ds
 
 // ---- host driver ------------------------------------------------------------------------------
 
-// Panel Cholesky + inverse over `nb` Gram blocks (TN_SVD_CHOL=1 selects the one-barrier-per-column kernel).
+// Panel Cholesky + inverse over `nb` Gram blocks (TN_SVD_CHOL=1 selects the one-barrier-per-column kernel, 2 the 16-wide blocked one).
 static void launch_chol(int nb, const cplx* Gp, cplx* Rinv, cplx* Rtot, int pass, int last, double shift_factor, int* flag, cudaStream_t s) {
   static int ver = -1;
-  if (ver < 0) { const char* e = getenv("TN_SVD_CHOL"); ver = (e && e[0] == '1') ? 1 : 2; }
-  if (ver == 1) {
+  if (ver < 0) { const char* e = getenv("TN_SVD_CHOL"); ver = (e && e[0] == '1') ? 1 : ((e && e[0] == '2') ? 2 : 3); }
+  if (ver == 3) {
+    static DeviceOnce cfg3;
+    const int smem = 3 * JP * (JP + 1) * (int)sizeof(cplx);
+    cfg3.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64c_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
+    chol_inv64c_kernel<<<nb, CHOL3_THREADS, smem, s>>>(Gp, Rinv, Rtot, pass, last, shift_factor, flag);
+  } else if (ver == 1) {
     static DeviceOnce cfg1;
     const int smem = 2 * JP * (JP + 1) * (int)sizeof(cplx);
     cfg1.run([&] { TN_CUDA(cudaFuncSetAttribute(chol_inv64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); });
@@ -1060,6 +1268,14 @@ static bool wonly_enabled() {
   return v == 1;
 }
 
+// TN_SVD_JGEMM=0 routes the Gram blocks and the pair rotations through the general strided GEMM (tn_zgemm.cu) instead of the
+// dedicated kernels of tn_jacobi.cu (A/B runs).
+static bool jgemm_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_JGEMM"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
 
 // Optional phase timing (TN_SVD_PROFILE=1): CUDA events at the phase boundaries, summed per factorisation and printed
@@ -1091,6 +1307,138 @@ static SvdProf& prof() {
 }
 enum { PH_START = 0, PH_GRAM = 1, PH_EVD = 2, PH_ROT = 3, PH_QR = 4, PH_FIN = 5, PH_MISC = 6 };
 
+// ---- Split schedule ---------------------------------------------------------------------------------------------------------
+// In the circle method every pair of step t+1 takes its two blocks from the two NEIGHBOURING pairs of step t, so groups of pairs put
+// on separate streams advance in lockstep and the pair EVD (a latency chain on ~np SMs, 108 us per step whatever np is) never overlaps
+// the Gram / rotation kernels of another group (measured, < 3 %).  A sweep only has to visit every pair of column blocks once; the
+// recursive order
+//     RR(S)     = RR(S1) || RR(S2),  then BIP(S1, S2)                         (round robin inside a set of blocks)
+//     BIP(A, B) = BIP(A1, B1) || BIP(A2, B2),  then BIP(A1, B2) || BIP(A2, B1)  (every pair between two sets)
+// has the same number of steps when the block count divides evenly, but its concurrent tasks work on DISJOINT blocks for a whole
+// phase (3 phases per sweep for 2 groups, 7 for 4), so their streams drift apart freely: while one group sits in its EVD the others'
+// GEMMs have the machine.  tools/jacobi_sched_emul.py checks the schedule (every pair once, disjoint tasks) and its sweep counts.
+struct SplitSched {
+  struct Task { std::vector<int> step_off, step_np; int slot0 = 0; };   // offsets (in pairs) into the table; first G / J / skip slot
+  struct Phase { std::vector<Task> tasks; };
+  int nb = 0, groups = 1, depth = 0;
+  std::vector<Phase> phases;
+  std::vector<int> host;     // (p, q) of every pair, task after task, step after step
+  int* dev = nullptr;
+};
+namespace {
+typedef std::vector<std::vector<std::pair<int, int>>> Steps;          // one leaf task: steps of disjoint pairs
+typedef std::vector<std::vector<Steps>> Phases;                        // phases of concurrent leaf tasks
+Steps rr_steps(std::vector<int> S) {
+  Steps out;
+  if (S.size() < 2) return out;
+  if (S.size() % 2) S.push_back(-1);                                   // bye
+  const int n = (int)S.size();
+  for (int st = 0; st < n - 1; ++st) {
+    std::vector<std::pair<int, int>> prs;
+    for (int k = 0; k < n / 2; ++k) {
+      int a, b;
+      if (n == 2) { a = 0; b = 1; }
+      else if (k == 0) { a = n - 1; b = st; }
+      else { a = (st + k) % (n - 1); b = (st - k + (n - 1)) % (n - 1); }
+      if (S[a] >= 0 && S[b] >= 0) prs.push_back({std::min(S[a], S[b]), std::max(S[a], S[b])});
+    }
+    out.push_back(prs);
+  }
+  return out;
+}
+Steps bip_steps(std::vector<int> A, std::vector<int> B) {
+  Steps out;
+  if (A.size() > B.size()) std::swap(A, B);
+  if (A.empty()) return out;
+  const int nB = (int)B.size();
+  for (int sft = 0; sft < nB; ++sft) {
+    std::vector<std::pair<int, int>> prs;
+    for (int i = 0; i < (int)A.size(); ++i) { const int q = B[(i + sft) % nB]; prs.push_back({std::min(A[i], q), std::max(A[i], q)}); }
+    out.push_back(prs);
+  }
+  return out;
+}
+Phases par(const Phases& x, const Phases& y) {
+  Phases out;
+  for (size_t i = 0; i < std::max(x.size(), y.size()); ++i) {
+    std::vector<Steps> ph;
+    if (i < x.size()) ph.insert(ph.end(), x[i].begin(), x[i].end());
+    if (i < y.size()) ph.insert(ph.end(), y[i].begin(), y[i].end());
+    out.push_back(ph);
+  }
+  return out;
+}
+Phases cat(Phases x, const Phases& y) { x.insert(x.end(), y.begin(), y.end()); return x; }
+Phases expand_bip(const std::vector<int>& A, const std::vector<int>& B, int c);
+Phases expand_rr(const std::vector<int>& S, int c) {
+  if (c <= 1 || S.size() < 4) { Steps st = rr_steps(S); return st.empty() ? Phases{} : Phases{{st}}; }
+  const size_t h = (S.size() + 1) / 2;
+  const std::vector<int> S1(S.begin(), S.begin() + h), S2(S.begin() + h, S.end());
+  return cat(par(expand_rr(S1, c / 2), expand_rr(S2, c / 2)), expand_bip(S1, S2, c));
+}
+Phases expand_bip(const std::vector<int>& A, const std::vector<int>& B, int c) {
+  if (c <= 1 || std::min(A.size(), B.size()) < 2) { Steps st = bip_steps(A, B); return st.empty() ? Phases{} : Phases{{st}}; }
+  const size_t ha = (A.size() + 1) / 2, hb = (B.size() + 1) / 2;
+  const std::vector<int> A1(A.begin(), A.begin() + ha), A2(A.begin() + ha, A.end()), B1(B.begin(), B.begin() + hb), B2(B.begin() + hb, B.end());
+  return cat(par(expand_bip(A1, B1, c / 2), expand_bip(A2, B2, c / 2)), par(expand_bip(A1, B2, c / 2), expand_bip(A2, B1, c / 2)));
+}
+}  // namespace
+
+// The schedule for nb blocks in `groups` concurrent groups (cached in the workspace); nullptr when it would need more steps than the
+// circle method (block counts that do not halve evenly) or offers no concurrency.
+static SplitSched* split_schedule(SvdWork& w, int nb, int groups, cudaStream_t s) {
+  if (w.split && w.split->nb == nb && w.split->groups == groups) return w.split->phases.empty() ? nullptr : w.split;
+  if (w.split) { if (w.split->dev) cudaFree(w.split->dev); delete w.split; w.split = nullptr; }
+  SplitSched* sc = new SplitSched();
+  sc->nb = nb; sc->groups = groups;
+  w.split = sc;
+  std::vector<int> all(nb);
+  for (int i = 0; i < nb; ++i) all[i] = i;
+  Phases ph = expand_rr(all, groups);
+  int depth = 0; size_t maxtasks = 0;
+  for (auto& p : ph) { size_t d = 0; for (auto& t : p) d = std::max(d, t.size()); depth += (int)d; maxtasks = std::max(maxtasks, p.size()); }
+  if (depth != nb - 1 || maxtasks < 2 || maxtasks > 4) return nullptr;       // phases stays empty: "no split schedule for this nb"
+  for (auto& p : ph) {
+    SplitSched::Phase P;
+    int slot = 0;
+    for (auto& t : p) {
+      SplitSched::Task T;
+      T.slot0 = slot;
+      int mx = 0;
+      for (auto& st : t) {
+        T.step_off.push_back((int)(sc->host.size() / 2)); T.step_np.push_back((int)st.size());
+        for (auto& pq : st) { sc->host.push_back(pq.first); sc->host.push_back(pq.second); }
+        mx = std::max(mx, (int)st.size());
+      }
+      slot += mx;
+      P.tasks.push_back(T);
+    }
+    if (slot > nb / 2) { sc->phases.clear(); sc->host.clear(); return nullptr; }   // would not fit the G / J / skip buffers of a circle-method step
+    sc->phases.push_back(P);
+  }
+  sc->depth = depth;
+  TN_CUDA(cudaMalloc((void**)&sc->dev, sc->host.size() * sizeof(int)));
+  TN_CUDA(cudaMemcpyAsync(sc->dev, sc->host.data(), sc->host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < 3; ++i) if (!w.aux[i]) {
+    TN_CUDA(cudaStreamCreateWithFlags(&w.aux[i], cudaStreamNonBlocking));
+    TN_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
+  }
+  if (!w.ev_fork) TN_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+  return sc;
+}
+// number of concurrent pair groups (TN_SVD_SPLIT; 1 = circle method on one stream) and the smallest block count that is split
+static int split_groups() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_SPLIT"); v = e ? std::max(1, std::min(4, atoi(e))) : 2; }
+  return v;
+}
+static int split_min_blocks() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_SPLIT_MINNB"); v = e ? std::max(4, atoi(e)) : 32; }
+  return v;
+}
+
 // Jacobi sweeps on Z = [W ; V] (W: jrows x ncols_pad, V: ncols_pad x ncols_pad), leading dimension ldz.
 static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   const int nb = w.ncols_pad / JB, np = nb / 2, steps = nb - 1;
@@ -1117,9 +1465,40 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   const int inner_sweeps = (np == 1) ? 12 : 1;
   const int nact = (np == 1) ? std::max(2, std::min(JP, (w.ncols + 1) / 2 * 2)) : JP;
   w.sweeps = 0;
+  SplitSched* sched = (jgemm_enabled() && !prof().on && split_groups() > 1 && nb >= split_min_blocks() && np > 1)
+                          ? split_schedule(w, nb, split_groups(), s) : nullptr;
+  const int rot_rows = jrows + (w.wonly ? 0 : w.ncols_pad);
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
-    for (int st = 0; st < steps; ++st) {
+    if (sched) {
+      for (const auto& ph : sched->phases) {
+        const int nt = (int)ph.tasks.size();
+        size_t depth = 0;
+        for (const auto& t : ph.tasks) depth = std::max(depth, t.step_off.size());
+        if (nt > 1) {
+          TN_CUDA(cudaEventRecord(w.ev_fork, s));
+          for (int t = 1; t < nt; ++t) TN_CUDA(cudaStreamWaitEvent(w.aux[t - 1], w.ev_fork, 0));
+        }
+        for (size_t i = 0; i < depth; ++i)
+          for (int t = 0; t < nt; ++t) {
+            const auto& T = ph.tasks[t];
+            if (i >= T.step_off.size() || T.step_np[i] == 0) continue;
+            cudaStream_t gs = t == 0 ? s : w.aux[t - 1];
+            const int* tb = sched->dev + 2 * (size_t)T.step_off[i];
+            const int npg = T.step_np[i];
+            cplx* Gg = w.Gpart + (size_t)T.slot0 * JP * JP;
+            cplx* Jg = w.J + (size_t)T.slot0 * JP * JP;
+            jacobi_gram64(w.Z, w.ldz, jrows, tb, npg, Gg, std::min(max_split(), 8), gs);
+            launch_evd(npg, Gg, Jg, tol, w.offmax, inner_sweeps, nact, w.skip + T.slot0, gs);
+            jacobi_rot64(w.Z, w.ldz, rot_rows, tb, npg, Jg, w.skip + T.slot0, gs);
+          }
+        for (int t = 1; t < nt; ++t) {
+          TN_CUDA(cudaEventRecord(w.ev_join[t - 1], w.aux[t - 1]));
+          TN_CUDA(cudaStreamWaitEvent(s, w.ev_join[t - 1], 0));
+        }
+      }
+    }
+    for (int st = 0; st < (sched ? 0 : steps); ++st) {
       const int* tb = tab + (size_t)st * np * 2;
       // the pairs [p0, p1) of this step on stream gs: Gram -> EVD -> rotation.  (Splitting a step into pair groups on
       // separate streams, so that the EVD of one group overlaps the GEMMs of another, was measured: < 3 % -- the groups run
@@ -1129,6 +1508,14 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
         Idx2 cols{JB, (long long)w.ldz, colblk, tb + 2 * p0, 2};
         cplx* Gg = w.Gpart + (size_t)p0 * JP * JP;
         cplx* Jg = w.J + (size_t)p0 * JP * JP;
+        if (jgemm_enabled()) {
+          jacobi_gram64(w.Z, w.ldz, jrows, tb + 2 * p0, npg, Gg, max_split(), gs);
+          if (marks) prof().mark(PH_GRAM, gs);
+          launch_evd(npg, Gg, Jg, tol, w.offmax, inner_sweeps, nact, w.skip + p0, gs);
+          if (marks) prof().mark(PH_EVD, gs);
+          jacobi_rot64(w.Z, w.ldz, jrows + (w.wonly ? 0 : w.ncols_pad), tb + 2 * p0, npg, Jg, w.skip + p0, gs);
+          return;
+        }
         GemmDesc g{};
         g.M = JP; g.N = JP; g.K = jrows;
         g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
@@ -1173,6 +1560,39 @@ static void jacobi_sweeps(SvdWork& w, int jrows, cudaStream_t s) {
   }
 }
 
+// Column-block "pairs" of the QR panels for the kernels of tn_jacobi.cu: panel pk of problem b = blocks (b nbk + 2 pk, b nbk + 2 pk + 1);
+// entry ((pk * B + b) * 2) of the table.
+static int* build_panel_table(int B, int nbk, cudaStream_t s) {
+  const int npanels = nbk / 2;
+  std::vector<int> h((size_t)npanels * B * 2);
+  for (int pk = 0; pk < npanels; ++pk)
+    for (int b = 0; b < B; ++b) { h[((size_t)pk * B + b) * 2] = b * nbk + 2 * pk; h[((size_t)pk * B + b) * 2 + 1] = b * nbk + 2 * pk + 1; }
+  int* d = nullptr;
+  TN_CUDA(cudaMalloc((void**)&d, h.size() * sizeof(int)));
+  TN_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  return d;
+}
+
+// Trailing tiles of the QR panels: for panel pk the tiles (b, i), i < npanels - pk - 1, = panel pk + 1 + i of problem b;
+// the entries of panel pk start at offset 2 * B * (pk * npanels - pk * (pk + 1) / 2) ... computed by trail_offset().
+static size_t trail_offset(int B, int npanels, int pk) { return (size_t)2 * B * ((size_t)pk * npanels - (size_t)pk * (pk + 1) / 2); }
+static int* build_trail_table(int B, int nbk, cudaStream_t s) {
+  const int npanels = nbk / 2;
+  std::vector<int> h(trail_offset(B, npanels, npanels > 0 ? npanels - 1 : 0) + 2);
+  for (int pk = 0; pk + 1 < npanels; ++pk) {
+    const int ntl = npanels - pk - 1;
+    int* o = h.data() + trail_offset(B, npanels, pk);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < ntl; ++i) { o[((size_t)b * ntl + i) * 2] = b * nbk + 2 * (pk + 1 + i); o[((size_t)b * ntl + i) * 2 + 1] = b * nbk + 2 * (pk + 1 + i) + 1; }
+  }
+  int* d = nullptr;
+  TN_CUDA(cudaMalloc((void**)&d, h.size() * sizeof(int)));
+  TN_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+  TN_CUDA(cudaStreamSynchronize(s));
+  return d;
+}
+
 static GemmDesc gd(int M, int N, int K, const cplx* A, Idx2 am, Idx2 ak, int conjA, const cplx* B, Idx2 bk, Idx2 bn, int conjB,
                    cplx* C, Idx2 cm, Idx2 cn, double alpha = 1.0, double beta = 0.0) {
   GemmDesc g{};
@@ -1194,12 +1614,29 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
   cplx* Rinv = w.small; cplx* Rtot = w.small + JP * JP;
   const double shift_factor = 11.0 * ((double)rows * JP + (double)JP * (JP + 1)) * 2.220446049250313e-16;
   const int npanels = npad / JP;
+  const int* ptab = nullptr; const int* ttab = nullptr;
+  if (jgemm_enabled()) {
+    const int key = 1000000 + npad / JB;
+    auto itb = w.tables.find(key);
+    if (itb == w.tables.end()) itb = w.tables.emplace(key, build_panel_table(1, npad / JB, s)).first;
+    ptab = itb->second;
+    const int key2 = 2000000 + npad / JB;
+    auto itt = w.tables.find(key2);
+    if (itt == w.tables.end()) itt = w.tables.emplace(key2, build_trail_table(1, npad / JB, s)).first;
+    ttab = itt->second;
+  }
   for (int pk = 0; pk < npanels; ++pk) {
     cplx* P = Q + (long long)pk * JP * ldq;
     for (int it = 0; it < chol_passes; ++it) {
-      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
       // third pass of CholeskyQR3: skipped on the device when the second pass found the panel already orthonormal to 1e-3
       const int* skip3 = (chol_passes == 3 && it == 2) ? w.cflag : nullptr;
+      if (ptab) {
+        jacobi_gram64(Q, ldq, rows, ptab + 2 * pk, 1, w.Gpart, std::min(32, max_split()), s, skip3);
+        launch_chol(1, w.Gpart, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0, chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr, s);
+        jacobi_rot64(Q, ldq, rows, ptab + 2 * pk, 1, Rinv, skip3, s);
+        continue;
+      }
+      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
       g.skip = skip3;
       if (g.atomic_c) TN_CUDA(cudaMemsetAsync(w.Gpart, 0, (size_t)JP * JP * sizeof(cplx), s));
@@ -1227,7 +1664,8 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
       zgemm_auto(c, s);
       // T <- T - P C
-      zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
+      if (ttab) jacobi_update64(Q, ldq, ptab + 2 * pk, Q, ldq, rows, ttab + trail_offset(1, npanels, pk), 1, nt / JP, Rrow, npad, 0, s);
+      else zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
     }
   }
 }
@@ -1514,6 +1952,9 @@ void svd_free(SvdWork& w) {
   if (w.offmax) { cudaFree(w.offmax); cudaFree(w.kout); cudaFree(w.small); cudaFree(w.cflag); }
   for (cplx* p : {w.Q1, w.Q2, w.Ra, w.Rb, w.Rc, w.Tg, w.R1}) if (p) cudaFree(p);
   for (auto& kv : w.tables) cudaFree(kv.second);
+  if (w.split) { if (w.split->dev) cudaFree(w.split->dev); delete w.split; }
+  for (int i = 0; i < 3; ++i) { if (w.aux[i]) cudaStreamDestroy(w.aux[i]); if (w.ev_join[i]) cudaEventDestroy(w.ev_join[i]); }
+  if (w.ev_fork) cudaEventDestroy(w.ev_fork);
   delete w.bview;
   w = SvdWork{};
 }
@@ -1600,6 +2041,16 @@ double svd_dist_step(SvdWork& w, const int* pairs_host, int npairs, cudaStream_t
   const long long colblk = (long long)JB * w.ldz;
   TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
   Idx2 cols{JB, (long long)w.ldz, colblk, w.dtab, 2};
+  if (jgemm_enabled()) {
+    jacobi_gram64(w.Z, w.ldz, jrows, w.dtab, npairs, w.Gpart, max_split(), s);
+    launch_evd(npairs, w.Gpart, w.J, tol, w.offmax, 1, JP, w.skip, s);
+    jacobi_rot64(w.Z, w.ldz, jrows + w.ncols_pad, w.dtab, npairs, w.J, w.skip, s);
+    unsigned long long bits0 = 0;
+    TN_CUDA(cudaMemcpyAsync(&bits0, w.offmax, 8, cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaStreamSynchronize(s));
+    double off0; std::memcpy(&off0, &bits0, 8);
+    return off0;
+  }
   GemmDesc g{};
   g.M = JP; g.N = JP; g.K = jrows;
   g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
@@ -1696,6 +2147,13 @@ static void jacobi_sweeps_b(SvdBatch& w, int jrows, cudaStream_t s) {
     TN_CUDA(cudaMemsetAsync(w.offmax, 0, 8, s));
     for (int st = 0; st < steps; ++st) {
       Idx2 cols{JB, (long long)w.ldz, colblk, tab + (size_t)st * npg * 2, 2};
+      if (jgemm_enabled() && npg <= 65535) {
+        const int* tb = tab + (size_t)st * npg * 2;
+        jacobi_gram64(w.Z, w.ldz, jrows, tb, npg, w.Gpart, max_split(), s);
+        launch_evd(npg, w.Gpart, w.J, tol, w.offmax, inner_sweeps, nact, w.skip, s);
+        jacobi_rot64(w.Z, w.ldz, jrows + (w.wonly ? 0 : w.npad), tb, npg, w.J, w.skip, s);
+        continue;
+      }
       GemmDesc g{};
       g.M = JP; g.N = JP; g.K = jrows;
       g.A = w.Z; g.am = cols; g.ak = idx1(1); g.conjA = 1;
@@ -1741,11 +2199,29 @@ static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, 
   cplx* Rinv = w.small; cplx* Rtot = w.small + (size_t)B * gs;
   const double shift_factor = 11.0 * ((double)rows * JP + (double)JP * (JP + 1)) * 2.220446049250313e-16;
   const int npanels = npad / JP;
+  const int* ptab = nullptr; const int* ttab = nullptr;
+  if (jgemm_enabled() && B <= 65535) {
+    const auto key = std::make_pair(-B, npad / JB);
+    auto itb = w.tables.find(key);
+    if (itb == w.tables.end()) itb = w.tables.emplace(key, build_panel_table(B, npad / JB, s)).first;
+    ptab = itb->second;
+    const auto key2 = std::make_pair(-B - 100000, npad / JB);
+    auto itt = w.tables.find(key2);
+    if (itt == w.tables.end()) itt = w.tables.emplace(key2, build_trail_table(B, npad / JB, s)).first;
+    ttab = itt->second;
+  }
   for (int pk = 0; pk < npanels; ++pk) {
     cplx* P = Q + (long long)pk * JP * ldq;
     for (int it = 0; it < chol_passes; ++it) {
-      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
       const int* skip3 = (chol_passes == 3 && it == 2) ? w.cflag : nullptr;     // per problem: third CholeskyQR pass not needed
+      if (ptab) {
+        const int* tb = ptab + (size_t)pk * B * 2;
+        jacobi_gram64(Q, ldq, rows, tb, B, w.Gpart, std::min(32, max_split()), s, skip3);
+        launch_chol(B, w.Gpart, Rinv, Rtot, it, it == chol_passes - 1 ? 1 : 0, chol_passes == 3 ? shift_factor : 0.0, chol_passes == 3 ? w.cflag : nullptr, s);
+        jacobi_rot64(Q, ldq, rows, tb, B, Rinv, skip3, s);
+        continue;
+      }
+      GemmDesc g = gd(JP, JP, rows, P, idx1(ldq), idx1(1), 1, P, idx1(1), idx1(ldq), 0, w.Gpart, idx1(1), idx1(JP));
       g.batch = B; g.bsA = qs; g.bsB = qs; g.bsC = gs;
       g.ksplit = ksplit; g.kchunk = kchunk; g.ssC = 0; g.atomic_c = ksplit > 1 ? 1 : 0;
       g.skip = skip3;
@@ -1771,9 +2247,13 @@ static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, 
       c.batch = B; c.bsA = qs; c.bsB = qs; c.bsC = rs;
       c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
       zgemm_auto(c, s);
-      GemmDesc u = gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0);
-      u.batch = B; u.bsA = qs; u.bsB = rs; u.bsC = qs;
-      zgemm_auto(u, s);
+      if (ttab && (long long)B * (nt / JP) <= 65535) {
+        jacobi_update64(Q, ldq, ptab + (size_t)pk * B * 2, Q, ldq, rows, ttab + trail_offset(B, npanels, pk), B, nt / JP, Rrow, npad, rs, s);
+      } else {
+        GemmDesc u = gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0);
+        u.batch = B; u.bsA = qs; u.bsB = rs; u.bsC = qs;
+        zgemm_auto(u, s);
+      }
     }
   }
 }

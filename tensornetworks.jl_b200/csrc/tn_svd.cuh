@@ -21,6 +21,10 @@ struct SvdWork {
   int* cflag = nullptr;                            // CholeskyQR3 early-termination flag of the current panel
   int* kout = nullptr;                             // device-side truncation rank
   std::map<int, int*> tables;                      // round-robin pair tables per block count
+  // split pair schedule (tn_svd.cu, "Split schedule"): steps that fall apart into independent groups on auxiliary streams
+  struct SplitSched* split = nullptr;
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   // QR preconditioner (two GEMM-based QR factorisations: A = Q1 R1, R1^H = Q2 R2, Jacobi on X = R2^H)
   cplx* Q1 = nullptr; size_t Q1_cap = 0;           // rows x ncols_pad
   cplx* Q2 = nullptr; size_t Q2_cap = 0;           // ncols_pad x ncols_pad
@@ -114,6 +118,14 @@ void svd_batcher_destroy(SvdBatcher* b);
 void svd_batcher_attach(SvdBatcher* b);            // the calling thread's svd_factor calls join the rounds from now on
 void svd_batcher_detach(cudaStream_t s);           // the calling thread leaves (may complete a round on stream s)
 long long svd_batcher_rounds(SvdBatcher* b, long long* problems);
+// tn_jacobi.cu: the Gram block G_p = P_p^H P_p and the in-place rotation Z(:, pair p) <- Z(:, pair p) J_p of column-block pairs
+// (tab: 2 block indices per pair, 32 columns per block) as dedicated kernels
+void jacobi_gram64(const cplx* Z, long long ldz, int rows, const int* tab, int npairs, cplx* G, int max_split, cudaStream_t s, const int* skip = nullptr);
+void jacobi_rot64(cplx* Z, long long ldz, int rows, const int* tab, int npairs, const cplx* J, const int* skip, cudaStream_t s);
+// T_b(:, tile i) -= P_b * C_b(:, tile i): the rank-64 trailing updates of the block Gram-Schmidt QR (P_b = column blocks ptab[2b], ptab[2b+1] of A;
+// tile (b, i) = column blocks ttab[2 (b ntiles + i)], .. + 1 of T; C_b = C + cstride b, 64 x 64 ntiles coefficients, leading dimension ldc)
+void jacobi_update64(const cplx* A, long long lda, const int* ptab, cplx* T, long long ldt, int rows, const int* ttab, int nprob, int ntiles,
+                     const cplx* C, long long ldc, long long cstride, cudaStream_t s);
 void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn

@@ -131,3 +131,38 @@ def test_split_factorisation_matches_lapack(m, n, side):
         # the weighted factor carries the singular values: its Gram matrix is diag(S^2)
         wf = B if side == 1 else A.conj().T
         assert np.linalg.norm(wf @ wf.conj().T - np.diag(S ** 2)) <= 1e-11 * so[0] ** 2 * np.sqrt(k)
+
+
+@pytest.mark.parametrize("rows,ncols,npairs,with_skip", [(64, 64, 1, False), (200, 128, 2, False), (512, 512, 8, True), (1030, 256, 3, True),
+                                                          (2048, 2048, 32, False)])
+def test_jacobi_pair_kernels_match_numpy(rows, ncols, npairs, with_skip):
+    """The Gram-block and in-place rotation kernels of the Jacobi step (csrc/tn_jacobi.cu) on their own: G_p = P_p^H P_p (full
+    Hermitian block: only the upper 8x8 tiles are computed, the mirror image is written by the epilogue) and Z(:, pair) <- Z(:, pair) J_p
+    over a multi-row-block cp.async ring, for row counts that are / are not multiples of the 64-row block and the 16-row k-tile."""
+    import ctypes as C
+    import tnb200
+    from tnb200.api import _ptr, _f, check
+    rng = np.random.default_rng(rows + ncols)
+    ctx = tnb200.Context.default()
+    Z = _f(crandn(rng, rows, ncols))
+    nb = ncols // 32
+    blocks = rng.permutation(nb)[:2 * npairs].astype(np.int32)
+    pairs = np.ascontiguousarray(blocks.reshape(npairs, 2))
+    J = np.stack([_f(crandn(rng, 64, 64)) for _ in range(npairs)])          # any matrix: the kernel is a plain product
+    Jflat = np.concatenate([j.reshape(-1, order='F') for j in J])
+    skip = (rng.integers(0, 2, npairs).astype(np.int32) if with_skip else None)
+    G = np.zeros(npairs * 64 * 64, dtype=np.complex128)
+    Zout = np.zeros((rows, ncols), dtype=np.complex128, order='F')
+    check(ctx.lib.tn_jacobi_pair_pass(ctx.h, _ptr(Z), rows, ncols, pairs.ctypes.data_as(C.c_void_p), npairs, _ptr(Jflat),
+                                      skip.ctypes.data_as(C.c_void_p) if skip is not None else None, _ptr(G), _ptr(Zout)))
+    want = Z.copy()
+    for p in range(npairs):
+        cols = np.concatenate([np.arange(32) + 32 * pairs[p, 0], np.arange(32) + 32 * pairs[p, 1]])
+        P = Z[:, cols]
+        Gp = np.reshape(G[p * 4096:(p + 1) * 4096], (64, 64), order='F')
+        ref = P.conj().T @ P
+        assert np.linalg.norm(Gp - ref) <= 1e-13 * np.linalg.norm(ref), (p, "gram")
+        assert np.linalg.norm(Gp - Gp.conj().T) == 0.0 or np.linalg.norm(Gp - Gp.conj().T) <= 1e-15 * np.linalg.norm(ref)
+        if skip is None or skip[p] == 0:
+            want[:, cols] = P @ J[p]
+    assert np.linalg.norm(Zout - want) <= 1e-13 * np.linalg.norm(want)
