@@ -92,3 +92,32 @@ def test_truncated_svd_properties_at_c2_size():
         r = svd_properties(svd_fn, 2048, np.random.default_rng(1), **kw)
         assert r["rank_ok"] and r["sorted_ok"], r
         assert r["sv_err"] < 5e-12 and r["orthU"] < 1e-11 and r["orthV"] < 1e-11 and r["recon"] < 1e-11, r
+
+
+def test_dmrg_chi4096_on_the_4x6_j1j2_cylinder_reproduces_exact_diagonalisation():
+    """BASELINE config 5 / the north-star target at the size where the answer is known.  Two-site DMRG (cutoff = 0) of the J1-J2 model on
+    a 4 x 6 cylinder (N = 24, MPO bond 20) with maxdim ramped 64 -> 4096: the central bond of a 24-site chain is exact at 2^12, so the
+    energy has to reproduce exact diagonalisation in the S^z = 0 sector (tools/ed_j1j2.py: bit manipulation + ARPACK, no MPS code;
+    -47.290880085317, itself checked against the 12-site full-space values of tests/models.py).  The central bond of the last passes is
+    bench.py's headline workload: Theta (2048, 2, 2, 2048), w = 20, followed by a 4096 x 4096 factorisation kept at rank 4096.
+    Tolerance 1e-10 relative (north_star); measured 7e-13 (profiles/r02b_c5_exact_4x6_chi4096.jsonl)."""
+    import ctypes as C
+    import tnb200
+    from tnb200.mpo import MPO
+    from tnb200._lib import check, tn_lanczos_t
+    e_ed = -47.290880085317
+    ctx = tnb200.Context.default()
+    N = 24
+    gH = MPO(N, 2, tnb200.models.j1j2_cylinder_terms(4, 6), ctx=ctx)
+    g = tnb200.GMPS(1, 2, tnb200.models.random_canonical_mps(N, 2, 16, seed=7), 1)
+    g.movecenter(1)
+    Hs = tnb200.ProjMPS(g, gH, g, center=1)
+    direction, energy, maxbond = False, None, 0
+    for chi, passes in ((64, 4), (256, 2), (1024, 2), (2048, 2), (4096, 1)):
+        for _ in range(passes):
+            e, mb = C.c_double(), C.c_int64()
+            check(g.lib.tn_dmrg_sweep(g.h, Hs.h, int(direction), tn_lanczos_t(3, 2, 1e-14), tnb200.Trunc(0.0, chi, 1), C.byref(e), C.byref(mb)))
+            direction = not direction
+            energy, maxbond = e.value, mb.value
+    assert maxbond == 4096
+    assert abs(energy - e_ed) <= 1e-10 * abs(e_ed), (energy, e_ed)
