@@ -1100,42 +1100,76 @@ __global__ void __launch_bounds__(CHOL3_THREADS, 1) chol_inv64c_kernel(const cpl
   for (int e = tid; e < JP * JP; e += CHOL3_THREADS) { const int row = e / JP, col = e % JP; if (col < row) G[row][col] = make_double2(0, 0); }
   __syncthreads();
   // ---- R^-1 by recursive doubling: the diagonal 4 x 4 blocks are in Ri; merge blocks of size h into 2h ----
+  // A dependent FP64 operation costs ~50 cycles on this part and the CTA has two warps per scheduler, so every dot product below runs
+  // four output columns x two k-phases = 16 independent accumulation chains per thread (a task = one row, four consecutive columns).
   for (int h = 4; h < JP; h *= 2) {
-    const int nprob = JP / (2 * h);
-    // T = B C^-1 (B = R(rows, cols), C^-1 = Ri(cols, cols) upper triangular)
-    for (int e = tid; e < nprob * h * h; e += CHOL3_THREADS) {
-      const int pb = e / (h * h), r = (e % (h * h)) / h, c = e % h;
+    const int nprob = JP / (2 * h), q4 = h / 4;
+    // T = B C^-1 (B = R(rows, cols), C^-1 = Ri(cols, cols) upper triangular: its lower triangle holds zeros)
+    for (int e = tid; e < nprob * h * q4; e += CHOL3_THREADS) {
+      const int pb = e / (h * q4), r = (e % (h * q4)) / q4, c = 4 * (e % q4);
       const int r0 = pb * 2 * h, c0 = r0 + h;
-      double xr = 0, xi = 0;
-      for (int k = 0; k <= c; ++k) { const cplx a = G[r0 + r][c0 + k], b = Ri[c0 + k][c0 + c]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
-      Ro[r0 + r][c0 + c] = make_double2(xr, xi);
+      double xr[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, xi[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      for (int k = 0; k <= c + 3; k += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          if (k + ph > c + 3) continue;
+          const cplx a = G[r0 + r][c0 + k + ph];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const cplx b = Ri[c0 + k + ph][c0 + c + j]; xr[ph][j] += a.x * b.x - a.y * b.y; xi[ph][j] += a.x * b.y + a.y * b.x; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ro[r0 + r][c0 + c + j] = make_double2(xr[0][j] + xr[1][j], xi[0][j] + xi[1][j]);
     }
     __syncthreads();
     // Ri(rows, cols) = -A^-1 T (A^-1 = Ri(rows, rows) upper triangular)
-    for (int e = tid; e < nprob * h * h; e += CHOL3_THREADS) {
-      const int pb = e / (h * h), r = (e % (h * h)) / h, c = e % h;
+    for (int e = tid; e < nprob * h * q4; e += CHOL3_THREADS) {
+      const int pb = e / (h * q4), r = (e % (h * q4)) / q4, c = 4 * (e % q4);
       const int r0 = pb * 2 * h, c0 = r0 + h;
-      double xr = 0, xi = 0;
-      for (int k = r; k < h; ++k) { const cplx a = Ri[r0 + r][r0 + k], t = Ro[r0 + k][c0 + c]; xr += a.x * t.x - a.y * t.y; xi += a.x * t.y + a.y * t.x; }
-      Ri[r0 + r][c0 + c] = make_double2(-xr, -xi);
+      double xr[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, xi[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+      for (int k = r; k < h; k += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          if (k + ph >= h) continue;
+          const cplx a = Ri[r0 + r][r0 + k + ph];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const cplx t = Ro[r0 + k + ph][c0 + c + j]; xr[ph][j] += a.x * t.x - a.y * t.y; xi[ph][j] += a.x * t.y + a.y * t.x; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Ri[r0 + r][c0 + c + j] = make_double2(-(xr[0][j] + xr[1][j]), -(xi[0][j] + xi[1][j]));
     }
     __syncthreads();
   }
   for (int e = tid; e < JP * JP; e += CHOL3_THREADS) { const int row = e % JP, col = e / JP; Rinv_out[e] = Ri[row][col]; }
-  // ---- Rtot <- R * Rtot_old  (pass 0: Rtot = R) ----
+  // ---- Rtot <- R * Rtot_old  (pass 0: Rtot = R); both factors are upper triangular: k runs over [row, col] only ----
   if (pass != 0) {
     for (int e = tid; e < JP * JP; e += CHOL3_THREADS) Ro[e % JP][e / JP] = Rtot[e];
     __syncthreads();
   }
-  for (int e = tid; e < JP * JP; e += CHOL3_THREADS) {
-    const int col = e % JP, row = e / JP;                // a warp shares the row: uniform loop length, R(row, k) is a broadcast
-    double xr = 0, xi = 0;
-    if (pass == 0) { if (col >= row) { xr = G[row][col].x; xi = G[row][col].y; } }
-    else {
-      for (int k = row; k < JP; ++k) { const cplx a = G[row][k], b = Ro[k][col]; xr += a.x * b.x - a.y * b.y; xi += a.x * b.y + a.y * b.x; }
+  for (int e = tid; e < JP * (JP / 4); e += CHOL3_THREADS) {
+    const int row = e / (JP / 4), col = 4 * (e % (JP / 4));
+    double xr[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, xi[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    if (pass == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) if (col + j >= row) { xr[0][j] = G[row][col + j].x; xi[0][j] = G[row][col + j].y; }
+    } else if (col + 3 >= row) {
+      for (int k = row; k <= col + 3; k += 2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          if (k + ph > col + 3) continue;
+          const cplx a = G[row][k + ph];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const cplx b = Ro[k + ph][col + j]; xr[ph][j] += a.x * b.x - a.y * b.y; xi[ph][j] += a.x * b.y + a.y * b.x; }
+        }
+      }
     }
-    if (last_pass && nullcol[row]) { xr = 0; xi = 0; }
-    Rtot[row + (long long)JP * col] = make_double2(xr, xi);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double vr = xr[0][j] + xr[1][j], vi = xi[0][j] + xi[1][j];
+      if (last_pass && nullcol[row]) { vr = 0; vi = 0; }
+      Rtot[row + (long long)JP * (col + j)] = make_double2(vr, vi);
+    }
   }
 }
 
@@ -1430,7 +1464,7 @@ static SplitSched* split_schedule(SvdWork& w, int nb, int groups, cudaStream_t s
 // number of concurrent pair groups (TN_SVD_SPLIT; 1 = circle method on one stream) and the smallest block count that is split
 static int split_groups() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("TN_SVD_SPLIT"); v = e ? std::max(1, std::min(4, atoi(e))) : 2; }
+  if (v < 0) { const char* e = getenv("TN_SVD_SPLIT"); v = e ? std::max(1, std::min(4, atoi(e))) : 4; }
   return v;
 }
 static int split_min_blocks() {
