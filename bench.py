@@ -265,7 +265,7 @@ def c5_exact_sample(ctx, chi_max=4096):
     e_ed = -47.290880085317
     N = 24
     gH = MPO(N, 2, tnb200.models.j1j2_cylinder_terms(4, 6), ctx=ctx)
-    g = tnb200.GMPS(1, 2, tnb200.models.random_canonical_mps(N, 2, 16, seed=7), 1)
+    g = tnb200.GMPS(1, 2, tnb200.models.random_canonical_mps(N, 2, 16, seed=7), 1, ctx=ctx)
     g.movecenter(1)
     Hs = tnb200.ProjMPS(g, gH, g, center=1)
     direction, out = False, []

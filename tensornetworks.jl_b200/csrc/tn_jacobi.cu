@@ -151,6 +151,109 @@ __global__ void __launch_bounds__(G_THREADS, 3) jacobi_gram64_kernel(const cplx*
   }
 }
 
+// ---- C = P^H T (projection coefficients of the block Gram-Schmidt QR) ---------------------------------------------------------
+constexpr int X_BK = 8, X_LD = 2 * JP + 2, X_STAGES = 4, X_THREADS = 128;
+constexpr int X_STAGE = X_BK * X_LD;
+constexpr int X_SMEM = X_STAGES * X_STAGE * 16;         // 66 560 B -> three CTAs per SM
+
+// grid = (k-splits, items), item = (problem b, tile i) = b * ntiles + i.  C_b(:, tile i) (+)= P_b^H T_b(:, tile i) over the rows of the split:
+// P_b = column blocks atab[2 b], atab[2 b + 1] of A; the tile = column blocks ttab[2 item], ttab[2 item + 1] of T; the 64 x 64 result goes to
+// C + cstride b + 64 ldc i with leading dimension ldc.  A stage holds the k-tile of the panel (columns 0..63) next to that of the tile (64..127);
+// warp w owns the row groups 2w, 2w + 1 of the result and all eight column groups.
+__global__ void __launch_bounds__(X_THREADS, 3) jacobi_cross64_kernel(const cplx* __restrict__ A, long long lda, const int* __restrict__ atab,
+                                                                      const cplx* __restrict__ T, long long ldt, int rows, int kchunk,
+                                                                      const int* __restrict__ ttab, int ntiles, cplx* __restrict__ C, long long ldc,
+                                                                      long long cstride, int atomic) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* Ps = reinterpret_cast<cplx*>(smem_raw);
+  const int item = blockIdx.y, prob = item / ntiles, tile = item - prob * ntiles;
+  const int k_begin = blockIdx.x * kchunk, k_end = min(rows, k_begin + kchunk);
+  if (k_begin >= k_end) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  // load slots: row lk of the k-tile, columns lc + 16 i of the 128-column stage (i < 4: panel, i >= 4: tile)
+  const int lk = tid & 7, lc = tid >> 3;
+  const cplx* sa[2]; const cplx* st[2];             // column lc of the two panel blocks / the two tile blocks; columns lc + 16 follow at 16 ld
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    sa[b] = A + ((long long)atab[2 * prob + b] * JB + lc) * lda + k_begin + lk;
+    st[b] = T + ((long long)ttab[2 * item + b] * JB + lc) * ldt + k_begin + lk;
+  }
+  int krow = k_begin + lk;
+  auto load_stage = [&](int stage) {
+    cplx* ps = Ps + stage * X_STAGE + lk * X_LD + lc;
+    const bool p = krow < k_end;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      cpa16(ps + 32 * b, p ? sa[b] : A, p);
+      cpa16(ps + 32 * b + 16, p ? sa[b] + 16 * lda : A, p);
+      cpa16(ps + JP + 32 * b, p ? st[b] : A, p);
+      cpa16(ps + JP + 32 * b + 16, p ? st[b] + 16 * ldt : A, p);
+      sa[b] += X_BK; st[b] += X_BK;
+    }
+    krow += X_BK;
+  };
+  double re[2][8][2], im[2][8][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { re[i][j][0] = re[i][j][1] = 0.0; im[i][j][0] = im[i][j][1] = 0.0; }
+  const int ktiles = (k_end - k_begin + X_BK - 1) / X_BK;
+#pragma unroll
+  for (int s = 0; s < X_STAGES - 1; ++s) {
+    if (s < ktiles) load_stage(s);
+    cpa_commit();
+  }
+  const int a_frag = warp * 16 + g, b_frag = JP + g;
+  for (int kt = 0; kt < ktiles; ++kt) {
+    cpa_wait<X_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + X_STAGES - 1;
+      if (nk < ktiles) load_stage(nk % X_STAGES);
+      cpa_commit();
+    }
+    const cplx* ps = Ps + (kt % X_STAGES) * X_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < X_BK; kk += 4) {
+      const cplx* row = ps + (kk + t) * X_LD;
+      double ar[2], ai[2], nai[2], br[8], bi[8];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) { cplx v = row[a_frag + 8 * i]; ar[i] = v.x; ai[i] = v.y; nai[i] = -v.y; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { cplx v = row[b_frag + 8 * j]; br[j] = v.x; bi[j] = v.y; }
+      // C_ij += conj(a) b :  re += ar br + ai bi,  im += ar bi - ai br
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma2(re[i][j], ar[i], br[j]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma2(im[i][j], ar[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma2(re[i][j], ai[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma2(im[i][j], nai[i], br[j]);
+    }
+  }
+  cpa_wait<0>();
+  cplx* Cp = C + cstride * prob + (long long)JP * ldc * tile;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        cplx* p = Cp + (warp * 16 + i * 8 + g) + ldc * (j * 8 + 2 * t + q);
+        if (atomic) { atomicAdd(&p->x, re[i][j][q]); atomicAdd(&p->y, im[i][j][q]); }
+        else *p = make_double2(re[i][j][q], im[i][j][q]);
+      }
+}
+
 // ---- Z(:, pair) <- Z(:, pair) J ---------------------------------------------------------------------------------------------
 constexpr int R_BM = 64, R_BK = 8, R_LDA = R_BM + 2, R_LDB = JP + 2, R_STAGES = 5, R_THREADS = 128;
 constexpr int R_ASTAGE = R_BK * R_LDA;                              // complex elements per stage
@@ -257,17 +360,30 @@ __global__ void __launch_bounds__(R_THREADS, 2) jacobi_rot64_kernel(const cplx* 
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int m = rb * R_BM + wm * 32 + i * 8 + g;
+        if (UPDATE) {
+          // read-modify-write: all eight loads of this row first (one L2 round trip per i, not one per element -- ncu showed the
+          // element-by-element form stalled on the long scoreboard with the DMMA pipe 26 % active)
+          cplx old[4][2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (m < rows) {
-              cplx* p = Cb + (long long)(j * 8 + 2 * t + q) * ldz + m;
-              if (UPDATE) { const cplx o = *p; *p = make_double2(o.x - cre[i][j][q], o.y - cim[i][j][q]); }
-              else *p = make_double2(cre[i][j][q], cim[i][j][q]);
+            for (int q = 0; q < 2; ++q) old[j][q] = (m < rows) ? __ldcg(Cb + (long long)(j * 8 + 2 * t + q) * ldz + m) : make_double2(0, 0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (m < rows) Cb[(long long)(j * 8 + 2 * t + q) * ldz + m] = make_double2(old[j][q].x - cre[i][j][q], old[j][q].y - cim[i][j][q]);
+              cre[i][j][q] = 0.0; cim[i][j][q] = 0.0;
             }
-            cre[i][j][q] = 0.0; cim[i][j][q] = 0.0;
-          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (m < rows) Cb[(long long)(j * 8 + 2 * t + q) * ldz + m] = make_double2(cre[i][j][q], cim[i][j][q]);
+              cre[i][j][q] = 0.0; cim[i][j][q] = 0.0;
+            }
+        }
       }
     }
   }
@@ -328,6 +444,23 @@ void jacobi_update64(const cplx* A, long long lda, const int* ptab, cplx* T, lon
   const int per_tile = std::max(1, std::min(nrb, (int)((2 * sm_count() + items - 1) / items)));
   jacobi_rot64_kernel<true><<<dim3(per_tile, (unsigned)items), R_THREADS, R_SMEM, s>>>(A, lda, ptab, 2, ntiles, T, ldt, rows, ttab, C, ldc, (long long)JP * ldc, cstride,
                                                                                           nullptr);
+  TN_CUDA(cudaGetLastError());
+  count_launch(1);
+}
+
+// Projection coefficients C_b(:, tile i) = P_b^H T_b(:, tile i) (64 x 64 each; tables and strides as jacobi_update64).  C must be zero on
+// entry when the k range is split (contributions are added with red.global.add.f64).
+void jacobi_cross64(const cplx* A, long long lda, const int* ptab, const cplx* T, long long ldt, int rows, const int* ttab, int nprob, int ntiles,
+                    cplx* C, long long ldc, long long cstride, int max_split, cudaStream_t s) {
+  const long long items = (long long)nprob * ntiles;
+  if (items <= 0 || rows <= 0) return;
+  TN_CHECK(items <= 65535, "jacobi_cross64: too many tiles");
+  static DeviceOnce cfg;
+  cfg.run([&] { TN_CUDA(cudaFuncSetAttribute(jacobi_cross64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM)); });
+  int ksplit = std::max(1, std::min(std::min(max_split, rows / 64), (int)((3 * sm_count()) / items)));
+  int kchunk = ((rows + ksplit - 1) / ksplit + X_BK - 1) / X_BK * X_BK;
+  ksplit = (rows + kchunk - 1) / kchunk;
+  jacobi_cross64_kernel<<<dim3(ksplit, (unsigned)items), X_THREADS, X_SMEM, s>>>(A, lda, ptab, T, ldt, rows, kchunk, ttab, ntiles, C, ldc, cstride, ksplit > 1 ? 1 : 0);
   TN_CUDA(cudaGetLastError());
   count_launch(1);
 }

@@ -1310,6 +1310,12 @@ static bool jgemm_enabled() {
   return v == 1;
 }
 
+static bool cross_enabled() {       // TN_SVD_CROSS=0: projection coefficients of the QR through the general GEMM (A/B runs)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_SVD_CROSS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static void launch_1d(long long total, int& blocks) { blocks = (int)std::max<long long>(1, std::min<long long>(148 * 8, (total + 255) / 256)); }
 
 // Optional phase timing (TN_SVD_PROFILE=1): CUDA events at the phase boundaries, summed per factorisation and printed
@@ -1694,9 +1700,12 @@ static void bgs_pass(SvdWork& w, cplx* Q, long long ldq, int rows, int npad, cpl
       csplit = (rows + cchunk - 1) / cchunk;
       // split-K contributions go straight into the block row of R (zeroed by the memset above) with red.global.add.f64
       cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
-      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
-      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
-      zgemm_auto(c, s);
+      if (ttab && cross_enabled()) jacobi_cross64(Q, ldq, ptab + 2 * pk, Q, ldq, rows, ttab + trail_offset(1, npanels, pk), 1, nt / JP, Rrow, npad, 0, std::min(16, max_split()), s);
+      else {
+        GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
+        c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
+        zgemm_auto(c, s);
+      }
       // T <- T - P C
       if (ttab) jacobi_update64(Q, ldq, ptab + 2 * pk, Q, ldq, rows, ttab + trail_offset(1, npanels, pk), 1, nt / JP, Rrow, npad, 0, s);
       else zgemm_auto(gd(rows, nt, JP, P, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad), 0, T, idx1(1), idx1(ldq), -1.0, 1.0), s);
@@ -2277,10 +2286,14 @@ static void bgs_pass_b(SvdBatch& w, cplx* Q, long long ldq, int rows, int npad, 
       int cchunk = ((rows + csplit - 1) / csplit + 7) / 8 * 8;
       csplit = (rows + cchunk - 1) / cchunk;
       cplx* Rrow = R + (long long)pk * JP + (long long)(pk + 1) * JP * npad;
-      GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
-      c.batch = B; c.bsA = qs; c.bsB = qs; c.bsC = rs;
-      c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
-      zgemm_auto(c, s);
+      if (ttab && cross_enabled() && (long long)B * (nt / JP) <= 65535) {
+        jacobi_cross64(Q, ldq, ptab + (size_t)pk * B * 2, Q, ldq, rows, ttab + trail_offset(B, npanels, pk), B, nt / JP, Rrow, npad, rs, std::min(16, max_split()), s);
+      } else {
+        GemmDesc c = gd(JP, nt, rows, P, idx1(ldq), idx1(1), 1, T, idx1(1), idx1(ldq), 0, Rrow, idx1(1), idx1(npad));
+        c.batch = B; c.bsA = qs; c.bsB = qs; c.bsC = rs;
+        c.ksplit = csplit; c.kchunk = cchunk; c.ssC = 0; c.atomic_c = 1;
+        zgemm_auto(c, s);
+      }
       if (ttab && (long long)B * (nt / JP) <= 65535) {
         jacobi_update64(Q, ldq, ptab + (size_t)pk * B * 2, Q, ldq, rows, ttab + trail_offset(B, npanels, pk), B, nt / JP, Rrow, npad, rs, s);
       } else {

@@ -126,6 +126,9 @@ void jacobi_rot64(cplx* Z, long long ldz, int rows, const int* tab, int npairs, 
 // tile (b, i) = column blocks ttab[2 (b ntiles + i)], .. + 1 of T; C_b = C + cstride b, 64 x 64 ntiles coefficients, leading dimension ldc)
 void jacobi_update64(const cplx* A, long long lda, const int* ptab, cplx* T, long long ldt, int rows, const int* ttab, int nprob, int ntiles,
                      const cplx* C, long long ldc, long long cstride, cudaStream_t s);
+// C_b(:, tile i) = P_b^H T_b(:, tile i): the projection coefficients in front of jacobi_update64 (same tables / strides; C zeroed by the caller)
+void jacobi_cross64(const cplx* A, long long lda, const int* ptab, const cplx* T, long long ldt, int rows, const int* ttab, int nprob, int ntiles,
+                    cplx* C, long long ldc, long long cstride, int max_split, cudaStream_t s);
 void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn
