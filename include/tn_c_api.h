@@ -114,6 +114,13 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
                             const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out);
 
+/* The counter-based generator of QJMC throughput runs (uniforms == NULL in tn_qjmc_run / tn_qjmc_ensemble): Philox4x32-10 with key = seed and
+ * counter = (trajectory, step, slot); tn_qjmc_uniform is the [0, 1) uniform the drivers draw for (seed, trajectory, step, slot) -- the
+ * replacement of `rand()` in qjmc.jl:64,93-112 (Julia's global RNG cannot be reproduced; parity runs pass host-supplied uniforms instead).
+ * Pure host functions (no device needed). */
+int32_t tn_philox4x32_10(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
+int32_t tn_qjmc_uniform(uint64_t seed, uint64_t trajectory, uint64_t step, uint64_t slot, double* out);
+
 /* tuning switch (process-wide): 1 = QR-preconditioned Jacobi (default), 0 = plain Jacobi */
 int32_t tn_svd_set_precond(int32_t mode);
 

@@ -304,6 +304,13 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 
 int32_t tn_svd_set_precond(int32_t mode) { return guard([&] { svd_set_precond(mode); }); }
 
+int32_t tn_philox4x32_10(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+  return guard([&] { TN_CHECK(ctr4 && key2 && out4, "tn_philox4x32_10: null pointer"); philox4x32_10(ctr4, key2, out4); });
+}
+int32_t tn_qjmc_uniform(uint64_t seed, uint64_t trajectory, uint64_t step, uint64_t slot, double* out) {
+  return guard([&] { TN_CHECK(out, "tn_qjmc_uniform: null pointer"); *out = counter_uniform(seed, trajectory, step, slot); });
+}
+
 int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
                             const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out) {
   return guard([&] { TN_CHECK(ctx && Z && pairs && J && G_out && Z_out, "tn_jacobi_pair_pass: null pointer"); use_device(ctx);

@@ -153,4 +153,8 @@ IMps* imps_create(Ctx* c, int d, int L, const long long* dims, const cplx* const
 void imps_free(IMps* m);
 void itebd_apply_gate2(IMps* m, const cplx* gate_dev, Trunc tr);
 
+// tn_qjmc.cu: counter-based uniforms of the throughput runs (Philox4x32-10)
+void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double counter_uniform(uint64_t seed, uint64_t traj, uint64_t step, uint64_t slot);
+
 }  // namespace tn

@@ -8,13 +8,28 @@
 
 namespace tn {
 
-// counter-based generator keyed by (seed, trajectory, step, slot): splitmix64 finaliser
-static double counter_uniform(uint64_t seed, uint64_t traj, uint64_t step, uint64_t slot) {
-  uint64_t z = seed * 0x9E3779B97F4A7C15ull + traj * 0xBF58476D1CE4E5B9ull + step * 0x94D049BB133111EBull + slot * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+// Counter-based generator for throughput runs: Philox4x32-10 (Salmon et al., SC'11; the generator behind cuRAND's Philox and
+// Random123), key = seed, counter = (trajectory, step, slot).  Every (seed, trajectory, step, slot) has its own uniform, independent of how
+// trajectories are dealt to GPUs, worker threads or batching rounds.  Known-answer vectors: tests/test_cabi.py.
+void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// uniform in [0, 1) with 53 random bits; step < 2^30 and slot < 4 share one counter word
+double counter_uniform(uint64_t seed, uint64_t traj, uint64_t step, uint64_t slot) {
+  const uint32_t ctr[4] = {(uint32_t)traj, (uint32_t)(traj >> 32), (uint32_t)step, (uint32_t)((step >> 32) << 2 | (slot & 3))};
+  const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t o[4];
+  philox4x32_10(ctr, key, o);
+  const uint64_t bits = ((uint64_t)o[0] << 21) ^ ((uint64_t)o[1] >> 11);      // 32 + 21 = 53 bits
+  return (double)bits * (1.0 / 9007199254740992.0);
 }
 
 int qjmc_run(Mps* psi, Gates* gates, int njump, const int* jump_sites, const cplx* jump_ops, const double* jump_coeffs,

@@ -68,3 +68,39 @@ def test_null_handles_are_errors_not_crashes():
     # the sharded matvec validates its device list before touching CUDA
     h = C.c_void_p()
     assert lib.tn_heff_sharded_create(0, None, 4, 4, 2, 3, 3, 3, None, None, None, None, _lib.tn_cplx(1.0, 0.0), C.byref(h)) != 0
+
+
+def test_philox_known_answer_vectors_and_uniform_statistics():
+    """The counter-based generator of the QJMC throughput runs (csrc/tn_qjmc.cu) is Philox4x32-10: the three Random123
+    known-answer vectors, and the [0, 1) uniforms drawn for (seed, trajectory, step, slot): 53-bit resolution, mean / variance / a
+    64-bin chi-square within sampling error, no correlation between neighbouring trajectories, steps or slots.  Host functions: no GPU."""
+    import ctypes as C
+    import numpy as np
+    import tnb200
+    lib = tnb200.load()
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        c, k, o = (C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), (C.c_uint32 * 4)()
+        assert lib.tn_philox4x32_10(c, k, o) == 0
+        assert list(o) == want
+
+    def u(seed, traj, step, slot):
+        out = C.c_double()
+        assert lib.tn_qjmc_uniform(seed, traj, step, slot, C.byref(out)) == 0
+        return out.value
+    x = np.array([[[u(7, t, s, sl) for sl in range(3)] for s in range(40)] for t in range(200)])      # 24 000 uniforms
+    assert x.min() >= 0.0 and x.max() < 1.0
+    n = x.size
+    assert abs(x.mean() - 0.5) < 5 * np.sqrt(1 / 12 / n)
+    assert abs(x.var() - 1 / 12) < 5 * np.sqrt(1 / 180 / n)
+    hist = np.bincount((x.reshape(-1) * 64).astype(int), minlength=64)
+    chi2 = float(np.sum((hist - n / 64) ** 2 / (n / 64)))
+    assert chi2 < 63 + 5 * np.sqrt(2 * 63), chi2
+    for a, b in ((x[:-1], x[1:]), (x[:, :-1], x[:, 1:]), (x[:, :, :-1], x[:, :, 1:])):
+        r = np.corrcoef(a.reshape(-1), b.reshape(-1))[0, 1]
+        assert abs(r) < 5 / np.sqrt(a.size), r
+    assert u(7, 3, 5, 1) == u(7, 3, 5, 1) and u(7, 3, 5, 1) != u(8, 3, 5, 1)       # a pure function of its arguments, keyed by the seed
+    assert len({u(1, t, 0, 0) for t in range(1000)}) == 1000
+    assert any((u(1, t, 0, 0) * 2 ** 53) % 2 == 1 for t in range(64))             # the lowest of the 53 bits is in use
