@@ -789,13 +789,13 @@ int32_t tn_qjmc_ensemble(int32_t device, int32_t nworkers, int32_t ntraj, const 
     // trajectory-steps/s and 11x fewer launches, profiles/r02_first_run_qjmc_batching_and_sharded1.jsonl); TN_QJMC_BATCH=0
     // restores the independent multi-stream workers.
     const char* benv = getenv("TN_QJMC_BATCH");
-    // The workers are split into groups with one batcher each (default 2 groups from 16 workers on, TN_QJMC_GROUPS): while one group's
+    // The workers are split into groups with one batcher each (default 2 groups from 16 workers on, 4 from 64 on, TN_QJMC_GROUPS): while one group's
     // round sits in its latency-bound phases (pair EVD, panel Cholesky) the other group's GEMMs fill the SMs -- the only overlap
     // available to a Jacobi step, whose own phases depend on each other.
     int ngroups = 1;
     if (!(benv && benv[0] == '0') && nw > 1) {
       const char* genv = getenv("TN_QJMC_GROUPS");
-      ngroups = genv ? std::max(1, atoi(genv)) : (nw >= 16 ? 2 : 1);
+      ngroups = genv ? std::max(1, atoi(genv)) : (nw >= 64 ? 4 : (nw >= 16 ? 2 : 1));   // 64 workers: 4.5 (2 groups) -> 5.0 (4) trajectory-steps/s at C4
       ngroups = std::min(ngroups, nw / 2);
       ngroups = std::max(ngroups, 1);
     }
