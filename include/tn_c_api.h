@@ -114,6 +114,11 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
                             const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out);
 
+/* The pair schedule of the Jacobi sweeps for `nblocks` 32-column blocks in `groups` concurrent groups (csrc/tn_svd.cu "Split schedule"), for
+ * inspection: (phase, task, step, p, q) per pair into out5 (5 ints per pair, `capacity` pairs); *npairs_out = nblocks (nblocks - 1) / 2, or 0
+ * when this block count keeps the circle method.  Tasks of one phase run on separate streams and must own disjoint blocks.  Host function. */
+int32_t tn_svd_split_schedule(int32_t nblocks, int32_t groups, int32_t* out5, int64_t capacity, int64_t* npairs_out);
+
 /* The counter-based generator of QJMC throughput runs (uniforms == NULL in tn_qjmc_run / tn_qjmc_ensemble): Philox4x32-10 with key = seed and
  * counter = (trajectory, step, slot); tn_qjmc_uniform is the [0, 1) uniform the drivers draw for (seed, trajectory, step, slot) -- the
  * replacement of `rand()` in qjmc.jl:64,93-112 (Julia's global RNG cannot be reproduced; parity runs pass host-supplied uniforms instead).

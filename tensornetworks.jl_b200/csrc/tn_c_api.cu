@@ -304,6 +304,13 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 
 int32_t tn_svd_set_precond(int32_t mode) { return guard([&] { svd_set_precond(mode); }); }
 
+int32_t tn_svd_split_schedule(int32_t nblocks, int32_t groups, int32_t* out5, int64_t capacity, int64_t* npairs_out) {
+  return guard([&] { TN_CHECK(out5 && npairs_out && nblocks >= 2 && nblocks <= 4096 && groups >= 1 && groups <= 4, "tn_svd_split_schedule: bad argument");
+    const long long n = svd_split_schedule_dump(nblocks, groups, out5, capacity);
+    TN_CHECK(n >= 0, "tn_svd_split_schedule: output buffer too small");
+    *npairs_out = n;
+  });
+}
 int32_t tn_philox4x32_10(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
   return guard([&] { TN_CHECK(ctr4 && key2 && out4, "tn_philox4x32_10: null pointer"); philox4x32_10(ctr4, key2, out4); });
 }

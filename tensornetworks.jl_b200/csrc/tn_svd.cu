@@ -1434,10 +1434,15 @@ static SplitSched* split_schedule(SvdWork& w, int nb, int groups, cudaStream_t s
   w.split = sc;
   std::vector<int> all(nb);
   for (int i = 0; i < nb; ++i) all[i] = i;
-  Phases ph = expand_rr(all, groups);
-  int depth = 0; size_t maxtasks = 0;
-  for (auto& p : ph) { size_t d = 0; for (auto& t : p) d = std::max(d, t.size()); depth += (int)d; maxtasks = std::max(maxtasks, p.size()); }
-  if (depth != nb - 1 || maxtasks < 2 || maxtasks > 4) return nullptr;       // phases stays empty: "no split schedule for this nb"
+  Phases ph;
+  bool ok = false;
+  for (int g = groups; g >= 2 && !ok; g /= 2) {       // e.g. 36 blocks: quarters of 9 need byes (more steps), halves of 18 do not
+    ph = expand_rr(all, g);
+    int depth = 0; size_t maxtasks = 0;
+    for (auto& p : ph) { size_t d = 0; for (auto& t : p) d = std::max(d, t.size()); depth += (int)d; maxtasks = std::max(maxtasks, p.size()); }
+    ok = depth == nb - 1 && maxtasks >= 2 && maxtasks <= 4;
+  }
+  if (!ok) return nullptr;       // phases stays empty: "no split schedule for this nb"
   for (auto& p : ph) {
     SplitSched::Phase P;
     int slot = 0;
@@ -1456,7 +1461,7 @@ static SplitSched* split_schedule(SvdWork& w, int nb, int groups, cudaStream_t s
     if (slot > nb / 2) { sc->phases.clear(); sc->host.clear(); return nullptr; }   // would not fit the G / J / skip buffers of a circle-method step
     sc->phases.push_back(P);
   }
-  sc->depth = depth;
+  sc->depth = nb - 1;
   TN_CUDA(cudaMalloc((void**)&sc->dev, sc->host.size() * sizeof(int)));
   TN_CUDA(cudaMemcpyAsync(sc->dev, sc->host.data(), sc->host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
   TN_CUDA(cudaStreamSynchronize(s));
@@ -1467,6 +1472,35 @@ static SplitSched* split_schedule(SvdWork& w, int nb, int groups, cudaStream_t s
   if (!w.ev_fork) TN_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
   return sc;
 }
+// Host-side view of the split schedule for tests: writes (phase, task, step, p, q) per pair into out5 (capacity cap5 pairs) and returns the
+// number of pairs, 0 when this block count has no split schedule (the sweeps then use the circle method), -1 when out5 is too small.
+long long svd_split_schedule_dump(int nb, int groups, int* out5, long long cap5) {
+  std::vector<int> all(nb);
+  for (int i = 0; i < nb; ++i) all[i] = i;
+  Phases ph = expand_rr(all, groups);
+  int depth = 0; size_t maxtasks = 0;
+  for (auto& p : ph) { size_t d = 0; for (auto& t : p) d = std::max(d, t.size()); depth += (int)d; maxtasks = std::max(maxtasks, p.size()); }
+  if (depth != nb - 1 || maxtasks < 2 || maxtasks > 4) return 0;
+  long long n = 0;
+  for (size_t a = 0; a < ph.size(); ++a) {
+    int slot = 0;
+    for (size_t b = 0; b < ph[a].size(); ++b) {
+      int mx = 0;
+      for (size_t c = 0; c < ph[a][b].size(); ++c) {
+        mx = std::max(mx, (int)ph[a][b][c].size());
+        for (auto& pq : ph[a][b][c]) {
+          if (n >= cap5) return -1;
+          int* o = out5 + 5 * n++;
+          o[0] = (int)a; o[1] = (int)b; o[2] = (int)c; o[3] = pq.first; o[4] = pq.second;
+        }
+      }
+      slot += mx;
+    }
+    if (slot > nb / 2) return 0;
+  }
+  return n;
+}
+
 // number of concurrent pair groups (TN_SVD_SPLIT; 1 = circle method on one stream) and the smallest block count that is split
 static int split_groups() {
   static int v = -1;

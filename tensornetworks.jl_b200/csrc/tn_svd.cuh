@@ -129,6 +129,7 @@ void jacobi_update64(const cplx* A, long long lda, const int* ptab, cplx* T, lon
 // C_b(:, tile i) = P_b^H T_b(:, tile i): the projection coefficients in front of jacobi_update64 (same tables / strides; C zeroed by the caller)
 void jacobi_cross64(const cplx* A, long long lda, const int* ptab, const cplx* T, long long ldt, int rows, const int* ttab, int nprob, int ntiles,
                     cplx* C, long long ldc, long long cstride, int max_split, cudaStream_t s);
+long long svd_split_schedule_dump(int nb, int groups, int* out5, long long cap5);   // tests: the split pair schedule of the Jacobi sweeps
 void svd_set_precond(int mode);   // 1 (default): two-step QR preconditioning before the Jacobi sweeps; 0: plain Jacobi
 
 }  // namespace tn

@@ -104,3 +104,45 @@ def test_philox_known_answer_vectors_and_uniform_statistics():
     assert u(7, 3, 5, 1) == u(7, 3, 5, 1) and u(7, 3, 5, 1) != u(8, 3, 5, 1)       # a pure function of its arguments, keyed by the seed
     assert len({u(1, t, 0, 0) for t in range(1000)}) == 1000
     assert any((u(1, t, 0, 0) * 2 ** 53) % 2 == 1 for t in range(64))             # the lowest of the 53 bits is in use
+
+
+def test_split_pair_schedule_visits_every_pair_once_with_disjoint_concurrent_tasks():
+    """The Jacobi sweeps of large factorisations (>= 32 column blocks) run a pair schedule whose phases fall apart into 2 or 4 tasks on
+    separate streams (csrc/tn_svd.cu "Split schedule").  For every block count the library may see: every unordered pair of blocks exactly
+    once per sweep, the pairs of a step disjoint, the tasks of a phase on disjoint blocks (they run concurrently without ordering), and no
+    more steps than the circle method (block counts that do not halve evenly keep the circle method: npairs == 0).  Host function: no GPU."""
+    import ctypes as C
+    import numpy as np
+    import tnb200
+    lib = tnb200.load()
+    used = 0
+    for groups in (2, 4):
+        for nb in list(range(2, 71, 2)) + [96, 128, 192, 256]:
+            cap = nb * (nb - 1) // 2
+            buf = (C.c_int32 * (5 * cap))()
+            n = C.c_int64()
+            assert lib.tn_svd_split_schedule(nb, groups, buf, cap, C.byref(n)) == 0
+            if n.value == 0:
+                continue
+            used += 1
+            assert n.value == cap, (nb, groups, n.value)
+            a = np.frombuffer(buf, dtype=np.int32).reshape(cap, 5)
+            pairs = {(int(p), int(q)) for p, q in a[:, 3:]}
+            assert len(pairs) == cap and all(0 <= p < q < nb for p, q in pairs)
+            depth = 0
+            for ph in np.unique(a[:, 0]):
+                rows = a[a[:, 0] == ph]
+                blocks_of_task = []
+                for t in np.unique(rows[:, 1]):
+                    rt = rows[rows[:, 1] == t]
+                    for st in np.unique(rt[:, 2]):
+                        blk = rt[rt[:, 2] == st][:, 3:].reshape(-1)
+                        assert len(set(blk.tolist())) == len(blk), "a step must rotate disjoint pairs"
+                    blocks_of_task.append(set(rt[:, 3:].reshape(-1).tolist()))
+                for i in range(len(blocks_of_task)):
+                    for j in range(i):
+                        assert not (blocks_of_task[i] & blocks_of_task[j]), "concurrent tasks must own disjoint blocks"
+                assert 2 <= len(blocks_of_task) <= groups
+                depth += max(int(rows[rows[:, 1] == t][:, 2].max()) + 1 for t in np.unique(rows[:, 1]))
+            assert depth == nb - 1
+    assert used >= 20
