@@ -414,6 +414,172 @@ __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32, MinBlocks<WARPS_M, WAR
   }
 }
 
+// ---- 128 x 32 tile fed by the bulk-copy (TMA) engine ------------------------------------------------------------------------------
+// Same tile, fragments and arithmetic as zgemm_kernel<4,1,4,4,1>, for the shapes of the two chi^3 stages of the H_eff application: full
+// tiles, m unit-stride (a k-row of the A tile is 2 KiB of contiguous memory), B either k-fast (Theta: 8 contiguous elements per column)
+// or n-fast (the right block: 32 contiguous elements per k-row).  The four warps no longer issue their own 16-byte cp.async copies: per
+// k-tile ONE warp (they take turns) arms the stage's mbarrier with the byte count and issues 16 / 40 `cp.async.bulk` copies
+// (SASS: UBLKCP) straight into the padded stage rows; consumers wait on the stage's "full" mbarrier and release it through an "empty"
+// mbarrier -- no __syncthreads, no cp.async.wait_group, no per-thread pointer walk in the k loop.
+namespace bulk {
+constexpr int BM = 128, BN = 32, LDA = BM + 2, LDBN = BN + 2;
+template <int BK_, int ST_>
+struct Cfg {        // k-tile depth and ring length: 8 x 4 stages, or 16 x 2 stages (half as many stage hand-overs per DMMA); both 2 CTAs / SM
+  static constexpr int BK = BK_, ST = ST_, LDBK = BK_ + 1;
+  static constexpr int A_STAGE = BK * LDA, B_STAGE = (BN * LDBK > BK * LDBN) ? BN * LDBK : BK * LDBN;   // complex elements, either B layout
+  static constexpr int STAGE = A_STAGE + B_STAGE;
+  static constexpr int SMEM_BYTES = ST * STAGE * 16 + 2 * ST * 8;
+  static constexpr unsigned TX_BYTES = BK * BM * 16 + BK * BN * 16;
+};
+
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(s32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(s32(b)), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+}  // namespace bulk
+
+template <bool BKFAST, int BK_, int ST_>
+__global__ void __launch_bounds__(128, 2) zgemm_bulk_kernel(const GemmDesc d) {
+  using namespace bulk;
+  using C_ = bulk::Cfg<BK_, ST_>;
+  constexpr int BK = C_::BK, ST = C_::ST, LDBK = C_::LDBK, A_STAGE = C_::A_STAGE, STAGE = C_::STAGE;
+  constexpr unsigned TX_BYTES = C_::TX_BYTES;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* S = reinterpret_cast<cplx*>(smem_raw);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + ST * STAGE * 16);
+  unsigned long long* empty = full + ST;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  int fast = blockIdx.x, slow = blockIdx.y;
+  if (d.panel > 0) raster_tile((long long)blockIdx.x + (long long)gridDim.x * blockIdx.y, (int)gridDim.x, (int)gridDim.y, d.panel, fast, slow);
+  const int m_blk = (d.swap_raster ? slow : fast) * BM, n_blk = (d.swap_raster ? fast : slow) * BN;
+  const cplx* Ag = d.A + m_blk;                                                     // am.s0 == 1
+  const cplx* Bg = BKFAST ? d.B + (long long)n_blk * d.bn.s0 : d.B + n_blk;         // k-fast: bk.s0 == 1; n-fast: bn.s0 == 1
+  const int ktiles = d.K / BK;
+  if (tid == 0) {
+    for (int s = 0; s < ST; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
+  __syncthreads();
+  // executed by all lanes of one warp: refill the stage of k-tile `tile`
+  auto issue = [&](int tile) {
+    const int s = tile % ST;
+    cplx* as = S + s * STAGE;
+    cplx* bs = as + A_STAGE;
+    if (lane == 0) {
+      if (tile >= ST) mbar_wait(empty + s, (unsigned)((tile / ST - 1) & 1));       // every warp has finished the previous use of the stage
+      mbar_expect_tx(full + s, TX_BYTES);
+    }
+    __syncwarp();
+    const long long k0 = (long long)tile * BK;
+    if (lane < BK) bulk_g2s(as + lane * LDA, Ag + (k0 + lane) * d.ak.s0, BM * 16, full + s);
+    if (BKFAST) bulk_g2s(bs + lane * LDBK, Bg + (long long)lane * d.bn.s0 + k0, BK * 16, full + s);
+    else if (lane >= BK && lane < 2 * BK) bulk_g2s(bs + (lane - BK) * LDBN, Bg + (k0 + lane - BK) * d.bk.s0, BN * 16, full + s);
+  };
+  if (warp == 0)
+    for (int tile = 0; tile < ST - 1 && tile < ktiles; ++tile) issue(tile);
+
+  double cre[4][4][2], cim[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
+  const double sa = d.conjA ? -1.0 : 1.0, sb = d.conjB ? -1.0 : 1.0;
+  const int a_frag = warp * 32 + g;
+
+  for (int kt = 0; kt < ktiles; ++kt) {
+    const int s = kt % ST;
+    mbar_wait(full + s, (unsigned)((kt / ST) & 1));
+    const cplx* as = S + s * STAGE;
+    const cplx* bs = as + A_STAGE;
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double ar[4], ai[4], br[4], bi[4], nbi[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { cplx v = as[(kk + t) * LDA + a_frag + i * 8]; ar[i] = v.x; ai[i] = sa * v.y; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        cplx v = BKFAST ? bs[(g + j * 8) * LDBK + kk + t] : bs[(kk + t) * LDBN + g + j * 8];
+        br[j] = v.x; bi[j] = sb * v.y; nbi[j] = -bi[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], ar[i], br[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], ar[i], bi[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cre[i][j][0], cre[i][j][1], ai[i], nbi[j]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma(cim[i][j][0], cim[i][j][1], ai[i], br[j]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    const int nt = kt + ST - 1;
+    if (nt < ktiles && warp == (kt & 3)) issue(nt);
+    static_assert(2 * BK <= 32, "one warp issues the A rows and the n-fast B rows of a stage");
+  }
+
+  // epilogue: C = alpha*acc + beta*C, strided store (as gemm_tile)
+  cplx* __restrict__ Cb = d.C;
+  const bool has_beta = (d.beta.x != 0.0 || d.beta.y != 0.0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m_blk + warp * 32 + i * 8 + g;
+    const long long moff = idx_off_t(d.cm, m, 0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int n = n_blk + j * 8 + 2 * t + q;
+        const double xr = cre[i][j][q], xi = cim[i][j][q];
+        cplx o;
+        o.x = d.alpha.x * xr - d.alpha.y * xi;
+        o.y = d.alpha.x * xi + d.alpha.y * xr;
+        cplx* p = Cb + moff + idx_off_t(d.cn, n, 0);
+        if (has_beta) { const cplx c = *p; o.x += d.beta.x * c.x - d.beta.y * c.y; o.y += d.beta.x * c.y + d.beta.y * c.x; }
+        *p = o;
+      }
+  }
+}
+
+// TN_GEMM_BULK=1 / 2 moves the chi^3 stages to the bulk-copy kernel (8-deep k-tiles x 4 stages / 16-deep x 2 stages); default: cp.async kernel
+static int bulk_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TN_GEMM_BULK"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static bool single_level(const Idx2& ix, int extent) { return ix.tab == nullptr && (ix.n0 >= extent || ix.s1 == (long long)ix.n0 * ix.s0); }
+// 0: not applicable, 1: B k-fast, 2: B n-fast
+static int bulk_mode(const GemmDesc& d) {
+  using namespace bulk;
+  const int BK = bulk_variant() == 2 ? 16 : 8, ST = bulk_variant() == 2 ? 2 : 4;
+  if (bulk_variant() <= 0 || d.batch != 1 || d.ksplit != 1 || d.atomic_c || d.skip != nullptr) return 0;
+  if (d.M % BM || d.N % BN || d.K % BK || d.K < BK * ST) return 0;
+  if (!single_level(d.am, d.M) || d.am.s0 != 1 || !single_level(d.ak, d.K) || !single_level(d.bk, d.K) || !single_level(d.bn, d.N)) return 0;
+  if (d.cm.tab || d.cn.tab || d.C == d.A || d.C == d.B) return 0;
+  if (d.bk.s0 == 1 && d.bn.s0 != 1) return 1;
+  if (d.bn.s0 == 1) return 2;
+  return 0;
+}
+
 template <int WARPS_M, int WARPS_N, int TM, int TN, int KMODE>
 static void launch2(const GemmDesc& d, cudaStream_t stream) {
   using Cfg = TileCfg<WARPS_M, WARPS_N, TM, TN>;
@@ -492,6 +658,28 @@ static void launch2(const GemmDesc& d, cudaStream_t stream) {
   }
   dim3 grid(dd.swap_raster ? tn_ : tm, dd.swap_raster ? tm : tn_, d.batch * d.ksplit);
   TN_CHECK(grid.y <= 65535 && grid.z <= 65535, "zgemm: grid too large");
+  if (WARPS_M == 4 && WARPS_N == 1 && TM == 4 && TN == 4 && KMODE == 1) {
+    const int mode = bulk_mode(dd);
+    if (mode != 0) {
+      static DeviceOnce bcfg;
+      bcfg.run([&] {
+        TN_CUDA(cudaFuncSetAttribute(zgemm_bulk_kernel<true, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk::Cfg<8, 4>::SMEM_BYTES));
+        TN_CUDA(cudaFuncSetAttribute(zgemm_bulk_kernel<false, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk::Cfg<8, 4>::SMEM_BYTES));
+        TN_CUDA(cudaFuncSetAttribute(zgemm_bulk_kernel<true, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk::Cfg<16, 2>::SMEM_BYTES));
+        TN_CUDA(cudaFuncSetAttribute(zgemm_bulk_kernel<false, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bulk::Cfg<16, 2>::SMEM_BYTES));
+      });
+      if (bulk_variant() == 2) {
+        if (mode == 1) zgemm_bulk_kernel<true, 16, 2><<<grid, 128, bulk::Cfg<16, 2>::SMEM_BYTES, stream>>>(dd);
+        else zgemm_bulk_kernel<false, 16, 2><<<grid, 128, bulk::Cfg<16, 2>::SMEM_BYTES, stream>>>(dd);
+      } else {
+        if (mode == 1) zgemm_bulk_kernel<true, 8, 4><<<grid, 128, bulk::Cfg<8, 4>::SMEM_BYTES, stream>>>(dd);
+        else zgemm_bulk_kernel<false, 8, 4><<<grid, 128, bulk::Cfg<8, 4>::SMEM_BYTES, stream>>>(dd);
+      }
+      TN_CUDA(cudaGetLastError());
+      count_launch(1);
+      return;
+    }
+  }
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(dd);
   TN_CUDA(cudaGetLastError());
   count_launch(1);

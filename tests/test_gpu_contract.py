@@ -82,3 +82,34 @@ def test_two_level_k_blocks_aligned_to_tile():
         C = tnb200.contract_strided(M, N, k0 * k1, np.asfortranarray(A).reshape(-1, order='F'), (BIG, k0, 0), (k0, 1, k0 * M), 0,
                                     np.asfortranarray(B).reshape(-1, order='F'), (k0, N, N * k0), (BIG, 1, 0), 0, M * N, (BIG, 1, 0), (BIG, M, 0))
         assert relerr(C.reshape(M, N, order='F'), want) < 1e-13, (k0, k1, M, N)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_bulk_copy_kernel_variants_match_numpy(variant):
+    """The bulk-copy (TMA engine: cp.async.bulk + mbarrier) variants of the 128 x 32 kernel -- an experiment that is off by default
+    (TN_GEMM_BULK=1: 8-deep k-tiles x 4 stages, 2: 16-deep x 2 stages) -- on shapes that take them: full tiles, exactly one
+    wave of CTAs, B k-fast and B n-fast, with conjugation and alpha.  The switch is read once per process, hence the subprocess."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path[:0] = [%r, %r]
+        import tnb200
+        from gpu_util import crandn, relerr
+        BIG = 1 << 40
+        rng = np.random.default_rng(11)
+        M, N, K = 128 * 37, 32 * 8, 96
+        A = crandn(rng, M, K)
+        Bk = crandn(rng, K, N)                   # k-fast: column-major K x N
+        C = tnb200.contract_strided(M, N, K, np.asfortranarray(A).reshape(-1, order='F'), (BIG, 1, 0), (BIG, M, 0), 0,
+                                    np.asfortranarray(Bk).reshape(-1, order='F'), (BIG, 1, 0), (BIG, K, 0), 1, M * N, (BIG, 1, 0), (BIG, M, 0), alpha=0.5 - 2j)
+        assert relerr(C.reshape(M, N, order='F'), (0.5 - 2j) * (A @ Bk.conj())) < 1e-13
+        Bn = crandn(rng, N, K)                   # n-fast: column-major N x K, used as its transpose
+        C = tnb200.contract_strided(M, N, K, np.asfortranarray(A).reshape(-1, order='F'), (BIG, 1, 0), (BIG, M, 0), 0,
+                                    np.asfortranarray(Bn).reshape(-1, order='F'), (BIG, N, 0), (BIG, 1, 0), 0, M * N, (BIG, 1, 0), (BIG, M, 0))
+        assert relerr(C.reshape(M, N, order='F'), A @ Bn.T) < 1e-13
+        print("ok", tnb200.Context.default().counters()["launches"])
+    ''') % (os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tensornetworks.jl_b200"), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TN_GEMM_BULK=str(variant))
+    env["PYTHONPATH"] = os.path.dirname(os.path.dirname(os.path.abspath(__file__))) + os.pathsep + env.get("PYTHONPATH", "")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
