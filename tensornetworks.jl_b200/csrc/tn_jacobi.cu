@@ -34,6 +34,7 @@ __device__ __forceinline__ void cpa16(void* smem, const void* gmem, bool pred) {
 __device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+__device__ __forceinline__ double neg_bits(double x) { return __longlong_as_double(__double_as_longlong(x) ^ (long long)0x8000000000000000ull); }   // integer pipe, not FP64
 __device__ __forceinline__ void dmma2(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(G_THREADS, 3) jacobi_gram64_kernel(const cplx*
 #pragma unroll
       for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
-        for (int d = 0; d < 4; ++d) dmma2(im[ii * 4 + d], -fi[ii], fr[ii + d]);
-      dmma2(im[8], -fi[5], fr[6]);
+        for (int d = 0; d < 4; ++d) dmma2(im[ii * 4 + d], neg_bits(fi[ii]), fr[ii + d]);
+      dmma2(im[8], neg_bits(fi[5]), fr[6]);
     }
   }
   cpa_wait<0>();
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(X_THREADS, 3) jacobi_cross64_kernel(const cplx
       const cplx* row = ps + (kk + t) * X_LD;
       double ar[2], ai[2], nai[2], br[8], bi[8];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) { cplx v = row[a_frag + 8 * i]; ar[i] = v.x; ai[i] = v.y; nai[i] = -v.y; }
+      for (int i = 0; i < 2; ++i) { cplx v = row[a_frag + 8 * i]; ar[i] = v.x; ai[i] = v.y; nai[i] = neg_bits(v.y); }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { cplx v = row[b_frag + 8 * j]; br[j] = v.x; bi[j] = v.y; }
       // C_ij += conj(a) b :  re += ar br + ai bi,  im += ar bi - ai br
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(R_THREADS, 2) jacobi_rot64_kernel(const cplx* 
 #pragma unroll
       for (int i = 0; i < 4; ++i) { cplx x = as[(kk + t) * R_LDA + a_frag + i * 8]; ar[i] = x.x; ai[i] = x.y; }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { cplx x = bs[(kk + t) * R_LDB + b_frag + j * 8]; br[j] = x.x; bi[j] = x.y; nbi[j] = -x.y; }
+      for (int j = 0; j < 4; ++j) { cplx x = bs[(kk + t) * R_LDB + b_frag + j * 8]; br[j] = x.x; bi[j] = x.y; nbi[j] = neg_bits(x.y); }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll

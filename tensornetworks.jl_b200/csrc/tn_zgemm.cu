@@ -39,6 +39,10 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// Sign flips of fragment registers as integer operations on the sign bit: a DMUL / DADD would occupy the FP64 pipe the DMMAs run on
+// (12 of them per 64 DMMA in the k loop).  flip = 0 or 0x8000000000000000.
+__device__ __forceinline__ double sign_xor(double x, unsigned long long flip) { return __longlong_as_double(__double_as_longlong(x) ^ (long long)flip); }
+
 __device__ __forceinline__ long long idx_off(const Idx2& ix, int i, int batch) {
   if (i < ix.n0) return (long long)i * ix.s0;
   int i1 = i / ix.n0, i0 = i - i1 * ix.n0;
@@ -231,8 +235,8 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     cp_async_commit();
   }
 
-  const double sa = d.conjA ? -1.0 : 1.0;   // conj-on-load: flip the sign of the imaginary fragment
-  const double sb = d.conjB ? -1.0 : 1.0;
+  const unsigned long long fa = d.conjA ? 0x8000000000000000ull : 0ull;   // conj-on-load: flip the sign of the imaginary fragment
+  const unsigned long long fb = d.conjB ? 0x8000000000000000ull : 0ull, fnb = fb ^ 0x8000000000000000ull;
   const int a_frag = wm * TM * 8 + g;       // + mi*8, row (k) = t
   const int b_frag = wn * TN * 8 + g;
 
@@ -252,12 +256,12 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
 #pragma unroll
       for (int i = 0; i < TM; ++i) {
         cplx v = as[(kk + t) * LDA + a_frag + i * 8];
-        ar[i] = v.x; ai[i] = sa * v.y;
+        ar[i] = v.x; ai[i] = sign_xor(v.y, fa);
       }
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         cplx v = bs[(kk + t) * LDB + b_frag + j * 8];
-        br[j] = v.x; bi[j] = sb * v.y; nbi[j] = -bi[j];
+        br[j] = v.x; bi[j] = sign_xor(v.y, fb); nbi[j] = sign_xor(v.y, fnb);
       }
 #pragma unroll
       for (int i = 0; i < TM; ++i)
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(128, 2) zgemm_bulk_kernel(const GemmDesc d) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
-  const double sa = d.conjA ? -1.0 : 1.0, sb = d.conjB ? -1.0 : 1.0;
+  const unsigned long long fa = d.conjA ? 0x8000000000000000ull : 0ull, fb = d.conjB ? 0x8000000000000000ull : 0ull, fnb = fb ^ 0x8000000000000000ull;
   const int a_frag = warp * 32 + g;
 
   for (int kt = 0; kt < ktiles; ++kt) {
@@ -507,11 +511,11 @@ __global__ void __launch_bounds__(128, 2) zgemm_bulk_kernel(const GemmDesc d) {
     for (int kk = 0; kk < BK; kk += 4) {
       double ar[4], ai[4], br[4], bi[4], nbi[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { cplx v = as[(kk + t) * LDA + a_frag + i * 8]; ar[i] = v.x; ai[i] = sa * v.y; }
+      for (int i = 0; i < 4; ++i) { cplx v = as[(kk + t) * LDA + a_frag + i * 8]; ar[i] = v.x; ai[i] = sign_xor(v.y, fa); }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         cplx v = BKFAST ? bs[(g + j * 8) * LDBK + kk + t] : bs[(kk + t) * LDBN + g + j * 8];
-        br[j] = v.x; bi[j] = sb * v.y; nbi[j] = -bi[j];
+        br[j] = v.x; bi[j] = sign_xor(v.y, fb); nbi[j] = sign_xor(v.y, fnb);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
