@@ -741,6 +741,8 @@ void zgemm_auto(GemmDesc d, cudaStream_t stream) {
     else if (variant == 1) launch<2, 2, 4, 4>(d, stream);            // 64 x 64, 2 CTAs / SM
     else if (variant == 3) launch<2, 1, 4, 4>(d, stream);            // 64 x 32, 4 CTAs / SM
     else if (variant == 4) launch<1, 2, 4, 4>(d, stream);            // 32 x 64, 4 CTAs / SM
+    else if (variant == 5) launch<4, 2, 4, 2>(d, stream);            // 128 x 32 with 8 warps of 32 x 16: 16 warps / SM (4 per scheduler)
+    else if (variant == 6) launch<2, 4, 4, 2>(d, stream);            // 64 x 64 with 8 warps of 32 x 16: 16 warps / SM
     else launch<4, 1, 4, 4>(d, stream);                              // 128 x 32, 2 CTAs / SM
   }
 }
