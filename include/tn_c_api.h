@@ -114,6 +114,11 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 int32_t tn_jacobi_pair_pass(tn_ctx* ctx, const tn_cplx* Z, int64_t rows, int64_t ncols, const int32_t* pairs, int32_t npairs,
                             const tn_cplx* J, const int32_t* skip, tn_cplx* G_out, tn_cplx* Z_out);
 
+/* One trailing update of the block Gram-Schmidt QR inside the factorisations above, on caller data (csrc/tn_jacobi.cu: jacobi_cross64 + the rank-64
+ * update form of the rotation kernel).  Q: rows x ncols column-major on the host (ncols a multiple of 64); P = the 64 columns of panel `panel`,
+ * T = all columns to its right.  C_out (64 x (ncols - 64 (panel + 1)), leading dimension 64) = P^H T; Q_out = Q with T replaced by T - P C. */
+int32_t tn_jacobi_qr_update_pass(tn_ctx* ctx, const tn_cplx* Q, int64_t rows, int64_t ncols, int32_t panel, tn_cplx* C_out, tn_cplx* Q_out);
+
 /* The pair schedule of the Jacobi sweeps for `nblocks` 32-column blocks in `groups` concurrent groups (csrc/tn_svd.cu "Split schedule"), for
  * inspection: (phase, task, step, p, q) per pair into out5 (5 ints per pair, `capacity` pairs); *npairs_out = nblocks (nblocks - 1) / 2, or 0
  * when this block count keeps the circle method.  Tasks of one phase run on separate streams and must own disjoint blocks.  Host function. */

@@ -304,6 +304,28 @@ int32_t tn_svd_trunc_batched(tn_ctx* ctx, int32_t B, const tn_cplx* mats, int64_
 
 int32_t tn_svd_set_precond(int32_t mode) { return guard([&] { svd_set_precond(mode); }); }
 
+int32_t tn_jacobi_qr_update_pass(tn_ctx* ctx, const tn_cplx* Q, int64_t rows, int64_t ncols, int32_t panel, tn_cplx* C_out, tn_cplx* Q_out) {
+  return guard([&] { TN_CHECK(ctx && Q && C_out && Q_out, "tn_jacobi_qr_update_pass: null pointer"); use_device(ctx);
+    TN_CHECK(rows >= 1 && rows < (1ll << 30) && ncols >= 128 && ncols % 64 == 0 && ncols < (1ll << 20), "tn_jacobi_qr_update_pass: bad shape");
+    const int npanels = (int)(ncols / 64), ntiles = npanels - panel - 1;
+    TN_CHECK(panel >= 0 && ntiles >= 1, "tn_jacobi_qr_update_pass: the panel needs at least one trailing tile");
+    Ctx* c = &ctx->c; cudaStream_t s = c->stream;
+    const size_t qe = (size_t)rows * ncols, ce = (size_t)64 * 64 * ntiles;
+    cplx* dQ = c->scratch[0].get(qe, s);
+    cplx* dC = c->scratch[1].get(ce, s);
+    int* dI = reinterpret_cast<int*>(c->scratch[3].get((size_t)npanels, s));      // 16 B per entry: 2 ints per panel fit twice over
+    std::vector<int> tab((size_t)2 * npanels);
+    for (int i = 0; i < 2 * npanels; ++i) tab[i] = i;                              // panel p = column blocks (2p, 2p + 1)
+    TN_CUDA(cudaMemcpyAsync(dQ, Q, qe * sizeof(cplx), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemcpyAsync(dI, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    TN_CUDA(cudaMemsetAsync(dC, 0, ce * sizeof(cplx), s));
+    jacobi_cross64(dQ, rows, dI + 2 * panel, dQ, rows, (int)rows, dI + 2 * (panel + 1), 1, ntiles, dC, 64, 0, 16, s);
+    jacobi_update64(dQ, rows, dI + 2 * panel, dQ, rows, (int)rows, dI + 2 * (panel + 1), 1, ntiles, dC, 64, 0, s);
+    TN_CUDA(cudaMemcpyAsync(C_out, dC, ce * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    TN_CUDA(cudaMemcpyAsync(Q_out, dQ, qe * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+    c->sync();
+  });
+}
 int32_t tn_svd_split_schedule(int32_t nblocks, int32_t groups, int32_t* out5, int64_t capacity, int64_t* npairs_out) {
   return guard([&] { TN_CHECK(out5 && npairs_out && nblocks >= 2 && nblocks <= 4096 && groups >= 1 && groups <= 4, "tn_svd_split_schedule: bad argument");
     const long long n = svd_split_schedule_dump(nblocks, groups, out5, capacity);

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "tn_heff_sharded_apply": [P, P, P],
     "tn_heff_sharded_free": [P],
     "tn_svd_trunc_split": [P, P, I64, I64, tn_trunc_t, I32, P, pF64, P, pI64, pI32, I32, pF64],
+    "tn_jacobi_qr_update_pass": [P, P, I64, I64, I32, P, P],
     "tn_svd_split_schedule": [I32, I32, P, I64, P],
     "tn_philox4x32_10": [P, P, P],
     "tn_qjmc_uniform": [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)],

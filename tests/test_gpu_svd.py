@@ -166,3 +166,26 @@ def test_jacobi_pair_kernels_match_numpy(rows, ncols, npairs, with_skip):
         if skip is None or skip[p] == 0:
             want[:, cols] = P @ J[p]
     assert np.linalg.norm(Zout - want) <= 1e-13 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("rows,ncols,panel", [(64, 128, 0), (300, 256, 1), (1024, 512, 0), (2048, 1024, 5), (520, 2048, 0)])
+def test_qr_trailing_update_kernels_match_numpy(rows, ncols, panel):
+    """The projection-coefficient kernel C = P^H T and the rank-64 trailing update T -= P C of the QR phase (csrc/tn_jacobi.cu) on their
+    own: split-K with atomics and without, one to 31 trailing tiles, row counts that are / are not multiples of the tile sizes."""
+    import tnb200
+    from tnb200.api import _ptr, _f, check
+    rng = np.random.default_rng(rows + ncols + panel)
+    ctx = tnb200.Context.default()
+    Q = _f(crandn(rng, rows, ncols))
+    nt = ncols - 64 * (panel + 1)
+    Cout = np.zeros(64 * nt, dtype=np.complex128)
+    Qout = np.zeros((rows, ncols), dtype=np.complex128, order='F')
+    check(ctx.lib.tn_jacobi_qr_update_pass(ctx.h, _ptr(Q), rows, ncols, panel, _ptr(Cout), _ptr(Qout)))
+    P, T = Q[:, 64 * panel:64 * (panel + 1)], Q[:, 64 * (panel + 1):]
+    Cref = P.conj().T @ T
+    Cg = np.reshape(Cout, (64, nt), order='F')
+    assert np.linalg.norm(Cg - Cref) <= 1e-13 * np.linalg.norm(Cref)
+    want = Q.copy()
+    want[:, 64 * (panel + 1):] = T - P @ Cg
+    assert np.linalg.norm(Qout - want) <= 1e-13 * np.linalg.norm(want)
+    assert np.array_equal(Qout[:, :64 * (panel + 1)], Q[:, :64 * (panel + 1)])
