@@ -40,8 +40,8 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 // Sign flips of fragment registers as integer operations on the sign bit: a DMUL / DADD would occupy the FP64 pipe the DMMAs run on
-// (12 of them per 64 DMMA in the k loop).  flip = 0 or 0x8000000000000000.
-__device__ __forceinline__ double sign_xor(double x, unsigned long long flip) { return __longlong_as_double(__double_as_longlong(x) ^ (long long)flip); }
+// (12 of them per 64 DMMA in the k loop).  flip_hi = 0 or 0x80000000 (applied to the high word).
+__device__ __forceinline__ double sign_xor(double x, unsigned flip_hi) { return __hiloint2double(__double2hiint(x) ^ (int)flip_hi, __double2loint(x)); }
 
 __device__ __forceinline__ long long idx_off(const Idx2& ix, int i, int batch) {
   if (i < ix.n0) return (long long)i * ix.s0;
@@ -235,8 +235,8 @@ __device__ __forceinline__ void gemm_tile(const GemmDesc& d, cplx* As, cplx* Bs,
     cp_async_commit();
   }
 
-  const unsigned long long fa = d.conjA ? 0x8000000000000000ull : 0ull;   // conj-on-load: flip the sign of the imaginary fragment
-  const unsigned long long fb = d.conjB ? 0x8000000000000000ull : 0ull, fnb = fb ^ 0x8000000000000000ull;
+  const unsigned fa = d.conjA ? 0x80000000u : 0u;   // conj-on-load: flip the sign of the imaginary fragment
+  const unsigned fb = d.conjB ? 0x80000000u : 0u, fnb = fb ^ 0x80000000u;
   const int a_frag = wm * TM * 8 + g;       // + mi*8, row (k) = t
   const int b_frag = wn * TN * 8 + g;
 
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(128, 2) zgemm_bulk_kernel(const GemmDesc d) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { cre[i][j][0] = cre[i][j][1] = 0.0; cim[i][j][0] = cim[i][j][1] = 0.0; }
-  const unsigned long long fa = d.conjA ? 0x8000000000000000ull : 0ull, fb = d.conjB ? 0x8000000000000000ull : 0ull, fnb = fb ^ 0x8000000000000000ull;
+  const unsigned fa = d.conjA ? 0x80000000u : 0u, fb = d.conjB ? 0x80000000u : 0u, fnb = fb ^ 0x80000000u;
   const int a_frag = warp * 32 + g;
 
   for (int kt = 0; kt < ktiles; ++kt) {
